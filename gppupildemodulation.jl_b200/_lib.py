@@ -1,0 +1,144 @@
+"""ctypes binding of libgppd.so (include/gppd.h).  No fallback: if the shared
+library is missing or no B200 is visible, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgppd.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+OK = 0
+ONLYHIGH, FITOFFSETS, NO_RECENTER, KEEPRAW, BIG_ENDIAN = 1, 2, 4, 8, 16
+METHOD_AUTO, METHOD_DIRECT, METHOD_HARMONIC = 0, 1, 2
+INFO_STRIDE = 4
+TRACE_MAX = 160
+
+
+class Options(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("method", C.c_int32), ("maxfun", C.c_int32),
+                ("has_xinit", C.c_int32), ("xinit", C.c_double * 2),
+                ("rhobeg", C.c_double), ("rhoend", C.c_double)]
+
+
+class GppdError(RuntimeError):
+    def __init__(self, status, what, detail):
+        super().__init__(f"libgppd: {what} (status {status}){': ' + detail if detail else ''}")
+        self.status = status
+
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_i8p = C.POINTER(C.c_int8)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libgppd.so for sm_100a with nvcc (make is incremental)."""
+    subprocess.run(["make", "-C", CSRC] + ([] if verbose else ["-s"]), check=True)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises when libgppd.so has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GppdError(-1, "libgppd.so is not built", f"run `make -C {CSRC}` (needs nvcc); "
+                        "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.gppd_version.restype = C.c_int
+    L.gppd_strerror.restype = C.c_char_p
+    L.gppd_strerror.argtypes = [C.c_int]
+    L.gppd_last_error.restype = C.c_char_p
+    L.gppd_create.argtypes = [C.c_int, C.POINTER(H)]
+    L.gppd_destroy.argtypes = [H]
+    L.gppd_alloc_pinned.argtypes = [H, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.gppd_free_pinned.argtypes = [H, C.c_void_p]
+    L.gppd_idx.argtypes = [C.c_int] * 3
+    L.gppd_phirange.argtypes = [_dp]
+    L.gppd_buildstates.argtypes = [H, C.c_int64, _dp, _dp, C.c_int64, _dp, C.c_int64,
+                                   C.c_int64, C.c_double, C.c_double, _i8p]
+    L.gppd_num_windows.restype = C.c_int64
+    L.gppd_num_windows.argtypes = [C.c_int64, C.c_int64]
+    L.gppd_demodulate_f64.argtypes = [H, C.c_int64, C.c_int64, _dp, _dp, _i8p,
+                                      C.POINTER(Options), _dp, _dp, _dp, _i32p, _dp]
+    L.gppd_table_windows.argtypes = [C.c_int64, _i32p, C.c_double, C.c_double, _i64p, _i64p]
+    tab = [C.c_int64, _i32p, C.c_double, _fp, _dp, _dp, C.c_int64, _dp, C.c_int64,
+           C.c_double, C.POINTER(Options), _fp, _dp, _dp, _i32p, _i8p]
+    L.gppd_process_table_f32.argtypes = [H] + tab
+    L.gppd_submit_table_f32.argtypes = [H, C.c_int] + tab
+    L.gppd_wait.argtypes = [H, C.c_int]
+    L.gppd_num_slots.argtypes = [H]
+    L.gppd_process_table_f32_dev.argtypes = [
+        H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
+        C.c_void_p, _dp, C.c_int64, _dp, C.c_int64, C.POINTER(Options), C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gppd_launch_count.restype = C.c_int64
+    L.gppd_launch_count.argtypes = [H]
+    for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
+                 "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
+                 "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
+                 "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(status: int):
+    if status != OK:
+        L = lib()
+        raise GppdError(status, L.gppd_strerror(status).decode(),
+                        (L.gppd_last_error() or b"").decode())
+
+
+def ptr(a, typ=_dp):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+class Handle:
+    """Owns one gppd_handle (streams, scratch, pinned staging) on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().gppd_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            lib().gppd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def raw(self):
+        return self._h
+
+    @property
+    def launches(self) -> int:
+        return int(lib().gppd_launch_count(self._h))
+
+    @property
+    def num_slots(self) -> int:
+        return int(lib().gppd_num_slots(self._h))
+
+
+_default = {}
+
+
+def default_handle() -> Handle:
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    if dev not in _default:
+        _default[dev] = Handle(dev)
+    return _default[dev]

@@ -1,0 +1,129 @@
+// fit_driver.cuh -- the per-diode fit procedure of demodulateall as a resumable
+// state machine around "evaluate chi2 at (b, phi)":
+//
+//   8-point phase scan at b = 0.1            reference src/Modulation.jl:402-406
+//   x = minimize!(lkl, xinit)  (NEWUOA)      :407  -> :332-336
+//   lklval = lkl(x)                          :408
+//   phipi = x[2] + (x[2] < 0 ? +pi : -pi)    :409
+//   if lklval > lkl(x[1], phipi): NEWUOA again from [x[1], phipi]   :411-414
+//   likelihood = lkl(x)                      :416   (this call fixes a and c)
+//
+// Every objective call is requested through step(): the caller evaluates
+// chi2(b, phi) however it likes (one thread, a block-wide reduction, ...).
+#pragma once
+#include "gppd_device.cuh"
+#include "newuoa2.cuh"
+
+namespace gppd {
+
+struct FitDriver {
+    enum { SCAN, NEWUOA1, LKL_X, LKL_FLIP, NEWUOA2, FINAL, DONE };
+    Newuoa2 nu;
+    double b, phi;         // point to evaluate next
+    double x1, x2;         // current solution
+    double best, lklval, phipi, chi2;
+    double rhobeg, rhoend;
+    int maxfun, phase, k, kbest, have_nan, nfev, second, status;
+
+    __device__ void start(const FitOptions &o) {
+        rhobeg = o.rhobeg;
+        rhoend = o.rhoend;
+        maxfun = o.maxfun;
+        nfev = 0;
+        second = 0;
+        status = 0;
+        k = 0;
+        kbest = 0;
+        have_nan = 0;
+        best = 0.0;
+        if (o.has_xinit) {  // init = [b, phi], reference :362-364
+            x1 = o.xinit[0];
+            x2 = o.xinit[1];
+            phase = NEWUOA1;
+            nu.start(x1, x2, rhobeg, rhoend, maxfun);
+            advance_solver(0.0, LKL_X);
+        } else {
+            phase = SCAN;
+            b = 0.1;  // binit, reference :403
+            phi = o.phi8[0];
+        }
+    }
+
+    // run the solver until it needs an objective value or finishes
+    __device__ void advance_solver(double f, int next_phase) {
+        if (nu.step(f)) {
+            b = nu.x[1];
+            phi = nu.x[2];
+        } else {
+            status = nu.status;
+            x1 = nu.x[1];
+            x2 = nu.x[2];
+            phase = next_phase;
+            b = x1;
+            phi = x2;
+        }
+    }
+
+    // f = chi2 at the (b, phi) handed out by the previous call.
+    // Returns true while another evaluation (at this->b, this->phi) is needed.
+    __device__ bool step(const FitOptions &o, double f) {
+        ++nfev;
+        switch (phase) {
+        case SCAN:
+            // argmin over the scan; Julia's argmin returns the first NaN
+            if (!have_nan) {
+                if (f != f) {
+                    kbest = k;
+                    have_nan = 1;
+                } else if (k == 0 || f < best) {
+                    best = f;
+                    kbest = k;
+                }
+            }
+            ++k;
+            if (k < 8) {
+                phi = o.phi8[k];
+                return true;
+            }
+            x1 = 0.1;
+            x2 = o.phi8[kbest];
+            phase = NEWUOA1;
+            nu.start(x1, x2, rhobeg, rhoend, maxfun);
+            advance_solver(0.0, LKL_X);
+            return true;
+        case NEWUOA1:
+            advance_solver(f, LKL_X);
+            return true;
+        case LKL_X:
+            lklval = f;
+            phipi = x2 + (x2 < 0 ? PI_F64 : -PI_F64);
+            phase = LKL_FLIP;
+            b = x1;
+            phi = phipi;
+            return true;
+        case LKL_FLIP:
+            if (lklval > f) {  // "bad minima", strict >
+                second = 1;
+                phase = NEWUOA2;
+                nu.start(x1, phipi, rhobeg, rhoend, maxfun);
+                advance_solver(0.0, FINAL);
+                return true;
+            }
+            phase = FINAL;
+            b = x1;
+            phi = x2;
+            return true;
+        case NEWUOA2:
+            advance_solver(f, FINAL);
+            return true;
+        case FINAL:
+            chi2 = f;
+            phase = DONE;
+            return false;
+        default:
+            return false;
+        }
+    }
+};
+
+}  // namespace gppd

@@ -1,0 +1,485 @@
+// stream_kernels.cu -- the HBM-bound passes around the fit:
+//   * FAINT segmentation (reference buildstates, src/Faint.jl:21-73)
+//   * per-row sin/cos basis of theta = fl(omega t) and per-job theta range
+//   * per-state mean/variance of |d| (reference compute_mean_var_power,
+//     src/Faint.jl:89-100)
+//   * demodulation + repack (reference src/Modulation.jl:417-425 and
+//     src/GPPupilDemodulation.jl:163-171,253)
+#include "gppd_device.cuh"
+#include "kernels.h"
+
+namespace gppd {
+
+// ---------------------------------------------------------------------------
+// order-preserving map double -> uint64 for atomicMin/atomicMax
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double f64_unkey(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+
+// ===========================================================================
+// Segmentation.  The reference scans the rows serially carrying two timer
+// queues; at most one event per queue fires per row.  With non-decreasing
+// timestamps the row at which the k-th event of a queue fires is
+//     trig_k = max(trig_{k-1} + 1, lower_bound(t, event_k))
+// so the scan reduces to (1) lower bounds of all timer values (parallel),
+// (2) a serial merge over the O(100) events, (3) a parallel fill.
+// Non-monotonic timestamps take the serial path, statement for statement.
+// ===========================================================================
+struct SegParams {
+    long long n;
+    const double *timer1, *timer2;  // device copies (HIGH series, LOW series)
+    int n1, n2;
+    long long lag;
+    double pre, post;
+};
+
+struct SegEvent {
+    long long row;
+    long long forget;
+    int state;
+    int pad;
+};
+
+struct SegWork {
+    long long *lb1, *lb2;   // lower bounds of timer values (+ sentinel at index n1 / n2)
+    SegEvent *events;
+    int max_events;
+    int *nevents;           // [0] count, [1] fallback flag (non-monotone / overflow)
+};
+
+__global__ void k_seg_monotone(TableView tv, int *flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i + 1 < tv.n; i += stride) {
+        double a = row_time(tv, i), b = row_time(tv, i + 1);
+        if (!(b >= a)) bad = true;
+    }
+    if (bad) flags[1] = 1;
+}
+
+__device__ long long seg_lower_bound(const TableView &tv, double v) {
+    long long lo = 0, hi = tv.n;  // first i with t[i] >= v
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (row_time(tv, mid) >= v) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void k_seg_lower_bounds(TableView tv, SegParams sp, SegWork wk) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int tot = sp.n1 + 1 + sp.n2 + 1;
+    if (k >= tot) return;
+    double timestep = row_time(tv, 1) - row_time(tv, 0);        // src/Faint.jl:24
+    double shift = (double)sp.lag * timestep;                   // :25-26
+    double tlast = row_time(tv, tv.n - 1);
+    if (k <= sp.n1) {
+        double v = (k < sp.n1) ? __dadd_rn(sp.timer1[k], shift) : tlast;
+        wk.lb1[k] = seg_lower_bound(tv, v);
+    } else {
+        int j = k - sp.n1 - 1;
+        double v = (j < sp.n2) ? __dadd_rn(sp.timer2[j], shift) : tlast;
+        wk.lb2[j] = seg_lower_bound(tv, v);
+    }
+}
+
+__device__ __forceinline__ long long seg_ceil_count(double delay, double timestep) {
+    double r = ceil(delay / timestep);                           // :29-30
+    if (!(r > 0.0)) return 0;
+    if (r > 4.0e18) return 4000000000000000000ll;
+    return (long long)r;
+}
+
+// serial merge of the two event queues (one thread)
+__global__ void k_seg_events(TableView tv, SegParams sp, SegWork wk) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (wk.nevents[1]) return;  // non-monotone: serial path
+    double timestep = row_time(tv, 1) - row_time(tv, 0);
+    double shift = (double)sp.lag * timestep;
+    double tlast = row_time(tv, tv.n - 1);
+    long long premax = seg_ceil_count(sp.pre, timestep);
+    long long postmax = seg_ceil_count(sp.post, timestep);
+    long long lb_last = wk.lb1[sp.n1];
+    int i1 = 0, i2 = 0;                       // next queue element to pop
+    double first1 = __dadd_rn(sp.timer1[i1], shift); long long lbh1 = wk.lb1[i1]; ++i1;
+    double first2 = __dadd_rn(sp.timer2[i2], shift); long long lbh2 = wk.lb2[i2]; ++i2;
+    long long last1 = -1, last2 = -1;
+    int cur = ST_NORMAL;
+    int ne = 0;
+    for (;;) {
+        long long tr1 = lbh1 > last1 + 1 ? lbh1 : last1 + 1;
+        long long tr2 = lbh2 > last2 + 1 ? lbh2 : last2 + 1;
+        long long row = tr1 < tr2 ? tr1 : tr2;
+        if (row >= tv.n) break;
+        long long forget = 0;
+        bool fired = false;
+        if (tr1 == row) {                      // :40-52
+            cur = ST_HIGH;
+            forget = premax;
+            fired = true;
+            if (i1 >= sp.n1) {
+                first1 = tlast; lbh1 = lb_last;
+                if (first2 == tlast) cur = ST_NORMAL;
+            } else {
+                first1 = __dadd_rn(sp.timer1[i1], shift); lbh1 = wk.lb1[i1]; ++i1;
+            }
+            last1 = row;
+        }
+        if (tr2 == row) {                      // :54-65
+            cur = ST_LOW;
+            forget = postmax;
+            fired = true;
+            if (i2 >= sp.n2) {
+                first2 = tlast; lbh2 = lb_last;
+                if (first1 == tlast) cur = ST_NORMAL;
+            } else {
+                first2 = __dadd_rn(sp.timer2[i2], shift); lbh2 = wk.lb2[i2]; ++i2;
+            }
+            last2 = row;
+        }
+        if (fired) {
+            if (ne >= wk.max_events) { wk.nevents[1] = 1; return; }
+            SegEvent ev; ev.row = row; ev.forget = forget; ev.state = cur; ev.pad = 0;
+            wk.events[ne++] = ev;
+        }
+    }
+    wk.nevents[0] = ne;
+}
+
+__global__ void k_seg_fill(long long n, SegWork wk, int8_t *state) {
+    if (wk.nevents[1]) return;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ne = wk.nevents[0];
+    int lo = 0, hi = ne;  // last event with row <= i
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (wk.events[mid].row <= i) lo = mid + 1; else hi = mid;
+    }
+    int st = ST_NORMAL;
+    if (lo > 0) {
+        SegEvent ev = wk.events[lo - 1];
+        st = (i - ev.row < ev.forget) ? ST_TRANSIENT : ev.state;   // :66-71
+    }
+    state[i] = (int8_t)st;
+}
+
+// the reference's loop, statement for statement (fallback, one thread)
+__global__ void k_seg_serial(TableView tv, SegParams sp, SegWork wk, int8_t *state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!wk.nevents[1]) return;
+    double timestep = row_time(tv, 1) - row_time(tv, 0);
+    double shift = (double)sp.lag * timestep;
+    double tlast = row_time(tv, tv.n - 1);
+    long long premax = seg_ceil_count(sp.pre, timestep);
+    long long postmax = seg_ceil_count(sp.post, timestep);
+    int i1 = 0, i2 = 0;
+    double first1 = __dadd_rn(sp.timer1[i1++], shift);
+    double first2 = __dadd_rn(sp.timer2[i2++], shift);
+    int cur = ST_NORMAL;
+    long long forget = 0;
+    for (long long k = 0; k < tv.n; ++k) {
+        double time = row_time(tv, k);
+        if (time >= first1) {
+            cur = ST_HIGH; forget = premax;
+            if (i1 >= sp.n1) { first1 = tlast; if (first2 == tlast) cur = ST_NORMAL; }
+            else first1 = __dadd_rn(sp.timer1[i1++], shift);
+        }
+        if (time >= first2) {
+            cur = ST_LOW; forget = postmax;
+            if (i2 >= sp.n2) { first2 = tlast; if (first1 == tlast) cur = ST_NORMAL; }
+            else first2 = __dadd_rn(sp.timer2[i2++], shift);
+        }
+        if (forget > 0) { state[k] = (int8_t)ST_TRANSIENT; --forget; }
+        else state[k] = (int8_t)cur;
+    }
+}
+
+void launch_segmentation(const Launcher &L, const TableView &tv, const double *d_timer1,
+                         int n1, const double *d_timer2, int n2, long long lag, double pre,
+                         double post, long long *d_lb, void *d_events, int max_events,
+                         int *d_flags, int8_t *d_state) {
+    SegParams sp{tv.n, d_timer1, d_timer2, n1, n2, lag, pre, post};
+    SegWork wk{d_lb, d_lb + (n1 + 1), reinterpret_cast<SegEvent *>(d_events), max_events, d_flags};
+    cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), L.stream);
+    int blocks = (int)((tv.n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    k_seg_monotone<<<blocks, 256, 0, L.stream>>>(tv, d_flags);
+    int tot = n1 + n2 + 2;
+    k_seg_lower_bounds<<<(tot + 127) / 128, 128, 0, L.stream>>>(tv, sp, wk);
+    k_seg_events<<<1, 32, 0, L.stream>>>(tv, sp, wk);
+    k_seg_fill<<<(int)((tv.n + 255) / 256), 256, 0, L.stream>>>(tv.n, wk, d_state);
+    k_seg_serial<<<1, 32, 0, L.stream>>>(tv, sp, wk, d_state);
+    *L.counter += 5;
+}
+
+// ===========================================================================
+// Basis: (sin theta, cos theta) per row with full-accuracy reduction of the
+// ~3e10 rad argument, done ONCE per row instead of once per objective call,
+// plus the per-job theta range and valid-row count.
+// ===========================================================================
+__global__ void k_basis(TableView tv, long long wrows, const int8_t *state, unsigned flags,
+                        double2 *basis, unsigned long long *thkeys, int *nvalid) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= tv.n) return;
+    double th = row_theta(tv, i);
+    double s, c;
+    sincos(th, &s, &c);
+    basis[i] = make_double2(s, c);
+    long long job = i / wrows;
+    unsigned long long key = f64_key(th);
+    int valid = state ? (row_valid(state[i], flags) ? 1 : 0) : 1;
+    // warp-aggregate when a full warp sits in one job
+    unsigned mask = __activemask();
+    if (mask == 0xffffffffu) {
+        long long job0 = __shfl_sync(mask, job, 0);
+        if (__all_sync(mask, job == job0)) {
+            unsigned long long kmin = key, kmax = key;
+            int cnt = valid;
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long a = __shfl_xor_sync(mask, kmin, o);
+                unsigned long long b = __shfl_xor_sync(mask, kmax, o);
+                cnt += __shfl_xor_sync(mask, cnt, o);
+                kmin = a < kmin ? a : kmin;
+                kmax = b > kmax ? b : kmax;
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(thkeys + 2 * job, kmin);
+                atomicMax(thkeys + 2 * job + 1, kmax);
+                if (cnt) atomicAdd(nvalid + job, cnt);
+            }
+            return;
+        }
+    }
+    atomicMin(thkeys + 2 * job, key);
+    atomicMax(thkeys + 2 * job + 1, key);
+    if (valid) atomicAdd(nvalid + job, 1);
+}
+
+__global__ void k_init_thkeys(unsigned long long *thkeys, int njobs) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    thkeys[2 * j] = ~0ull;
+    thkeys[2 * j + 1] = 0ull;
+}
+
+__global__ void k_jobinfo(long long n, long long wrows, int njobs, const unsigned long long *thkeys,
+                          const int *nvalid, JobInfo *jobs) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    JobInfo ji;
+    ji.thmin = f64_unkey(thkeys[2 * j]);
+    ji.thmax = f64_unkey(thkeys[2 * j + 1]);
+    ji.row0 = (long long)j * wrows;
+    long long rem = n - ji.row0;
+    ji.nrows = (int)(rem < wrows ? rem : wrows);
+    ji.nvalid = nvalid[j];
+    jobs[j] = ji;
+}
+
+void launch_basis(const Launcher &L, const TableView &tv, long long wrows, int njobs,
+                  const int8_t *d_state, unsigned flags, double2 *d_basis,
+                  unsigned long long *d_thkeys, int *d_nvalid, JobInfo *d_jobs) {
+    // keys: min slot = all ones, max slot = 0
+    cudaMemsetAsync(d_nvalid, 0, sizeof(int) * (size_t)njobs, L.stream);
+    k_init_thkeys<<<(njobs + 255) / 256, 256, 0, L.stream>>>(d_thkeys, njobs);
+    k_basis<<<(int)((tv.n + 255) / 256), 256, 0, L.stream>>>(tv, wrows, d_state, flags, d_basis,
+                                                             d_thkeys, d_nvalid);
+    k_jobinfo<<<(njobs + 255) / 256, 256, 0, L.stream>>>(tv.n, wrows, njobs, d_thkeys, d_nvalid,
+                                                         d_jobs);
+    *L.counter += 3;
+}
+
+// ===========================================================================
+// Per-state statistics of |d| (FAINT): mean and 1/var with the n-1 divisor,
+// two passes like the reference so that var is a sum of squared deviations.
+// One thread block per fit; fixed reduction order (deterministic).
+// ===========================================================================
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) s += red[k];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_stats(TableView tv, const JobInfo *jobs,
+                                               const int8_t *state, unsigned flags,
+                                               double2 *stats /* [fit][4] = (mean, weight) */) {
+    __shared__ double red[8];
+    int fit = blockIdx.x;
+    int job = fit / NDIODE, ch = fit % NDIODE;
+    JobInfo ji = jobs[job];
+    double sum[4] = {0, 0, 0, 0};
+    double cnt[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < ji.nrows; i += 256) {
+        long long r = ji.row0 + i;
+        int st = state[r];
+        if (!row_valid(st, flags) || st < 0 || st > 3) continue;
+        double2 d = row_sample(tv, r, ch);
+        double a = hypot(d.x, d.y);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (st == s) { sum[s] += a; cnt[s] += 1.0; }
+    }
+    double mean[4], tot[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        tot[s] = block_sum<256>(cnt[s], red);
+        mean[s] = block_sum<256>(sum[s], red) / tot[s];
+    }
+    double ssq[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < ji.nrows; i += 256) {
+        long long r = ji.row0 + i;
+        int st = state[r];
+        if (!row_valid(st, flags) || st < 0 || st > 3) continue;
+        double2 d = row_sample(tv, r, ch);
+        double a = hypot(d.x, d.y);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (st == s) { double e = a - mean[s]; ssq[s] += e * e; }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        double v = block_sum<256>(ssq[s], red) / (tot[s] - 1.0);  // n == 1 -> 0/0 = NaN as in Julia
+        if (threadIdx.x == 0) stats[(long long)fit * 4 + s] = make_double2(mean[s], 1.0 / v);
+    }
+}
+
+void launch_stats(const Launcher &L, const TableView &tv, int njobs, const JobInfo *d_jobs,
+                  const int8_t *d_state, unsigned flags, double2 *d_stats) {
+    k_stats<<<njobs * NDIODE, 256, 0, L.stream>>>(tv, d_jobs, d_state, flags, d_stats);
+    *L.counter += 1;
+}
+
+// ===========================================================================
+// Demodulation + repack: out = (d [- c]) * exp(-j psi),
+//   psi = fl(fl(b sin(fl(theta + phi)) + alpha) - alpha)   over ALL rows
+// (reference src/Modulation.jl:417-425, getphase :66-69), then the float32
+// re-interleave of src/GPPupilDemodulation.jl:163-171,253.
+// ===========================================================================
+__device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned flags, double theta,
+                                                double2 sc, double2 d) {
+    PhaseQ pq;
+    pq.uniform = fr.uniform; pq.q = fr.q; pq.cq = fr.cq; pq.sq = fr.sq;
+    double sn = sin_arg(pq, fr.phi, theta, sc);
+    if (!(flags & 4u)) {  // recenter = true
+        double gp = __dadd_rn(__dmul_rn(fr.b, sn), fr.alpha);
+        double psi = __dadd_rn(gp, -fr.alpha);
+        double sp, cp;
+        sincos(psi, &sp, &cp);
+        double vr = d.x, vi = d.y;
+        if (flags & 2u) { vr -= fr.cre; vi -= fr.cim; }
+        // (vr + j vi) * (cp - j sp)
+        return make_double2(__dadd_rn(__dmul_rn(vr, cp), __dmul_rn(vi, sp)),
+                            __dadd_rn(__dmul_rn(vi, cp), -__dmul_rn(vr, sp)));
+    }
+    // recenter = false: data * exp(-1im * angle(model(t))), :424
+    double u = __dmul_rn(fr.b, sn);
+    double su, cu;
+    sincos(u, &su, &cu);
+    double mr = __dadd_rn(__dmul_rn(fr.are, cu), -__dmul_rn(fr.aim, su));
+    double mi = __dadd_rn(__dmul_rn(fr.are, su), __dmul_rn(fr.aim, cu));
+    if (flags & 2u) { mr += fr.cre; mi += fr.cim; }
+    double ang = atan2(mi, mr);
+    double sa, ca;
+    sincos(ang, &sa, &ca);
+    return make_double2(__dadd_rn(__dmul_rn(d.x, ca), __dmul_rn(d.y, sa)),
+                        __dadd_rn(__dmul_rn(d.y, ca), -__dmul_rn(d.x, sa)));
+}
+
+__global__ void __launch_bounds__(128) k_demod(TableView tv, OutView ov, long long wrows,
+                                               const double2 *basis, const FitResult *results,
+                                               unsigned flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= tv.n) return;
+    long long job = i / wrows;
+    const FitResult *fr = results + job * NDIODE;
+    double theta = row_theta(tv, i);
+    double2 sc = basis[i];
+    if (ov.kind == 1) {
+        for (int ch = 0; ch < NDIODE; ++ch) {
+            double2 d = row_sample(tv, i, ch);
+            ov.out[(long long)ch * tv.n + i] = demod_sample(fr[ch], flags, theta, sc, d);
+        }
+        for (int ch = NDIODE; ch < NCHAN; ++ch)
+            ov.out[(long long)ch * tv.n + i] = row_sample(tv, i, ch);  // output = copy(data), :353
+        return;
+    }
+    float *orow = reinterpret_cast<float *>(reinterpret_cast<char *>(ov.volt) + i * ov.volt_stride);
+    int base = 0;
+    if (ov.keepraw) {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
+        const float *irow = reinterpret_cast<const float *>(
+            reinterpret_cast<const char *>(tv.volt) + i * tv.volt_stride);
+        for (int k = 0; k < 2 * NCHAN; ++k)
+            reinterpret_cast<uint32_t *>(orow)[k] = __ldg(reinterpret_cast<const uint32_t *>(irow) + k);
+        base = 2 * NCHAN;
+    }
+    for (int ch = 0; ch < NDIODE; ++ch) {
+        double2 d = row_sample(tv, i, ch);
+        double2 o = demod_sample(fr[ch], flags, theta, sc, d);
+        store_f32(orow + base + 2 * ch, __double2float_rn(o.x), ov.big_endian);
+        store_f32(orow + base + 2 * ch + 1, __double2float_rn(o.y), ov.big_endian);
+    }
+    if (!ov.keepraw) {
+        for (int ch = NDIODE; ch < NCHAN; ++ch) {  // centred FC channels, :170-171
+            double2 d = row_sample(tv, i, ch);
+            store_f32(orow + 2 * ch, __double2float_rn(d.x), ov.big_endian);
+            store_f32(orow + 2 * ch + 1, __double2float_rn(d.y), ov.big_endian);
+        }
+    }
+}
+
+void launch_demod(const Launcher &L, const TableView &tv, const OutView &ov, long long wrows,
+                  const double2 *d_basis, const FitResult *d_results, unsigned flags) {
+    k_demod<<<(int)((tv.n + 127) / 128), 128, 0, L.stream>>>(tv, ov, wrows, d_basis, d_results, flags);
+    *L.counter += 1;
+}
+
+// ===========================================================================
+// results -> caller layout: params (c.re,c.im,a.re,a.im,b,phi) with the sign
+// normalisation of reference src/Modulation.jl:426-431, chi2, info
+// ===========================================================================
+__global__ void k_export(int nfits, const FitResult *results, double *params, double *chi2,
+                         int *info) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfits) return;
+    FitResult r = results[f];
+    double b = r.b, phi = r.phi;
+    if (b < 0) {
+        b = -b;
+        phi += (phi < 0 ? PI_F64 : -PI_F64);
+    }
+    double *p = params + 6ll * f;
+    p[0] = r.cre; p[1] = r.cim; p[2] = r.are; p[3] = r.aim; p[4] = b; p[5] = phi;
+    chi2[f] = r.chi2;
+    if (info) {
+        info[4 * f] = r.nfev; info[4 * f + 1] = r.status;
+        info[4 * f + 2] = r.method; info[4 * f + 3] = r.second;
+    }
+}
+
+void launch_export(const Launcher &L, int nfits, const FitResult *d_results, double *d_params,
+                   double *d_chi2, int *d_info) {
+    k_export<<<(nfits + 127) / 128, 128, 0, L.stream>>>(nfits, d_results, d_params, d_chi2, d_info);
+    *L.counter += 1;
+}
+
+}  // namespace gppd

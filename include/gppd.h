@@ -1,0 +1,189 @@
+/*
+ * gppd.h -- C ABI of libgppd.so: the B200 (sm_100a) implementation of
+ * GPPupilDemodulation.jl's `demodulateall` hot path.
+ *
+ * The reference has no native interface for this path (it is plain Julia); its
+ * only FFI idiom is `ccall(...)::Cint` + `fits_assert_ok(status)`
+ * (reference src/FitsUtils.jl:42-58).  This header follows that idiom: every
+ * entry point returns an int status (0 = OK), takes plain pointers and sizes,
+ * never keeps a caller pointer after it returns, and never throws.  The Julia
+ * side binds it with `ccall` (see INTEGRATION.md and julia/GPPDB200.jl).
+ *
+ * Layout conventions (all little-endian host order unless stated):
+ *   complex128 = two consecutive doubles (re, im) == Julia ComplexF64
+ *   data / out of the *_f64 calls: N x 40 column-major == Julia
+ *       Matrix{ComplexF64}(N, 40): channel c (0-based) starts at 2*N*c doubles
+ *   VOLT of the *_f32 calls: 80 x N column-major in Julia == N rows of 80
+ *       floats in memory; channel c = (VOLT[2c], VOLT[2c+1]) of each row
+ *       (reference src/GPPupilDemodulation.jl:148)
+ *   params: 6 doubles per fitted diode (c.re, c.im, a.re, a.im, b, phi), diode
+ *       order = channel order 0..31 (reference idx(), src/Modulation.jl:17-22)
+ *   state: int8 MetState values OFF=0 LOW=1 NORMAL=2 HIGH=3 TRANSIENT=-1
+ *       (reference src/Faint.jl:1)
+ */
+#ifndef GPPD_H
+#define GPPD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPPD_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------ */
+#define GPPD_OK 0
+#define GPPD_ERR_ARG 1        /* bad argument (NULL, n < 2, ...) */
+#define GPPD_ERR_CUDA 2       /* a CUDA call failed; see gppd_last_error() */
+#define GPPD_ERR_NO_DEVICE 3  /* no usable sm_100 device: there is no CPU fallback */
+#define GPPD_ERR_NOMEM 4
+#define GPPD_ERR_UNSUPPORTED 5 /* e.g. --center empirical (broken in the reference too) */
+
+/* ---- option flags ------------------------------------------------------ */
+#define GPPD_ONLYHIGH 1u    /* demodulateall(onlyhigh=true)   src/Modulation.jl:348 */
+#define GPPD_FITOFFSETS 2u  /* demodulateall(fitoffsets=true) src/Modulation.jl:349 */
+#define GPPD_NO_RECENTER 4u /* demodulateall(recenter=false)  src/Modulation.jl:346 */
+#define GPPD_KEEPRAW 8u     /* processmetrology(keepraw=true) src/GPPupilDemodulation.jl:163 */
+#define GPPD_BIG_ENDIAN 16u /* table buffers are raw FITS (big-endian) bytes */
+
+/* which evaluator computes chi2(b, phi) inside the fit */
+#define GPPD_METHOD_AUTO 0     /* harmonic when its validity conditions hold, else direct */
+#define GPPD_METHOD_DIRECT 1   /* O(N) pass per objective call (the reference's formulation) */
+#define GPPD_METHOD_HARMONIC 2 /* Jacobi-Anger sums once, O(K) per objective call */
+
+typedef struct gppd_handle_s *gppd_handle;
+
+typedef struct gppd_options {
+    uint32_t flags;     /* GPPD_* bits */
+    int32_t method;     /* GPPD_METHOD_* */
+    int32_t maxfun;     /* NEWUOA objective-call cap; 0 => 60 (30n, OptimPackNextGen default) */
+    int32_t has_xinit;  /* 0: init=:auto (8-point phase scan), 1: use xinit */
+    double xinit[2];    /* demodulateall(init=[b, phi])       src/Modulation.jl:345,362 */
+    double rhobeg;      /* 0 => 1.0   (src/Modulation.jl:335) */
+    double rhoend;      /* 0 => 1e-3  (src/Modulation.jl:335) */
+} gppd_options;
+
+/* per-fit diagnostics (optional output, 4 int32 per diode) */
+#define GPPD_INFO_STRIDE 4 /* [0]=objective calls, [1]=NEWUOA status of the last
+                              run, [2]=evaluator used (GPPD_METHOD_*), [3]=second
+                              NEWUOA run taken (the "bad minima" retry, :411) */
+
+/* optional trace of every objective call of every fit: GPPD_TRACE_MAX entries
+ * of (b, phi, chi2) per diode, in call order; entry count = info[0] */
+#define GPPD_TRACE_MAX 160
+
+/* ---- library / handle -------------------------------------------------- */
+int gppd_version(void);
+const char *gppd_strerror(int status);
+/* message of the last failure on this thread (CUDA error string etc.) */
+const char *gppd_last_error(void);
+
+/* Opens CUDA device `device`, creates the handle's streams and scratch.
+ * Fails with GPPD_ERR_NO_DEVICE when no sm_100 GPU is present. */
+int gppd_create(int device, gppd_handle *out);
+int gppd_destroy(gppd_handle h);
+
+/* Page-locked host buffers for the ingest layer (FitsUtils reads table
+ * columns straight into these so that uploads run at PCIe rate). */
+int gppd_alloc_pinned(gppd_handle h, uint64_t bytes, void **out);
+int gppd_free_pinned(gppd_handle h, void *p);
+
+/* ---- small host-side helpers (no GPU work) ------------------------------ */
+/* reference idx(), src/Modulation.jl:17-22: side 0=FT 16=SC, telescope 1..4,
+ * diode 1..4 or 5=FC; returns the 1-based channel number, or -1 */
+int gppd_idx(int side, int telescope, int diode);
+/* the phase-scan grid range(-pi, pi, 8), src/Modulation.jl:360 */
+int gppd_phirange(double *phi8);
+
+/* ---- buildstates, src/Faint.jl:21-73 ----------------------------------- */
+/* timer1 = HIGH series, timer2 = LOW series (the FaintStates constructor swap,
+ * src/Faint.jl:12-19, is done by the caller). */
+int gppd_buildstates(gppd_handle h, int64_t n, const double *t,
+                     const double *timer1, int64_t n1, const double *timer2,
+                     int64_t n2, int64_t lag, double preswitchdelay,
+                     double postswitchdelay, int8_t *state_out);
+
+/* ---- demodulateall, src/Modulation.jl:344-435 --------------------------- */
+/*
+ * One call = `nwin` independent demodulateall calls over consecutive row
+ * windows of `nwindow` rows (the loop of src/GPPupilDemodulation.jl:204-225);
+ * nwindow <= 0 or >= n means one call over all n rows.
+ *   t      [n]            seconds (absolute, as the reference passes them)
+ *   data   [n x 40]       complex128, column-major
+ *   state  [n] or NULL    faintparam = Vector{MetState} / nothing
+ *   out    [n x 40]       complex128, column-major (columns 32..39 = input)
+ *   params [nwin x 32 x 6], chi2 [nwin x 32]
+ *   info   [nwin x 32 x GPPD_INFO_STRIDE] or NULL
+ *   trace  [nwin x 32 x GPPD_TRACE_MAX x 3] or NULL
+ * nwin = ceil(n / nwindow); gppd_num_windows() computes it.
+ */
+int64_t gppd_num_windows(int64_t n, int64_t nwindow);
+int gppd_demodulate_f64(gppd_handle h, int64_t n, int64_t nwindow, const double *t,
+                        const double *data, const int8_t *state,
+                        const gppd_options *opt, double *out, double *params,
+                        double *chi2, int32_t *info, double *trace);
+
+/* ---- processmetrology on arrays, src/GPPupilDemodulation.jl:128-255 ----- */
+/*
+ * Table-level fast path: everything between reading the METROLOGY columns and
+ * writing them back, on the device.
+ *   time_us [n] int32, mjd               TIME column and MJD-OBS          (:139)
+ *   volt    [n x 80] float32             VOLT column                       (:147)
+ *   offsets [40] complex128 or NULL      centres to subtract; NULL => fit  (:150-157)
+ *   timer1/timer2                        FAINT timers (n1 = 0 => bright)   (:141-145)
+ *   window_s                             --window seconds; <= 0 => whole   (:192)
+ *   volt_out [n x 80] (or n x 144 with GPPD_KEEPRAW) float32               (:163-171,253)
+ *   params/chi2/info as above with nwin = *nwin_out windows; the caller sizes
+ *   them with gppd_table_windows()
+ *   state_out [n] int8 or NULL           STATE column                      (:248)
+ */
+int gppd_table_windows(int64_t n, const int32_t *time_us, double mjd,
+                       double window_s, int64_t *nwindow_rows, int64_t *nwin);
+int gppd_process_table_f32(gppd_handle h, int64_t n, const int32_t *time_us,
+                           double mjd, const float *volt, const double *offsets,
+                           const double *timer1, int64_t n1, const double *timer2,
+                           int64_t n2, double window_s, const gppd_options *opt,
+                           float *volt_out, double *params, double *chi2,
+                           int32_t *info, int8_t *state_out);
+
+/*
+ * Asynchronous variant for pipelines over many files: the call enqueues the
+ * upload, the kernels and the download on pipeline slot `slot`
+ * (0 <= slot < gppd_num_slots()) and returns; gppd_wait(h, slot) blocks until
+ * that slot's results are in the caller's buffers.  Buffers must stay valid
+ * until then.  Uploads are truly asynchronous only from pinned memory
+ * (gppd_alloc_pinned); pageable memory works but serialises.
+ */
+int gppd_num_slots(gppd_handle h);
+int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n,
+                          const int32_t *time_us, double mjd, const float *volt,
+                          const double *offsets, const double *timer1, int64_t n1,
+                          const double *timer2, int64_t n2, double window_s,
+                          const gppd_options *opt, float *volt_out, double *params,
+                          double *chi2, int32_t *info, int8_t *state_out);
+int gppd_wait(gppd_handle h, int slot);
+
+/*
+ * Device-resident variant (all pointers are device pointers on the handle's
+ * GPU; `stream` is a cudaStream_t passed as void*, NULL = the slot's own
+ * stream).  No host<->device copies, no synchronisation: the caller orders
+ * and synchronises the stream.  nwindow_rows as in gppd_demodulate_f64.
+ * Scratch comes from pipeline slot `slot`.
+ */
+int gppd_process_table_f32_dev(gppd_handle h, int slot, void *stream, int64_t n,
+                               int64_t nwindow_rows, const int32_t *d_time_us,
+                               double mjd, const float *d_volt,
+                               const double *d_offsets, const double *timer1,
+                               int64_t n1, const double *timer2, int64_t n2,
+                               const gppd_options *opt, float *d_volt_out,
+                               double *d_params, double *d_chi2, int32_t *d_info,
+                               int8_t *d_state_out);
+
+/* number of kernels this library has launched on the handle so far */
+int64_t gppd_launch_count(gppd_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPPD_H */
