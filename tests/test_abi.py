@@ -1,0 +1,74 @@
+"""The C-ABI library: every symbol include/gppd.h declares is exported, the
+host-only helpers work without a GPU, and GPU entry points fail loudly (no CPU
+fallback) when no B200 is visible."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gppd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gppd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(gp):
+    L = gp._lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/gppd.h but not exported"
+
+
+def test_host_helpers(gp, ora):
+    L = gp._lib.lib()
+    assert L.gppd_version() == 100
+    for side in (0, 16):
+        for tel in range(1, 5):
+            for dio in range(1, 6):
+                assert gp.idx(side, tel, dio) == ora.idx(side, tel, dio)
+    with pytest.raises(ValueError):
+        gp.idx(3, 1, 1)
+    p = np.empty(8)
+    assert L.gppd_phirange(p.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    assert p.tobytes() == ora.phirange().tobytes()
+    assert L.gppd_num_windows(1000, 0) == 1 and L.gppd_num_windows(1000, 300) == 4
+    # --window arithmetic of src/GPPupilDemodulation.jl:192
+    tu = (2000 * np.arange(10)).astype(np.int32)
+    assert gp.table_windows(tu, 59949.0, 100.0)[0] == 50004
+    assert gp.table_windows(tu, 59949.0, 1.0)[0] == 500
+    assert gp.table_windows(tu, 59949.0, None) == (10, 1)
+    assert L.gppd_strerror(3).decode().startswith("no sm_100")
+
+
+def test_options_struct_layout(gp):
+    # must match `struct gppd_options` of include/gppd.h
+    assert C.sizeof(gp._lib.Options) == 4 * 4 + 2 * 8 + 8 + 8
+    assert gp._lib.Options.xinit.offset == 16 and gp._lib.Options.rhobeg.offset == 32
+
+
+def test_no_cpu_fallback(gp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible: the loud-failure path is for GPU-less hosts")
+    with pytest.raises(gp.GppdError) as e:
+        gp.Handle(0)
+    assert e.value.status == 3
+    t = np.arange(10.0)
+    with pytest.raises(gp.GppdError):
+        gp.demodulateall(t, np.zeros((10, 40), complex))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gppupildemodulation.jl_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(base, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+                assert "#include \"../oracle" not in txt and "oracle/" not in txt.replace("(oracle/newuoa.c)", ""), f
