@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- diode-samples demodulated per second (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2]): a synthetic GRAVITY+ night of 100 METROLOGY
+tables of 1e5 rows each (70 bright / 30 FAINT, whole-file fits, `--center stefan`)
+per GPU; one *step* = one pass of the hot path over the whole night.  Weak
+scaling: every rank demodulates its own night (files are independent, no
+collective on the data path).
+
+  value : whole-job diode-samples/s with all inputs resident in HBM
+          (C ABI gppd_process_table_f32_dev on the bench's CUDA streams, timed
+          with CUDA events on those streams, max over ranks)
+  e2e   : same metric through gppd_submit_table_f32 / gppd_wait with HOST
+          (pinned) buffers: H2D of TIME+VOLT and D2H of VOLT+params inside the
+          timed region
+  roofline     : the dominant pass (by CUDA-event time inside the timed region)
+                 against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline : the CPU oracle (restated reference algorithm, 8 threads like the
+                 reference's Threads.@threads over the 8 diode groups) on a
+                 bounded sample of the same night, on this box's host cores
+
+`--impl reference` times that CPU restatement alone (the reference is Julia and
+cannot run in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_ROW = 644.0          # TIME 4 B + VOLT 320 B in, VOLT 320 B out
+DIODES = 32
+METRIC = "diode-samples demodulated/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gppd", choices=["gppd", "reference"])
+    ap.add_argument("--files", type=int, default=100)
+    ap.add_argument("--rows", type=int, default=100_000)
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--cpu-files", type=int, default=12, help="files in the CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+def night_plan(nfiles):
+    """70 % bright, 30 % FAINT, interleaved deterministically."""
+    return [(k % 10) in (3, 6, 9) for k in range(nfiles)]
+
+
+def generate_night(torch, gp, dev, nfiles, nrows, rank):
+    """Synthetic night on the GPU (same model as gppd_b200.synthetic.make_table):
+    returns time_us [F, N] int32, volt [F, N, 80] float32, mjd list, FaintStates list."""
+    centres = torch.tensor(gp.synthetic.stefan_centres().view(np.float64).reshape(40, 2),
+                           device=dev)
+    time_us = torch.empty((nfiles, nrows), dtype=torch.int32, device=dev)
+    volt = torch.empty((nfiles, nrows, 80), dtype=torch.float32, device=dev)
+    faint = night_plan(nfiles)
+    mjds, fss = [], []
+    base = (2000 * torch.arange(nrows, device=dev, dtype=torch.int64))
+    for k in range(nfiles):
+        kk = rank * nfiles + k
+        mjd = 59949.0 + kk / 100.0
+        g = torch.Generator(device=dev)
+        g.manual_seed(20230105 + kk)
+        jit = torch.randint(-1, 2, (nrows,), generator=g, device=dev)
+        jit[0] = 0
+        tu = (base + jit).to(torch.int32)
+        time_us[k] = tu
+        t = tu.to(torch.float64) * 1e-6 + 86400.0 * mjd
+        pscale = torch.ones(nrows, dtype=torch.float64, device=dev)
+        fs = None
+        if faint[k]:
+            hdr = gp.synthetic.faint_header(mjd)
+            fs = gp.buildfaintparameters(hdr)
+            st = torch.from_numpy(gp.buildstates(fs, t.cpu().numpy())).to(dev)
+            pscale = torch.where(st == 3, 3.0, torch.where(st == 1, 0.2, 1.0)).to(torch.float64)
+        wt = 6.283185 * t
+        for grp in range(8):
+            phi_fc = torch.cumsum(0.02 * torch.randn(nrows, generator=g, device=dev, dtype=torch.float64), 0)
+            phi_fc = phi_fc + float(torch.rand(1, generator=g, device=dev)) * 6.28 - 3.14
+            efc = torch.polar(torch.ones_like(phi_fc), phi_fc)
+            fcch = 32 + grp
+            fc = torch.complex(centres[fcch, 0], centres[fcch, 1]) + 0.3 * efc
+            fc = fc + 0.002 * torch.complex(torch.randn(nrows, generator=g, device=dev, dtype=torch.float64),
+                                            torch.randn(nrows, generator=g, device=dev, dtype=torch.float64))
+            volt[k, :, 2 * fcch] = fc.real.float()
+            volt[k, :, 2 * fcch + 1] = fc.imag.float()
+            par = torch.rand(16, generator=g, device=dev, dtype=torch.float64).cpu().numpy()
+            for dio in range(4):
+                ch = 4 * grp + dio
+                amp = 0.05 + 0.45 * par[4 * dio]
+                arg_a = -np.pi + 2 * np.pi * par[4 * dio + 1]
+                b = 0.3 + 2.2 * par[4 * dio + 2]
+                phi = -np.pi + 2 * np.pi * par[4 * dio + 3]
+                a = amp * np.exp(1j * arg_a)
+                mod = torch.polar(torch.ones_like(wt), b * torch.sin(wt + phi))
+                noise = 0.02 * amp * torch.complex(
+                    torch.randn(nrows, generator=g, device=dev, dtype=torch.float64),
+                    torch.randn(nrows, generator=g, device=dev, dtype=torch.float64))
+                d = torch.complex(centres[ch, 0], centres[ch, 1]) + complex(a) * pscale * efc * mod + noise
+                volt[k, :, 2 * ch] = d.real.float()
+                volt[k, :, 2 * ch + 1] = d.imag.float()
+        mjds.append(mjd)
+        fss.append(fs)
+    return time_us, volt, mjds, fss
+
+
+def cpu_reference_files(oracle, files, cores):
+    """The restated reference algorithm (oracle) on host copies of `files`
+    = [(time_us, volt, mjd, FaintStates|None)].  Returns seconds."""
+    off = None
+    import gppd_b200 as gp
+    off = gp.synthetic.stefan_centres()
+    t0 = time.perf_counter()
+    for tu, v, mjd, fs in files:
+        ofs = None if fs is None else oracle.FaintStates(fs.timer1, fs.timer2, 1.0, 2.0)
+        oracle.processmetrology(tu, v, mjd, offsets=off, faintparam=ofs, nthreads=cores)
+    return time.perf_counter() - t0
+
+
+# --------------------------------------------------------------------------
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import ctypes as C
+    import gppd_b200 as gp
+    from gppd_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libgppd has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = gp.Handle(local)
+    L = _lib.lib()
+    F, N, S = args.files, args.rows, max(1, min(args.streams, h.num_slots))
+    faint = night_plan(F)
+    time_us, volt, mjds, fss = generate_night(torch, gp, dev, F, N, rank)
+    out = torch.empty_like(volt)
+    params = torch.empty((F, 32, 6), dtype=torch.float64, device=dev)
+    chi2 = torch.empty((F, 32), dtype=torch.float64, device=dev)
+    info = torch.zeros((F, 32, 4), dtype=torch.int32, device=dev)
+    offsets = torch.tensor(gp.synthetic.stefan_centres().view(np.float64), device=dev)
+    opt = gp.api._options()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    torch.cuda.synchronize()
+
+    def p(tensor):
+        return C.c_void_p(tensor.data_ptr())
+
+    def dptr(a):
+        return None if a is None else a.ctypes.data_as(_lib._dp)
+
+    def step_resident():
+        main_s = torch.cuda.current_stream()
+        ev0 = torch.cuda.Event()
+        ev0.record(main_s)
+        for s in streams:
+            s.wait_event(ev0)
+        for k in range(F):
+            s = streams[k % S]
+            fs = fss[k]
+            _lib.check(L.gppd_process_table_f32_dev(
+                h.raw, k % S, C.c_void_p(s.cuda_stream), N, 0, p(time_us[k]), mjds[k], p(volt[k]),
+                p(offsets), dptr(fs.timer1) if fs else None, fs.timer1.size if fs else 0,
+                dptr(fs.timer2) if fs else None, fs.timer2.size if fs else 0, C.byref(opt),
+                p(out[k]), p(params[k]), p(chi2[k]), p(info[k]), None))
+        for s in streams:
+            e = torch.cuda.Event()
+            e.record(s)
+            main_s.wait_event(e)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ---------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    h.enable_timing(True)
+    h.pass_times(reset=True)
+    launches0 = h.launches
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    passes = h.pass_times(reset=True)
+    h.enable_timing(False)
+    launches = h.launches - launches0
+    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    units_per_step = F * N * DIODES * world
+    value = units_per_step / (ms_per_step * 1e-3)
+    nfev_mean = float(info[:, :, 0].double().mean().item())
+
+    # ---- e2e: host buffers through the C ABI ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_time = torch.empty((F, N), dtype=torch.int32).pin_memory()
+        h_volt = torch.empty((F, N, 80), dtype=torch.float32).pin_memory()
+        h_out = torch.empty((F, N, 80), dtype=torch.float32).pin_memory()
+        h_par = torch.empty((F, 32, 6), dtype=torch.float64).pin_memory()
+        h_chi = torch.empty((F, 32), dtype=torch.float64).pin_memory()
+        h_time.copy_(time_us); h_volt.copy_(volt)
+        torch.cuda.synchronize()
+        offs_h = gp.synthetic.stefan_centres()
+
+        def hp(t, typ):
+            return C.cast(C.c_void_p(t.data_ptr()), typ)
+
+        def step_e2e():
+            for k in range(F):
+                fs = fss[k]
+                _lib.check(L.gppd_submit_table_f32(
+                    h.raw, k % S, N, hp(h_time[k], _lib._i32p), mjds[k], hp(h_volt[k], _lib._fp),
+                    dptr(offs_h.view(np.float64)), dptr(fs.timer1) if fs else None,
+                    fs.timer1.size if fs else 0, dptr(fs.timer2) if fs else None,
+                    fs.timer2.size if fs else 0, 0.0, C.byref(opt), hp(h_out[k], _lib._fp),
+                    hp(h_par[k], _lib._dp), hp(h_chi[k], _lib._dp), None, None))
+            for s in range(S):
+                _lib.check(L.gppd_wait(h.raw, s))
+
+        for _ in range(max(1, args.warmup - 1)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_val = units_per_step * args.steps / float(tm.item())
+        # result check of the e2e path against the resident path (same fits)
+        same = bool(torch.equal(h_par.to(dev), params))
+        e2e = {"value": e2e_val, "unit": "diode-samples/s",
+               "h2d_bytes_per_step": int(F * (N * 4 + N * 320)),
+               "d2h_bytes_per_step": int(F * (N * 320 + 32 * 7 * 8)),
+               "timing": "host wall clock around the K steps, device-synchronised, max over ranks",
+               "matches_resident_path": same}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant pass ----------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    dom = max((k for k in passes if passes[k][1] > 0), key=lambda k: passes[k][0])
+    dom_ms, dom_n = passes[dom]
+    avg_ms = dom_ms / dom_n
+    alg_bytes_per_launch = ALG_BYTES_PER_ROW * N          # one launch = one table
+    achieved = alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    fp64_peak = h.fp64_peak_tflops()
+    # algorithmic FP64 work of the fit: measured objective calls x ~35 FMA-class
+    # operations per row and call, 2 flop each
+    fit_flops_per_launch = nfev_mean * 32 * N * 35 * 2.0
+    fit_ms, fit_n = passes["fit"]
+    fp64 = {"achieved_tflops": fit_flops_per_launch / (fit_ms / max(fit_n, 1) * 1e-3) / 1e12,
+            "peak_tflops": fp64_peak, "peak_source": "DFMA micro-benchmark in this run",
+            "objective_calls_per_fit": nfev_mean,
+            "note": "per-launch event time with %d tables in flight on %d streams" % (S, S)}
+    fp64["frac"] = fp64["achieved_tflops"] / fp64_peak if fp64_peak else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "avg_launch_ms": avg_ms, "launches_timed": dom_n,
+                "pass_ms_per_step": {k: v[0] / args.steps for k, v in passes.items() if v[1]},
+                "fp64": fp64,
+                "note": "the fit is FP64-pipe bound, not HBM bound; kernels of %d tables overlap "
+                        "on %d streams, so a launch's event time is stretched by that factor" % (S, S)}
+
+    # ---- CPU baseline on a bounded sample -------------------------------
+    cpu = None
+    if not args.no_cpu:
+        import oracle
+        oracle.build()
+        cores = min(8, os.cpu_count() or 1)
+        nf = min(args.cpu_files, F)
+        files = [(time_us[k].cpu().numpy(), volt[k].cpu().numpy(), mjds[k], fss[k]) for k in range(nf)]
+        secs = cpu_reference_files(oracle, files, cores)
+        cpu = {"value": nf * N * DIODES / secs, "unit": "diode-samples/s", "cores": cores,
+               "kind": "port",
+               "sample": "first %d tables of the night (%d rows each), whole-file fits, %.1f s" % (nf, N, secs)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "diode-samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "night of %d METROLOGY tables x %d rows per GPU (70%% bright / 30%% FAINT), "
+                               "whole-file fits, --center stefan (BASELINE.json configs[2])" % (F, N),
+                   "tables_per_gpu": F, "rows_per_table": N, "diodes": DIODES, "streams": S,
+                   "cache": "inputs (%.1f GB per step) larger than L2" % (F * N * 324 / 1e9),
+                   "sharding": "files -> ranks, no data-path collective"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle restatement; the
+    Julia package cannot run here) on this box's host cores, same night, each
+    step a bounded sample of it."""
+    if rank != 0:
+        return
+    import gppd_b200 as gp
+    import oracle
+    oracle.build()
+    cores = min(8, os.cpu_count() or 1)
+    F, N = args.files, args.rows
+    nf = max(1, min(4, F))       # tables per step
+    faint = night_plan(F)
+    files = []
+    for k in range(nf):
+        tab = gp.synthetic.make_table(N, k=k, jitter=True)
+        fs = None
+        if faint[k]:
+            hdr = gp.synthetic.faint_header(tab["mjd"])
+            fs = oracle.buildfaintparameters(hdr)
+            t = oracle.make_times(tab["time_us"], tab["mjd"])
+            st = oracle.buildstates(fs, t)
+            tab = gp.synthetic.make_table(N, k=k, jitter=True, faint=True, state=st)
+        files.append((tab["time_us"], tab["volt"], tab["mjd"], fs))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_files(oracle, files[:1], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_files(oracle, files, cores)
+    dt = time.perf_counter() - t0
+    value = nf * N * DIODES * args.steps / dt
+    sample = "%d tables x %d rows per step (of the %d-table night), whole-file fits" % (nf, N, F)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "diode-samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "night of %d METROLOGY tables x %d rows per GPU (70%% bright / 30%% FAINT), "
+                               "whole-file fits, --center stefan (BASELINE.json configs[2])" % (F, N),
+                   "tables_per_gpu": F, "rows_per_table": N, "diodes": DIODES},
+        "cpu_baseline": {"value": value, "unit": "diode-samples/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "diode-samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "restated CPU reference algorithm (oracle/): the Julia package and its NEWUOA "
+                "dependency cannot be installed in this image",
+    }))
+
+
+if __name__ == "__main__":
+    main()

@@ -82,10 +82,14 @@ def lib():
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gppd_launch_count.restype = C.c_int64
     L.gppd_launch_count.argtypes = [H]
+    L.gppd_enable_timing.argtypes = [H, C.c_int]
+    L.gppd_pass_times.argtypes = [H, _dp, _i64p, C.c_int]
+    L.gppd_measure_fp64_peak.argtypes = [H, _dp]
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
-                 "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev"):
+                 "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev", "gppd_enable_timing",
+                 "gppd_pass_times", "gppd_measure_fp64_peak"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -132,6 +136,24 @@ class Handle:
     @property
     def num_slots(self) -> int:
         return int(lib().gppd_num_slots(self._h))
+
+    PASSES = ("segment", "basis", "stats", "fit", "demod", "export", "harmonics", "reserved")
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        check(lib().gppd_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def enable_timing(self, on: bool = True):
+        check(lib().gppd_enable_timing(self._h, int(on)))
+
+    def pass_times(self, reset: bool = True):
+        """{pass: (total ms, launches)} measured with CUDA events on the launching stream."""
+        import numpy as np
+        ms = np.zeros(8)
+        cnt = np.zeros(8, dtype=np.int64)
+        check(lib().gppd_pass_times(self._h, ptr(ms), ptr(cnt, _i64p), int(reset)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PASSES)}
 
 
 _default = {}

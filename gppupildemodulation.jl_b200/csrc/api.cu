@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/gppd.h"
 #include "kernels.h"
@@ -75,6 +76,14 @@ struct DevBuf {
 };
 
 constexpr int NSLOTS = 4;
+constexpr int NPASS = GPPD_NPASS;
+
+struct PassTimer {
+    std::vector<cudaEvent_t> ev;      // begin/end pairs
+    std::vector<int> pass;            // pass id per pair
+    double ms[NPASS] = {0};
+    long long count[NPASS] = {0};
+};
 constexpr int MAX_TIMER = 1 << 16;
 
 struct Slot {
@@ -85,8 +94,7 @@ struct Slot {
     DevBuf state, basis, z, y, thkeys, nvalid, jobs, stats, results;
     DevBuf params, chi2, info, trace;
     DevBuf timers, lb, events, flags, offsets;
-    double *h_small = nullptr;  // pinned: timers + offsets staging
-    size_t h_small_cap = 0;
+    PassTimer timer;
     bool busy = false;
 };
 
@@ -94,21 +102,12 @@ struct Slot {
 
 struct gppd_handle_s {
     int device = 0;
+    bool timing = false;
     Slot slots[NSLOTS];
     long long launches = 0;
 };
 
 namespace {
-
-int slot_small(Slot &s, size_t doubles) {
-    if (doubles <= s.h_small_cap) return GPPD_OK;
-    if (s.h_small) cudaFreeHost(s.h_small);
-    s.h_small = nullptr;
-    s.h_small_cap = 0;
-    CK(cudaMallocHost(&s.h_small, doubles * sizeof(double)));
-    s.h_small_cap = doubles;
-    return GPPD_OK;
-}
 
 void fill_options(const gppd_options *o, FitOptions &f) {
     gppd_options d;
@@ -123,6 +122,26 @@ void fill_options(const gppd_options *o, FitOptions &f) {
     f.rhoend = d.rhoend > 0 ? d.rhoend : 1e-3;
     gppd_phirange(f.phi8);
 }
+
+// cudaEvent pair around one pass (only when gppd_enable_timing is on)
+struct PassScope {
+    Slot *s;
+    cudaStream_t st;
+    bool on;
+    PassScope(gppd_handle h, Slot &slot, cudaStream_t stream, int pass) : s(&slot), st(stream), on(h->timing) {
+        if (!on) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        s->timer.ev.push_back(a);
+        s->timer.ev.push_back(b);
+        s->timer.pass.push_back(pass);
+    }
+    ~PassScope() {
+        if (on) cudaEventRecord(s->timer.ev.back(), st);
+    }
+};
 
 struct RunArgs {
     TableView tv;
@@ -168,19 +187,23 @@ int run_table(gppd_handle h, Slot &s, cudaStream_t stream, RunArgs &a, const gpp
             if ((rc = s.state.ensure((size_t)n))) return rc;
             st = s.state.as<int8_t>();
         }
-        if ((rc = slot_small(s, (size_t)(n1 + n2 + 80)))) return rc;
         if ((rc = s.timers.ensure(sizeof(double) * (size_t)(n1 + n2)))) return rc;
         if ((rc = s.lb.ensure(sizeof(long long) * (size_t)(n1 + n2 + 2)))) return rc;
         int max_events = n1 + n2 + 1024;
         if ((rc = s.events.ensure((size_t)SEG_EVENT_BYTES * max_events))) return rc;
         if ((rc = s.flags.ensure(2 * sizeof(int)))) return rc;
-        memcpy(s.h_small, a.timer1, sizeof(double) * n1);
-        memcpy(s.h_small + n1, a.timer2, sizeof(double) * n2);
-        CK(cudaMemcpyAsync(s.timers.p, s.h_small, sizeof(double) * (size_t)(n1 + n2),
+        // small pageable copies: the runtime stages them before returning, so the
+        // caller's arrays may be reused at once and tables of one slot cannot race
+        CK(cudaMemcpyAsync(s.timers.p, a.timer1, sizeof(double) * (size_t)n1,
                            cudaMemcpyHostToDevice, stream));
-        launch_segmentation(L, a.tv, s.timers.as<double>(), n1, s.timers.as<double>() + n1, n2, 0,
-                            0.0, 0.0, s.lb.as<long long>(), s.events.p, max_events,
-                            s.flags.as<int>(), st);
+        CK(cudaMemcpyAsync(s.timers.as<double>() + n1, a.timer2, sizeof(double) * (size_t)n2,
+                           cudaMemcpyHostToDevice, stream));
+        {
+            PassScope ps(h, s, stream, GPPD_PASS_SEGMENT);
+            launch_segmentation(L, a.tv, s.timers.as<double>(), n1, s.timers.as<double>() + n1, n2,
+                                0, 0.0, 0.0, s.lb.as<long long>(), s.events.p, max_events,
+                                s.flags.as<int>(), st);
+        }
         DBG(stream, "segmentation");
         d_state = st;
     } else if (d_state && a.d_state_out && a.d_state_out != d_state) {
@@ -198,19 +221,33 @@ int run_table(gppd_handle h, Slot &s, cudaStream_t stream, RunArgs &a, const gpp
     if (d_state)
         if ((rc = s.stats.ensure(sizeof(double2) * 4 * (size_t)nfits))) return rc;
 
-    launch_basis(L, a.tv, wrows, njobs, d_state, fo.flags, s.basis.as<double2>(),
-                 s.thkeys.as<unsigned long long>(), s.nvalid.as<int>(), s.jobs.as<JobInfo>());
+    {
+        PassScope ps(h, s, stream, GPPD_PASS_BASIS);
+        launch_basis(L, a.tv, wrows, njobs, d_state, fo.flags, s.basis.as<double2>(),
+                     s.thkeys.as<unsigned long long>(), s.nvalid.as<int>(), s.jobs.as<JobInfo>());
+    }
     DBG(stream, "basis");
-    if (d_state)
+    if (d_state) {
+        PassScope ps(h, s, stream, GPPD_PASS_STATS);
         launch_stats(L, a.tv, njobs, s.jobs.as<JobInfo>(), d_state, fo.flags, s.stats.as<double2>());
+    }
     DBG(stream, "stats");
-    launch_fit_direct(L, a.tv, nfits, s.jobs.as<JobInfo>(), d_state, s.stats.as<double2>(),
-                      s.basis.as<double2>(), s.z.as<double2>(), s.y.as<double2>(), fo, nullptr,
-                      s.results.as<FitResult>(), a.d_trace);
+    {
+        PassScope ps(h, s, stream, GPPD_PASS_FIT);
+        launch_fit_direct(L, a.tv, nfits, s.jobs.as<JobInfo>(), d_state, s.stats.as<double2>(),
+                          s.basis.as<double2>(), s.z.as<double2>(), s.y.as<double2>(), fo, nullptr,
+                          s.results.as<FitResult>(), a.d_trace);
+    }
     DBG(stream, "fit_direct");
-    launch_demod(L, a.tv, a.ov, wrows, s.basis.as<double2>(), s.results.as<FitResult>(), fo.flags);
+    {
+        PassScope ps(h, s, stream, GPPD_PASS_DEMOD);
+        launch_demod(L, a.tv, a.ov, wrows, s.basis.as<double2>(), s.results.as<FitResult>(), fo.flags);
+    }
     DBG(stream, "demod");
-    launch_export(L, nfits, s.results.as<FitResult>(), a.d_params, a.d_chi2, a.d_info);
+    {
+        PassScope ps(h, s, stream, GPPD_PASS_EXPORT);
+        launch_export(L, nfits, s.results.as<FitResult>(), a.d_params, a.d_chi2, a.d_info);
+    }
     DBG(stream, "export");
     CK(cudaGetLastError());
     return GPPD_OK;
@@ -310,7 +347,6 @@ int gppd_destroy(gppd_handle h) {
                           &s.stats, &s.results, &s.params, &s.chi2, &s.info, &s.trace,
                           &s.timers, &s.lb, &s.events, &s.flags, &s.offsets};
         for (DevBuf *b : bufs) b->release();
-        if (s.h_small) cudaFreeHost(s.h_small);
     }
     delete h;
     return GPPD_OK;
@@ -334,6 +370,57 @@ int gppd_free_pinned(gppd_handle h, void *p) {
 int gppd_num_slots(gppd_handle) { return NSLOTS; }
 
 int64_t gppd_launch_count(gppd_handle h) { return h ? h->launches : 0; }
+
+int gppd_measure_fp64_peak(gppd_handle h, double *tflops) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!tflops) return GPPD_ERR_ARG;
+    Slot &s = h->slots[0];
+    if ((rc = s.flags.ensure(64))) return rc;
+    *tflops = measure_dfma_tflops(s.stream, s.flags.as<double>());
+    h->launches += 4;
+    CK(cudaGetLastError());
+    return GPPD_OK;
+}
+
+int gppd_enable_timing(gppd_handle h, int on) {
+    if (!h) return GPPD_ERR_ARG;
+    h->timing = on != 0;
+    return GPPD_OK;
+}
+
+int gppd_pass_times(gppd_handle h, double *ms, int64_t *counts, int reset) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    for (int p = 0; p < NPASS; ++p) {
+        if (ms) ms[p] = 0.0;
+        if (counts) counts[p] = 0;
+    }
+    for (int i = 0; i < NSLOTS; ++i) {
+        PassTimer &t = h->slots[i].timer;
+        for (size_t k = 0; k < t.pass.size(); ++k) {
+            cudaEvent_t a = t.ev[2 * k], b = t.ev[2 * k + 1];
+            CK(cudaEventSynchronize(b));
+            float dt = 0.f;
+            CK(cudaEventElapsedTime(&dt, a, b));
+            t.ms[t.pass[k]] += dt;
+            t.count[t.pass[k]] += 1;
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+        t.ev.clear();
+        t.pass.clear();
+        for (int p = 0; p < NPASS; ++p) {
+            if (ms) ms[p] += t.ms[p];
+            if (counts) counts[p] += t.count[p];
+            if (reset) {
+                t.ms[p] = 0.0;
+                t.count[p] = 0;
+            }
+        }
+    }
+    return GPPD_OK;
+}
 
 int64_t gppd_num_windows(int64_t n, int64_t nwindow) {
     if (n <= 0) return 0;
@@ -520,15 +607,10 @@ int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n, const int32_t *tim
     if ((rc = s.info.ensure(sizeof(int) * GPPD_INFO_STRIDE * nfits))) return rc;
     if ((rc = s.state.ensure((size_t)n))) return rc;
     if ((rc = s.offsets.ensure(sizeof(double) * 80))) return rc;
-    if ((rc = slot_small(s, (size_t)(n1 + n2 + 80)))) return rc;
     CK(cudaMemcpyAsync(s.time.p, time_us, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s.volt.p, volt, vbytes, cudaMemcpyHostToDevice, st));
-    if (offsets) {
-        // staged behind the timers in the pinned scratch (timers use [0, n1+n2))
-        memcpy(s.h_small + (n1 + n2), offsets, sizeof(double) * 80);
-        CK(cudaMemcpyAsync(s.offsets.p, s.h_small + (n1 + n2), sizeof(double) * 80,
-                           cudaMemcpyHostToDevice, st));
-    }
+    if (offsets)
+        CK(cudaMemcpyAsync(s.offsets.p, offsets, sizeof(double) * 80, cudaMemcpyHostToDevice, st));
     RunArgs a;
     table_views(n, mjd, s.time.as<int32_t>(), s.volt.as<float>(),
                 offsets ? s.offsets.as<double>() : nullptr, s.volt_out.as<float>(), o.flags, a);

@@ -35,4 +35,7 @@ void launch_demod(const Launcher &L, const TableView &tv, const OutView &ov, lon
 void launch_export(const Launcher &L, int nfits, const FitResult *d_results, double *d_params,
                    double *d_chi2, int *d_info);
 
+// measured FP64 FMA throughput of the device (TFLOP/s), for the fit's roofline
+double measure_dfma_tflops(cudaStream_t stream, double *d_scratch);
+
 }  // namespace gppd

@@ -482,4 +482,47 @@ void launch_export(const Launcher &L, int nfits, const FitResult *d_results, dou
     *L.counter += 1;
 }
 
+// ===========================================================================
+// FP64 pipe micro-benchmark: 16 independent DFMA chains per thread.  Gives the
+// measured denominator of the fit's FP64 roofline (MEASURED_PEAKS.json has none).
+// ===========================================================================
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = (double)(threadIdx.x + k) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+double measure_dfma_tflops(cudaStream_t stream, double *d_scratch) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int iters = 20000, blocks = sms * 8;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a, stream);
+        k_dfma_peak<<<blocks, 256, 0, stream>>>(d_scratch, iters, 0.999999, 1e-9);
+        cudaEventRecord(b, stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        double flops = 2.0 * 16.0 * iters * 256.0 * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return best;
+}
+
 }  // namespace gppd

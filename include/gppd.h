@@ -183,6 +183,23 @@ int gppd_process_table_f32_dev(gppd_handle h, int slot, void *stream, int64_t n,
 /* number of kernels this library has launched on the handle so far */
 int64_t gppd_launch_count(gppd_handle h);
 
+/* Per-pass device timing (CUDA events on the launching stream around each pass
+ * of the launch sequence).  ms[p] / counts[p] accumulate over all slots since
+ * the last reset; gppd_pass_times waits for the recorded events. */
+#define GPPD_PASS_SEGMENT 0 /* FAINT segmentation (buildstates)          */
+#define GPPD_PASS_BASIS 1   /* per-row sin/cos basis + job ranges         */
+#define GPPD_PASS_STATS 2   /* per-state mean/variance (FAINT)            */
+#define GPPD_PASS_FIT 3     /* the modulation fit (NEWUOA + objective)    */
+#define GPPD_PASS_DEMOD 4   /* demodulation + repack                      */
+#define GPPD_PASS_EXPORT 5  /* parameter export                           */
+#define GPPD_PASS_HARMONICS 6 /* Jacobi-Anger harmonic sums (harmonic evaluator) */
+#define GPPD_NPASS 8
+int gppd_enable_timing(gppd_handle h, int on);
+/* measured FP64 FMA throughput of the device in TFLOP/s (a DFMA micro-benchmark):
+ * the denominator of the fit's FP64 roofline */
+int gppd_measure_fp64_peak(gppd_handle h, double *tflops);
+int gppd_pass_times(gppd_handle h, double *ms, int64_t *counts, int reset);
+
 #ifdef __cplusplus
 }
 #endif
