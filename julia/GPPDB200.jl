@@ -1,0 +1,119 @@
+# GPPDB200.jl -- the reference-side binding of libgppd.so.
+#
+# Drop this file next to the reference's src/Modulation.jl and
+# `include("GPPDB200.jl")` from src/GPPupilDemodulation.jl (after Modulation.jl):
+# it replaces the bodies of `demodulateall` (src/Modulation.jl:344-435) and
+# `buildstates` (src/Faint.jl:21-73) by `ccall`s into the B200 library while
+# keeping their signatures, keyword arguments and return types, so that
+# `processmetrology` (src/GPPupilDemodulation.jl:161,205), `main` and
+# bin/GPPupilDemodulation work unchanged.  Error convention = the reference's
+# own FFI idiom (src/FitsUtils.jl:42-58): Cint status, error raised on the
+# Julia side.
+#
+# NOTE: no Julia toolchain exists in the build image or on the GPU boxes, so
+# this file has never been executed; the same C ABI is exercised by the ctypes
+# host mirror (gppupildemodulation.jl_b200/api.py) in tests/.
+module GPPDB200
+
+import ..GPPupilDemodulation: MetState, FaintStates, Modulation, ModulationWithOffsets,
+    ModulationNoOffsets, M_2PI, HIGH, LOW, NORMAL, TRANSIENT
+
+const libgppd = get(ENV, "GPPD_LIBRARY", joinpath(@__DIR__, "libgppd.so"))
+
+const GPPD_ONLYHIGH    = UInt32(1)
+const GPPD_FITOFFSETS  = UInt32(2)
+const GPPD_NO_RECENTER = UInt32(4)
+const GPPD_KEEPRAW     = UInt32(8)
+
+# struct gppd_options (include/gppd.h)
+struct Options
+    flags::UInt32
+    method::Int32
+    maxfun::Int32
+    has_xinit::Int32
+    xinit::NTuple{2,Float64}
+    rhobeg::Float64
+    rhoend::Float64
+end
+
+const handle = Ref{Ptr{Cvoid}}(C_NULL)
+
+function gppd_assert_ok(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:gppd_strerror, libgppd), Cstring, (Cint,), status))
+    detail = unsafe_string(ccall((:gppd_last_error, libgppd), Cstring, ()))
+    error("libgppd: $msg ($detail)")
+end
+
+function gethandle()
+    if handle[] == C_NULL
+        dev = parse(Int, get(ENV, "GPPD_DEVICE", "0"))
+        gppd_assert_ok(ccall((:gppd_create, libgppd), Cint, (Cint, Ref{Ptr{Cvoid}}), dev, handle))
+        atexit(() -> ccall((:gppd_destroy, libgppd), Cint, (Ptr{Cvoid},), handle[]))
+    end
+    return handle[]
+end
+
+# buildstates(faintstates, timestamp; lag, preswitchdelay, postwitchdelay), src/Faint.jl:21
+function buildstates(faintstates::FaintStates{T,A}, timestamp::AbstractVector;
+                     lag::Integer=0, preswitchdelay=0, postwitchdelay=0) where {T<:AbstractFloat,A<:AbstractVector{T}}
+    t = collect(Float64, timestamp)
+    t1 = collect(Float64, faintstates.timer1)
+    t2 = collect(Float64, faintstates.timer2)
+    st = Vector{Int8}(undef, length(t))
+    gppd_assert_ok(ccall((:gppd_buildstates, libgppd), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64,
+         Float64, Float64, Ptr{Int8}),
+        gethandle(), length(t), t, t1, length(t1), t2, length(t2), lag,
+        Float64(preswitchdelay), Float64(postwitchdelay), st))
+    return MetState.(st)
+end
+
+# demodulateall(timestamp, data; ...) -> (output, param, likelihood), src/Modulation.jl:344-435
+function demodulateall(timestamp::AbstractVector, data::AbstractMatrix{Complex{T}};
+                       init::Union{Symbol,Vector{T}}=:auto,
+                       recenter::Bool=true,
+                       faintparam::Union{Nothing,FaintStates,S}=nothing,
+                       onlyhigh=false,
+                       fitoffsets=false,
+                       preswitchdelay=0.01,
+                       postwitchdelay=0.3) where {T<:AbstractFloat,S<:AbstractVector{MetState}}
+    n = length(timestamp)
+    size(data) == (n, 40) || error("voltage and time must have the same number of lines")
+    t = collect(Float64, timestamp)
+    d = Matrix{ComplexF64}(data)                       # N x 40, column-major
+    state = C_NULL
+    stvec = Int8[]
+    if isa(faintparam, FaintStates)                    # :366-367
+        stvec = Int8.(Integer.(buildstates(faintparam, t; preswitchdelay=preswitchdelay,
+                                           postwitchdelay=postwitchdelay)))
+        state = pointer(stvec)
+    elseif !isnothing(faintparam)                      # :368-369
+        stvec = Int8.(Integer.(faintparam))
+        state = pointer(stvec)
+    end
+    flags = (onlyhigh ? GPPD_ONLYHIGH : UInt32(0)) | (fitoffsets ? GPPD_FITOFFSETS : UInt32(0)) |
+            (recenter ? UInt32(0) : GPPD_NO_RECENTER)
+    opt = isa(init, Symbol) ? Options(flags, 0, 0, 0, (0.0, 0.0), 0.0, 0.0) :
+                              Options(flags, 0, 0, 1, (Float64(init[1]), Float64(init[2])), 0.0, 0.0)
+    output = Matrix{ComplexF64}(undef, n, 40)
+    params = Matrix{Float64}(undef, 6, 32)
+    chi2 = Vector{Float64}(undef, 32)
+    GC.@preserve stvec begin
+        gppd_assert_ok(ccall((:gppd_demodulate_f64, libgppd), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{ComplexF64}, Ptr{Int8}, Ref{Options},
+             Ptr{ComplexF64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+            gethandle(), n, 0, t, d, state, opt, output, params, chi2, C_NULL, C_NULL))
+    end
+    if fitoffsets
+        param = [ModulationWithOffsets{T}(complex(params[1, i], params[2, i]),
+                                          complex(params[3, i], params[4, i]),
+                                          params[5, i], params[6, i], M_2PI) for i in 1:32]
+    else
+        param = [ModulationNoOffsets{T}(complex(params[3, i], params[4, i]),
+                                        params[5, i], params[6, i], M_2PI) for i in 1:32]
+    end
+    return (Matrix{Complex{T}}(output), param, T.(chi2))
+end
+
+end # module
