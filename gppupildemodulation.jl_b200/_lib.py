@@ -80,6 +80,10 @@ def lib():
         H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
         C.c_void_p, _dp, C.c_int64, _dp, C.c_int64, C.POINTER(Options), C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    PP = C.POINTER(C.c_void_p)
+    L.gppd_process_tables_f32_dev.argtypes = [
+        H, C.c_int, C.c_void_p, C.c_int64, _i64p, _i64p, PP, _dp, PP, C.c_void_p,
+        C.POINTER(_dp), _i64p, C.POINTER(_dp), _i64p, C.POINTER(Options), PP, PP, PP, PP, PP]
     L.gppd_launch_count.restype = C.c_int64
     L.gppd_launch_count.argtypes = [H]
     L.gppd_enable_timing.argtypes = [H, C.c_int]
@@ -88,7 +92,8 @@ def lib():
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
-                 "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev", "gppd_enable_timing",
+                 "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",
+                 "gppd_process_tables_f32_dev", "gppd_enable_timing",
                  "gppd_pass_times", "gppd_measure_fp64_peak"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -137,7 +142,7 @@ class Handle:
     def num_slots(self) -> int:
         return int(lib().gppd_num_slots(self._h))
 
-    PASSES = ("segment", "basis", "stats", "fit", "demod", "export", "harmonics", "reserved")
+    PASSES = ("segment", "basis", "stats", "fit", "demod", "export", "harmonics", "fallback")
 
     def fp64_peak_tflops(self) -> float:
         v = C.c_double(0)

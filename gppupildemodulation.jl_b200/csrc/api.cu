@@ -1,8 +1,10 @@
 // api.cu -- the C ABI of libgppd.so (include/gppd.h): handle, pipeline slots,
-// host<->device staging and the launch sequence of one table.
+// host<->device staging and the launch sequence of one BATCH of tables.
 //
-// Launch sequence per table (all on the slot's stream, no host sync inside):
-//   [segmentation] -> basis -> [stats] -> fit -> demod -> export
+// Launch sequence per batch (all on one stream, no host synchronisation inside):
+//   [segmentation] -> basis -> [stats x2] -> harmonics -> harmonic fit
+//                  -> direct fit of flagged fits -> demod -> export
+// (method = direct: basis -> [stats] -> direct fit with HBM scratch -> demod -> export)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +79,7 @@ struct DevBuf {
 
 constexpr int NSLOTS = 4;
 constexpr int NPASS = GPPD_NPASS;
+constexpr int MAX_TIMER = 1 << 16;
 
 struct PassTimer {
     std::vector<cudaEvent_t> ev;      // begin/end pairs
@@ -84,18 +87,17 @@ struct PassTimer {
     double ms[NPASS] = {0};
     long long count[NPASS] = {0};
 };
-constexpr int MAX_TIMER = 1 << 16;
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    // staging of caller data
-    DevBuf time, volt, volt_out, t, data, out, state_in;
-    // scratch
-    DevBuf state, basis, z, y, thkeys, nvalid, jobs, stats, results;
-    DevBuf params, chi2, info, trace;
-    DevBuf timers, lb, events, flags, offsets;
+    // staging of caller data (host-buffer entry points)
+    DevBuf time, volt, volt_out, t, data, out, state_in, offsets;
+    DevBuf params, chi2, info, trace, state_out;
+    // batch scratch
+    DevBuf state, basis, z, y, thkeys, nvalid, jobs, results;
+    DevBuf spart1, spart2, partZ, partY, htab;
+    DevBuf timers, lb, events, flags, tabs, exps;
     PassTimer timer;
-    bool busy = false;
 };
 
 }  // namespace
@@ -109,7 +111,7 @@ struct gppd_handle_s {
 
 namespace {
 
-void fill_options(const gppd_options *o, FitOptions &f) {
+void fill_options(const gppd_options *o, FitOptions &f, int &method) {
     gppd_options d;
     memset(&d, 0, sizeof d);
     if (o) d = *o;
@@ -121,6 +123,7 @@ void fill_options(const gppd_options *o, FitOptions &f) {
     f.rhobeg = d.rhobeg > 0 ? d.rhobeg : 1.0;
     f.rhoend = d.rhoend > 0 ? d.rhoend : 1e-3;
     gppd_phirange(f.phi8);
+    method = d.method;
 }
 
 // cudaEvent pair around one pass (only when gppd_enable_timing is on)
@@ -128,7 +131,8 @@ struct PassScope {
     Slot *s;
     cudaStream_t st;
     bool on;
-    PassScope(gppd_handle h, Slot &slot, cudaStream_t stream, int pass) : s(&slot), st(stream), on(h->timing) {
+    PassScope(gppd_handle h, Slot &slot, cudaStream_t stream, int pass)
+        : s(&slot), st(stream), on(h->timing) {
         if (!on) return;
         cudaEvent_t a, b;
         cudaEventCreate(&a);
@@ -143,110 +147,228 @@ struct PassScope {
     }
 };
 
-struct RunArgs {
+// One table of a batch, as the entry points describe it (device pointers).
+struct TableArgs {
     TableView tv;
     OutView ov;
-    long long wrows;
-    const int8_t *d_state_in;  // device states or nullptr
-    const double *timer1, *timer2;  // host timers or nullptr
-    long long n1, n2;
-    double *d_params, *d_chi2;
-    int *d_info;
-    double *d_trace;
-    int8_t *d_state_out;  // where the states end up (may be nullptr)
+    long long wrows = 0;            // <= 0 or >= n: whole table
+    const int8_t *d_state_in = nullptr;
+    const double *timer1 = nullptr, *timer2 = nullptr;  // HOST timers
+    long long n1 = 0, n2 = 0, lag = 0;
+    double pre = 0.0, post = 0.0;
+    int8_t *d_state_out = nullptr;
+    double *d_params = nullptr, *d_chi2 = nullptr;
+    int *d_info = nullptr;
 };
 
-// Enqueue all passes of one table on `stream`.  Device pointers only.
-int run_table(gppd_handle h, Slot &s, cudaStream_t stream, RunArgs &a, const gppd_options *opt) {
+// Enqueue all passes of a batch on `stream`.  segment_only: stop after the
+// segmentation (gppd_buildstates).
+int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs> &tabs,
+              const gppd_options *opt, double *d_trace, bool segment_only) {
     FitOptions fo;
-    fill_options(opt, fo);
-    const long long n = a.tv.n;
-    if (n < 2) {
-        g_last_error = "need at least 2 rows";
-        return GPPD_ERR_ARG;
-    }
-    long long wrows = (a.wrows <= 0 || a.wrows >= n) ? n : a.wrows;
-    long long njobs_ll = (n + wrows - 1) / wrows;
-    if (njobs_ll * NDIODE > 0x7fffffffll || wrows > 0x7fffffffll) {
-        g_last_error = "too many windows / rows per window";
-        return GPPD_ERR_ARG;
-    }
-    int njobs = (int)njobs_ll, nfits = njobs * NDIODE;
+    int method;
+    fill_options(opt, fo, method);
+    const int T = (int)tabs.size();
+    if (T <= 0) return GPPD_OK;
     Launcher L{stream, &h->launches};
     int rc;
 
-    const int8_t *d_state = a.d_state_in;
-    if (!d_state && a.n1 > 0 && a.n2 > 0) {
-        if (a.n1 > MAX_TIMER || a.n2 > MAX_TIMER) {
-            g_last_error = "timer series too long";
+    // ---- plan ---------------------------------------------------------------
+    long long R = 0, max_rows = 0, njobs_ll = 0, max_wrows = 0;
+    int max_jobs = 0, max_timers = 0;
+    size_t ntimers = 0, nlb = 0, nevents = 0;
+    bool any_seg = false, any_state = false;
+    std::vector<TableDesc> td(T);
+    std::vector<ExportDesc> ex(T);
+    for (int t = 0; t < T; ++t) {
+        TableArgs &a = tabs[t];
+        const long long n = a.tv.n;
+        if (n < 2) {
+            g_last_error = "need at least 2 rows";
             return GPPD_ERR_ARG;
         }
-        int n1 = (int)a.n1, n2 = (int)a.n2;
-        int8_t *st = a.d_state_out;
-        if (!st) {
-            if ((rc = s.state.ensure((size_t)n))) return rc;
-            st = s.state.as<int8_t>();
+        const long long wrows = (a.wrows <= 0 || a.wrows >= n) ? n : a.wrows;
+        const long long nj = (n + wrows - 1) / wrows;
+        if (wrows > 0x7fffffffll || njobs_ll + nj > (0x7fffffffll / NDIODE)) {
+            g_last_error = "too many windows / rows per window";
+            return GPPD_ERR_ARG;
         }
-        if ((rc = s.timers.ensure(sizeof(double) * (size_t)(n1 + n2)))) return rc;
-        if ((rc = s.lb.ensure(sizeof(long long) * (size_t)(n1 + n2 + 2)))) return rc;
-        int max_events = n1 + n2 + 1024;
-        if ((rc = s.events.ensure((size_t)SEG_EVENT_BYTES * max_events))) return rc;
-        if ((rc = s.flags.ensure(2 * sizeof(int)))) return rc;
-        // small pageable copies: the runtime stages them before returning, so the
-        // caller's arrays may be reused at once and tables of one slot cannot race
-        CK(cudaMemcpyAsync(s.timers.p, a.timer1, sizeof(double) * (size_t)n1,
-                           cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(s.timers.as<double>() + n1, a.timer2, sizeof(double) * (size_t)n2,
-                           cudaMemcpyHostToDevice, stream));
-        {
-            PassScope ps(h, s, stream, GPPD_PASS_SEGMENT);
-            launch_segmentation(L, a.tv, s.timers.as<double>(), n1, s.timers.as<double>() + n1, n2,
-                                0, 0.0, 0.0, s.lb.as<long long>(), s.events.p, max_events,
-                                s.flags.as<int>(), st);
+        memset(&td[t], 0, sizeof(TableDesc));
+        td[t].tv = a.tv;
+        td[t].ov = a.ov;
+        td[t].wrows = wrows;
+        td[t].job0 = (int)njobs_ll;
+        td[t].njobs = (int)nj;
+        ex[t].fit0 = (int)njobs_ll * NDIODE;
+        ex[t].nfits = (int)nj * NDIODE;
+        ex[t].params = a.d_params;
+        ex[t].chi2 = a.d_chi2;
+        ex[t].info = a.d_info;
+        const bool seg = !a.d_state_in && a.n1 > 0 && a.n2 > 0;
+        if (seg) {
+            if (a.n1 > MAX_TIMER || a.n2 > MAX_TIMER) {
+                g_last_error = "timer series too long";
+                return GPPD_ERR_ARG;
+            }
+            any_seg = true;
+            ntimers += (size_t)(a.n1 + a.n2);
+            nlb += (size_t)(a.n1 + a.n2 + 2);
+            nevents += (size_t)(a.n1 + a.n2 + 1024);
+            if (a.n1 + a.n2 > max_timers) max_timers = (int)(a.n1 + a.n2);
         }
-        DBG(stream, "segmentation");
-        d_state = st;
-    } else if (d_state && a.d_state_out && a.d_state_out != d_state) {
-        CK(cudaMemcpyAsync(a.d_state_out, d_state, (size_t)n, cudaMemcpyDeviceToDevice, stream));
+        if (seg || a.d_state_in) any_state = true;
+        R += n;
+        njobs_ll += nj;
+        if (n > max_rows) max_rows = n;
+        if (wrows > max_wrows) max_wrows = wrows;
+        if (nj > max_jobs) max_jobs = (int)nj;
+    }
+    const int njobs = (int)njobs_ll, nfits = njobs * NDIODE, njg = njobs * NGROUP;
+    const bool offs = (fo.flags & GPPD_FITOFFSETS) != 0;
+    const bool direct = method == GPPD_METHOD_DIRECT;
+
+    // partial sums are taken over FIXED row segments of each job (so that a fit's
+    // result does not depend on the rest of the batch); P / SP = segments of the
+    // longest job = grid width and stride of the partial buffers
+    const int P = harm_max_segments(max_wrows);
+    const int SP = stats_max_segments(max_wrows);
+
+    // ---- scratch ------------------------------------------------------------
+    if ((rc = s.tabs.ensure(sizeof(TableDesc) * (size_t)T))) return rc;
+    if ((rc = s.exps.ensure(sizeof(ExportDesc) * (size_t)T))) return rc;
+    if ((rc = s.basis.ensure(sizeof(double2) * (size_t)R))) return rc;
+    if (any_seg) {
+        if ((rc = s.state.ensure((size_t)R))) return rc;
+        if ((rc = s.timers.ensure(sizeof(double) * ntimers))) return rc;
+        if ((rc = s.lb.ensure(sizeof(long long) * nlb))) return rc;
+        if ((rc = s.events.ensure((size_t)SEG_EVENT_BYTES * nevents))) return rc;
+        if ((rc = s.flags.ensure(2 * sizeof(int) * (size_t)T))) return rc;
+    }
+    if (!segment_only) {
+        if ((rc = s.thkeys.ensure(sizeof(unsigned long long) * 2 * (size_t)njobs))) return rc;
+        if ((rc = s.nvalid.ensure(sizeof(int) * (size_t)njobs))) return rc;
+        if ((rc = s.jobs.ensure(sizeof(JobInfo) * (size_t)njobs))) return rc;
+        if ((rc = s.results.ensure(sizeof(FitResult) * (size_t)nfits))) return rc;
+        if (any_state) {
+            if ((rc = s.spart1.ensure(sizeof(double) * STATS_VALS * (size_t)njg * SP))) return rc;
+            if ((rc = s.spart2.ensure(sizeof(double) * 16 * (size_t)njg * SP))) return rc;
+        }
+        if (direct) {
+            if ((rc = s.z.ensure(sizeof(double2) * (size_t)R * NDIODE))) return rc;
+            if (offs)
+                if ((rc = s.y.ensure(sizeof(double2) * (size_t)R * NDIODE))) return rc;
+        } else {
+            if ((rc = s.partZ.ensure(sizeof(double) * HP_Z * 4 * (size_t)njg * P))) return rc;
+            if (offs)
+                if ((rc = s.partY.ensure(sizeof(double) * HP_Y * 4 * (size_t)njg * P))) return rc;
+            if ((rc = s.htab.ensure(sizeof(double) * HV_COUNT * (size_t)nfits))) return rc;
+        }
     }
 
-    if ((rc = s.basis.ensure(sizeof(double2) * (size_t)n))) return rc;
-    if ((rc = s.thkeys.ensure(sizeof(unsigned long long) * 2 * (size_t)njobs))) return rc;
-    if ((rc = s.nvalid.ensure(sizeof(int) * (size_t)njobs))) return rc;
-    if ((rc = s.jobs.ensure(sizeof(JobInfo) * (size_t)njobs))) return rc;
-    if ((rc = s.results.ensure(sizeof(FitResult) * (size_t)nfits))) return rc;
-    if ((rc = s.z.ensure(sizeof(double2) * (size_t)n * NDIODE))) return rc;
-    if (fo.flags & GPPD_FITOFFSETS)
-        if ((rc = s.y.ensure(sizeof(double2) * (size_t)n * NDIODE))) return rc;
-    if (d_state)
-        if ((rc = s.stats.ensure(sizeof(double2) * 4 * (size_t)nfits))) return rc;
+    // ---- carve per-table slices, upload descriptors ---------------------------
+    {
+        size_t row_off = 0, tim_off = 0, lb_off = 0, ev_off = 0;
+        for (int t = 0; t < T; ++t) {
+            TableArgs &a = tabs[t];
+            TableDesc &d = td[t];
+            const long long n = a.tv.n;
+            d.basis = s.basis.as<double2>() + row_off;
+            if (direct && !segment_only) {
+                d.z = s.z.as<double2>() + row_off * NDIODE;
+                d.y = offs ? s.y.as<double2>() + row_off * NDIODE : nullptr;
+            }
+            const bool seg = !a.d_state_in && a.n1 > 0 && a.n2 > 0;
+            if (seg) {
+                d.state = a.d_state_out ? a.d_state_out : s.state.as<int8_t>() + row_off;
+                d.seg.timer1 = s.timers.as<double>() + tim_off;
+                d.seg.timer2 = d.seg.timer1 + a.n1;
+                d.seg.n1 = (int)a.n1;
+                d.seg.n2 = (int)a.n2;
+                d.seg.lag = a.lag;
+                d.seg.pre = a.pre;
+                d.seg.post = a.post;
+                d.seg.lb = s.lb.as<long long>() + lb_off;
+                d.seg.events = s.events.as<char>() + ev_off * SEG_EVENT_BYTES;
+                d.seg.max_events = (int)(a.n1 + a.n2 + 1024);
+                d.seg.flags = s.flags.as<int>() + 2 * t;
+                // small pageable copies are staged by the runtime before returning
+                CK(cudaMemcpyAsync((void *)d.seg.timer1, a.timer1, sizeof(double) * (size_t)a.n1,
+                                   cudaMemcpyHostToDevice, stream));
+                CK(cudaMemcpyAsync((void *)d.seg.timer2, a.timer2, sizeof(double) * (size_t)a.n2,
+                                   cudaMemcpyHostToDevice, stream));
+                tim_off += (size_t)(a.n1 + a.n2);
+                lb_off += (size_t)(a.n1 + a.n2 + 2);
+                ev_off += (size_t)(a.n1 + a.n2 + 1024);
+            } else if (a.d_state_in) {
+                d.state = const_cast<int8_t *>(a.d_state_in);
+                if (a.d_state_out && a.d_state_out != a.d_state_in)
+                    CK(cudaMemcpyAsync(a.d_state_out, a.d_state_in, (size_t)n,
+                                       cudaMemcpyDeviceToDevice, stream));
+            }
+            row_off += (size_t)n;
+        }
+        CK(cudaMemcpyAsync(s.tabs.p, td.data(), sizeof(TableDesc) * (size_t)T,
+                           cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(s.exps.p, ex.data(), sizeof(ExportDesc) * (size_t)T,
+                           cudaMemcpyHostToDevice, stream));
+    }
+    const TableDesc *d_tabs = s.tabs.as<TableDesc>();
 
+    // ---- launch sequence ------------------------------------------------------
+    if (any_seg) {
+        PassScope ps(h, s, stream, GPPD_PASS_SEGMENT);
+        launch_segmentation(L, d_tabs, T, max_rows, max_timers);
+    }
+    DBG(stream, "segmentation");
+    if (segment_only) {
+        CK(cudaGetLastError());
+        return GPPD_OK;
+    }
     {
         PassScope ps(h, s, stream, GPPD_PASS_BASIS);
-        launch_basis(L, a.tv, wrows, njobs, d_state, fo.flags, s.basis.as<double2>(),
+        launch_basis(L, d_tabs, T, max_rows, max_jobs, njobs, fo.flags,
                      s.thkeys.as<unsigned long long>(), s.nvalid.as<int>(), s.jobs.as<JobInfo>());
     }
     DBG(stream, "basis");
-    if (d_state) {
+    if (any_state) {
         PassScope ps(h, s, stream, GPPD_PASS_STATS);
-        launch_stats(L, a.tv, njobs, s.jobs.as<JobInfo>(), d_state, fo.flags, s.stats.as<double2>());
+        launch_stats(L, d_tabs, s.jobs.as<JobInfo>(), njobs, fo.flags, SP, s.spart1.as<double>(),
+                     s.spart2.as<double>());
     }
     DBG(stream, "stats");
-    {
+    if (direct) {
         PassScope ps(h, s, stream, GPPD_PASS_FIT);
-        launch_fit_direct(L, a.tv, nfits, s.jobs.as<JobInfo>(), d_state, s.stats.as<double2>(),
-                          s.basis.as<double2>(), s.z.as<double2>(), s.y.as<double2>(), fo, nullptr,
-                          s.results.as<FitResult>(), a.d_trace);
+        launch_fit_direct(L, d_tabs, s.jobs.as<JobInfo>(), nfits, SP, s.spart1.as<double>(),
+                          s.spart2.as<double>(), fo, true, s.results.as<FitResult>(), d_trace);
+    } else {
+        {
+            PassScope ps(h, s, stream, GPPD_PASS_HARMONICS);
+            launch_harmonics(L, d_tabs, s.jobs.as<JobInfo>(), njobs, fo.flags, P, SP,
+                             s.spart1.as<double>(), s.spart2.as<double>(), s.partZ.as<double>(),
+                             s.partY.as<double>(), s.htab.as<double>());
+        }
+        DBG(stream, "harmonics");
+        {
+            PassScope ps(h, s, stream, GPPD_PASS_FIT);
+            launch_fit_harmonic(L, d_tabs, s.jobs.as<JobInfo>(), s.htab.as<double>(), nfits, fo,
+                                s.results.as<FitResult>(), d_trace);
+        }
+        DBG(stream, "fit_harmonic");
+        {
+            PassScope ps(h, s, stream, GPPD_PASS_FALLBACK);
+            launch_fit_direct(L, d_tabs, s.jobs.as<JobInfo>(), nfits, SP, s.spart1.as<double>(),
+                              s.spart2.as<double>(), fo, false, s.results.as<FitResult>(), d_trace);
+        }
     }
     DBG(stream, "fit_direct");
     {
         PassScope ps(h, s, stream, GPPD_PASS_DEMOD);
-        launch_demod(L, a.tv, a.ov, wrows, s.basis.as<double2>(), s.results.as<FitResult>(), fo.flags);
+        launch_demod(L, d_tabs, T, max_rows, s.results.as<FitResult>(), fo.flags);
     }
     DBG(stream, "demod");
     {
         PassScope ps(h, s, stream, GPPD_PASS_EXPORT);
-        launch_export(L, nfits, s.results.as<FitResult>(), a.d_params, a.d_chi2, a.d_info);
+        launch_export(L, s.exps.as<ExportDesc>(), T, max_jobs * NDIODE, s.results.as<FitResult>());
     }
     DBG(stream, "export");
     CK(cudaGetLastError());
@@ -260,6 +382,26 @@ int check_handle(gppd_handle h) {
     }
     CK(cudaSetDevice(h->device));
     return GPPD_OK;
+}
+
+void table_views(int64_t n, double mjd, const int32_t *d_time, const float *d_volt,
+                 const double *d_offsets, float *d_volt_out, uint32_t flags, TableArgs &a) {
+    memset(&a.tv, 0, sizeof a.tv);
+    memset(&a.ov, 0, sizeof a.ov);
+    a.tv.kind = 0;
+    a.tv.big_endian = (flags & GPPD_BIG_ENDIAN) ? 1 : 0;
+    a.tv.n = n;
+    a.tv.time_us = d_time;
+    a.tv.time_stride = 4;
+    a.tv.volt = d_volt;
+    a.tv.volt_stride = 320;
+    a.tv.tmjd = 86400.0 * mjd;   // DAY_TO_SEC * mjd
+    a.tv.offsets = reinterpret_cast<const double2 *>(d_offsets);
+    a.ov.kind = 0;
+    a.ov.big_endian = a.tv.big_endian;
+    a.ov.keepraw = (flags & GPPD_KEEPRAW) ? 1 : 0;
+    a.ov.volt = d_volt_out;
+    a.ov.volt_stride = a.ov.keepraw ? 576 : 320;
 }
 
 }  // namespace
@@ -343,10 +485,12 @@ int gppd_destroy(gppd_handle h) {
             cudaStreamDestroy(s.stream);
         }
         DevBuf *bufs[] = {&s.time, &s.volt, &s.volt_out, &s.t, &s.data, &s.out, &s.state_in,
+                          &s.offsets, &s.params, &s.chi2, &s.info, &s.trace, &s.state_out,
                           &s.state, &s.basis, &s.z, &s.y, &s.thkeys, &s.nvalid, &s.jobs,
-                          &s.stats, &s.results, &s.params, &s.chi2, &s.info, &s.trace,
-                          &s.timers, &s.lb, &s.events, &s.flags, &s.offsets};
+                          &s.results, &s.spart1, &s.spart2, &s.partZ, &s.partY, &s.htab,
+                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps};
         for (DevBuf *b : bufs) b->release();
+        for (cudaEvent_t e : s.timer.ev) cudaEventDestroy(e);
     }
     delete h;
     return GPPD_OK;
@@ -441,28 +585,27 @@ int gppd_buildstates(gppd_handle h, int64_t n, const double *t, const double *ti
     }
     Slot &s = h->slots[0];
     cudaStream_t st = s.stream;
+    CK(cudaStreamSynchronize(st));
     if ((rc = s.t.ensure(sizeof(double) * (size_t)n))) return rc;
-    if ((rc = s.state.ensure((size_t)n))) return rc;
-    if ((rc = s.timers.ensure(sizeof(double) * (size_t)(n1 + n2)))) return rc;
-    if ((rc = s.lb.ensure(sizeof(long long) * (size_t)(n1 + n2 + 2)))) return rc;
-    int max_events = (int)(n1 + n2) + 1024;
-    if ((rc = s.events.ensure((size_t)SEG_EVENT_BYTES * max_events))) return rc;
-    if ((rc = s.flags.ensure(2 * sizeof(int)))) return rc;
+    if ((rc = s.state_out.ensure((size_t)n))) return rc;
     CK(cudaMemcpyAsync(s.t.p, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.timers.p, timer1, sizeof(double) * (size_t)n1, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.timers.as<double>() + n1, timer2, sizeof(double) * (size_t)n2,
-                       cudaMemcpyHostToDevice, st));
-    TableView tv;
-    memset(&tv, 0, sizeof tv);
-    tv.kind = 1;
-    tv.n = n;
-    tv.t = s.t.as<double>();
-    Launcher L{st, &h->launches};
-    launch_segmentation(L, tv, s.timers.as<double>(), (int)n1, s.timers.as<double>() + n1, (int)n2,
-                        lag, pre, post, s.lb.as<long long>(), s.events.p, max_events,
-                        s.flags.as<int>(), s.state.as<int8_t>());
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(state_out, s.state.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    std::vector<TableArgs> tabs(1);
+    TableArgs &a = tabs[0];
+    memset(&a.tv, 0, sizeof a.tv);
+    memset(&a.ov, 0, sizeof a.ov);
+    a.tv.kind = 1;
+    a.tv.n = n;
+    a.tv.t = s.t.as<double>();
+    a.timer1 = timer1;
+    a.timer2 = timer2;
+    a.n1 = n1;
+    a.n2 = n2;
+    a.lag = lag;
+    a.pre = pre;
+    a.post = post;
+    a.d_state_out = s.state_out.as<int8_t>();
+    if ((rc = run_batch(h, s, st, tabs, nullptr, nullptr, true))) return rc;
+    CK(cudaMemcpyAsync(state_out, s.state_out.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return GPPD_OK;
 }
@@ -480,6 +623,7 @@ int gppd_demodulate_f64(gppd_handle h, int64_t n, int64_t nwindow, const double 
     }
     Slot &s = h->slots[0];
     cudaStream_t st = s.stream;
+    CK(cudaStreamSynchronize(st));
     int64_t nwin = gppd_num_windows(n, nwindow);
     size_t nfits = (size_t)nwin * NDIODE;
     size_t cbytes = sizeof(double) * 2 * NCHAN * (size_t)n;
@@ -498,8 +642,10 @@ int gppd_demodulate_f64(gppd_handle h, int64_t n, int64_t nwindow, const double 
     if (state) CK(cudaMemcpyAsync(s.state_in.p, state, (size_t)n, cudaMemcpyHostToDevice, st));
     if (trace) CK(cudaMemsetAsync(s.trace.p, 0, sizeof(double) * 3 * GPPD_TRACE_MAX * nfits, st));
 
-    RunArgs a;
-    memset(&a, 0, sizeof a);
+    std::vector<TableArgs> tabs(1);
+    TableArgs &a = tabs[0];
+    memset(&a.tv, 0, sizeof a.tv);
+    memset(&a.ov, 0, sizeof a.ov);
     a.tv.kind = 1;
     a.tv.n = n;
     a.tv.t = s.t.as<double>();
@@ -511,8 +657,8 @@ int gppd_demodulate_f64(gppd_handle h, int64_t n, int64_t nwindow, const double 
     a.d_params = s.params.as<double>();
     a.d_chi2 = s.chi2.as<double>();
     a.d_info = s.info.as<int>();
-    a.d_trace = trace ? s.trace.as<double>() : nullptr;
-    if ((rc = run_table(h, s, st, a, opt))) return rc;
+    if ((rc = run_batch(h, s, st, tabs, opt, trace ? s.trace.as<double>() : nullptr, false)))
+        return rc;
 
     CK(cudaMemcpyAsync(out, s.out.p, cbytes, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(params, s.params.p, sizeof(double) * 6 * nfits, cudaMemcpyDeviceToHost, st));
@@ -555,26 +701,6 @@ int gppd_table_windows(int64_t n, const int32_t *time_us, double mjd, double win
     return GPPD_OK;
 }
 
-static int table_views(int64_t n, double mjd, const int32_t *d_time, const float *d_volt,
-                       const double *d_offsets, float *d_volt_out, uint32_t flags, RunArgs &a) {
-    memset(&a, 0, sizeof a);
-    a.tv.kind = 0;
-    a.tv.big_endian = (flags & GPPD_BIG_ENDIAN) ? 1 : 0;
-    a.tv.n = n;
-    a.tv.time_us = d_time;
-    a.tv.time_stride = 4;
-    a.tv.volt = d_volt;
-    a.tv.volt_stride = 320;
-    a.tv.tmjd = 86400.0 * mjd;
-    a.tv.offsets = reinterpret_cast<const double2 *>(d_offsets);
-    a.ov.kind = 0;
-    a.ov.big_endian = a.tv.big_endian;
-    a.ov.keepraw = (flags & GPPD_KEEPRAW) ? 1 : 0;
-    a.ov.volt = d_volt_out;
-    a.ov.volt_stride = a.ov.keepraw ? 576 : 320;
-    return GPPD_OK;
-}
-
 int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n, const int32_t *time_us,
                           double mjd, const float *volt, const double *offsets,
                           const double *timer1, int64_t n1, const double *timer2, int64_t n2,
@@ -605,34 +731,35 @@ int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n, const int32_t *tim
     if ((rc = s.params.ensure(sizeof(double) * 6 * nfits))) return rc;
     if ((rc = s.chi2.ensure(sizeof(double) * nfits))) return rc;
     if ((rc = s.info.ensure(sizeof(int) * GPPD_INFO_STRIDE * nfits))) return rc;
-    if ((rc = s.state.ensure((size_t)n))) return rc;
+    if ((rc = s.state_out.ensure((size_t)n))) return rc;
     if ((rc = s.offsets.ensure(sizeof(double) * 80))) return rc;
     CK(cudaMemcpyAsync(s.time.p, time_us, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s.volt.p, volt, vbytes, cudaMemcpyHostToDevice, st));
     if (offsets)
         CK(cudaMemcpyAsync(s.offsets.p, offsets, sizeof(double) * 80, cudaMemcpyHostToDevice, st));
-    RunArgs a;
+    std::vector<TableArgs> tabs(1);
+    TableArgs &a = tabs[0];
     table_views(n, mjd, s.time.as<int32_t>(), s.volt.as<float>(),
                 offsets ? s.offsets.as<double>() : nullptr, s.volt_out.as<float>(), o.flags, a);
     a.wrows = wrows;
+    const bool faint = timer1 && timer2 && n1 > 0 && n2 > 0;
     a.timer1 = timer1;
     a.timer2 = timer2;
-    a.n1 = (timer1 && timer2) ? n1 : 0;
-    a.n2 = (timer1 && timer2) ? n2 : 0;
+    a.n1 = faint ? n1 : 0;
+    a.n2 = faint ? n2 : 0;
     a.d_params = s.params.as<double>();
     a.d_chi2 = s.chi2.as<double>();
     a.d_info = s.info.as<int>();
-    a.d_state_out = s.state.as<int8_t>();
-    if ((rc = run_table(h, s, st, a, &o))) return rc;
+    a.d_state_out = s.state_out.as<int8_t>();
+    if ((rc = run_batch(h, s, st, tabs, &o, nullptr, false))) return rc;
     CK(cudaMemcpyAsync(volt_out, s.volt_out.p, obytes, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(params, s.params.p, sizeof(double) * 6 * nfits, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(chi2, s.chi2.p, sizeof(double) * nfits, cudaMemcpyDeviceToHost, st));
     if (info)
         CK(cudaMemcpyAsync(info, s.info.p, sizeof(int) * GPPD_INFO_STRIDE * nfits,
                            cudaMemcpyDeviceToHost, st));
-    if (state_out && a.n1 > 0)
-        CK(cudaMemcpyAsync(state_out, s.state.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    s.busy = true;
+    if (state_out && faint)
+        CK(cudaMemcpyAsync(state_out, s.state_out.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     return GPPD_OK;
 }
 
@@ -641,7 +768,6 @@ int gppd_wait(gppd_handle h, int slot) {
     if (rc) return rc;
     if (slot < 0 || slot >= NSLOTS) return GPPD_ERR_ARG;
     CK(cudaStreamSynchronize(h->slots[slot].stream));
-    h->slots[slot].busy = false;
     return GPPD_OK;
 }
 
@@ -656,18 +782,20 @@ int gppd_process_table_f32(gppd_handle h, int64_t n, const int32_t *time_us, dou
     return gppd_wait(h, 0);
 }
 
-int gppd_process_table_f32_dev(gppd_handle h, int slot, void *stream, int64_t n,
-                               int64_t nwindow_rows, const int32_t *d_time_us, double mjd,
-                               const float *d_volt, const double *d_offsets,
-                               const double *timer1, int64_t n1, const double *timer2,
-                               int64_t n2, const gppd_options *opt, float *d_volt_out,
-                               double *d_params, double *d_chi2, int32_t *d_info,
-                               int8_t *d_state_out) {
+int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t ntables,
+                                const int64_t *n, const int64_t *nwindow_rows,
+                                const int32_t *const *d_time_us, const double *mjd,
+                                const float *const *d_volt, const double *d_offsets,
+                                const double *const *timer1, const int64_t *n1,
+                                const double *const *timer2, const int64_t *n2,
+                                const gppd_options *opt, float *const *d_volt_out,
+                                double *const *d_params, double *const *d_chi2,
+                                int32_t *const *d_info, int8_t *const *d_state_out) {
     int rc = check_handle(h);
     if (rc) return rc;
-    if (slot < 0 || slot >= NSLOTS || !d_time_us || !d_volt || !d_volt_out || !d_params ||
-        !d_chi2 || n < 2) {
-        g_last_error = "process_table_f32_dev: bad slot, null buffer or n < 2";
+    if (slot < 0 || slot >= NSLOTS || ntables < 1 || !n || !d_time_us || !mjd || !d_volt ||
+        !d_volt_out || !d_params || !d_chi2) {
+        g_last_error = "process_tables_f32_dev: bad slot or null array";
         return GPPD_ERR_ARG;
     }
     gppd_options o;
@@ -677,18 +805,41 @@ int gppd_process_table_f32_dev(gppd_handle h, int slot, void *stream, int64_t n,
     else o.flags &= ~GPPD_FITOFFSETS;
     Slot &s = h->slots[slot];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-    RunArgs a;
-    table_views(n, mjd, d_time_us, d_volt, d_offsets, d_volt_out, o.flags, a);
-    a.wrows = nwindow_rows;
-    a.timer1 = timer1;
-    a.timer2 = timer2;
-    a.n1 = (timer1 && timer2) ? n1 : 0;
-    a.n2 = (timer1 && timer2) ? n2 : 0;
-    a.d_params = d_params;
-    a.d_chi2 = d_chi2;
-    a.d_info = d_info;
-    a.d_state_out = d_state_out;
-    return run_table(h, s, st, a, &o);
+    std::vector<TableArgs> tabs((size_t)ntables);
+    for (int64_t t = 0; t < ntables; ++t) {
+        TableArgs &a = tabs[(size_t)t];
+        if (!d_time_us[t] || !d_volt[t] || !d_volt_out[t] || !d_params[t] || !d_chi2[t] ||
+            n[t] < 2) {
+            g_last_error = "process_tables_f32_dev: null table buffer or n < 2";
+            return GPPD_ERR_ARG;
+        }
+        table_views(n[t], mjd[t], d_time_us[t], d_volt[t], d_offsets, d_volt_out[t], o.flags, a);
+        a.wrows = nwindow_rows ? nwindow_rows[t] : 0;
+        const bool faint = timer1 && timer2 && n1 && n2 && timer1[t] && timer2[t] && n1[t] > 0 &&
+                           n2[t] > 0;
+        a.timer1 = faint ? timer1[t] : nullptr;
+        a.timer2 = faint ? timer2[t] : nullptr;
+        a.n1 = faint ? n1[t] : 0;
+        a.n2 = faint ? n2[t] : 0;
+        a.d_params = d_params[t];
+        a.d_chi2 = d_chi2[t];
+        a.d_info = d_info ? d_info[t] : nullptr;
+        a.d_state_out = d_state_out ? d_state_out[t] : nullptr;
+    }
+    return run_batch(h, s, st, tabs, &o, nullptr, false);
+}
+
+int gppd_process_table_f32_dev(gppd_handle h, int slot, void *stream, int64_t n,
+                               int64_t nwindow_rows, const int32_t *d_time_us, double mjd,
+                               const float *d_volt, const double *d_offsets,
+                               const double *timer1, int64_t n1, const double *timer2,
+                               int64_t n2, const gppd_options *opt, float *d_volt_out,
+                               double *d_params, double *d_chi2, int32_t *d_info,
+                               int8_t *d_state_out) {
+    return gppd_process_tables_f32_dev(h, slot, stream, 1, &n, &nwindow_rows, &d_time_us, &mjd,
+                                       &d_volt, d_offsets, &timer1, &n1, &timer2, &n2, opt,
+                                       &d_volt_out, &d_params, &d_chi2, d_info ? &d_info : nullptr,
+                                       d_state_out ? &d_state_out : nullptr);
 }
 
 }  // extern "C"

@@ -6,16 +6,27 @@
 // oracle's floating-point steps (see newuoa2.cuh).  Hot loops therefore spell
 // out their fused multiply-adds with fma().
 //
-// Direct evaluator (this file, k_fit_direct): one thread block per fit.
-//   prologue  z_n = w_n conj(p_n) (d_n - mu),  y_n = w_n p_n  -> HBM scratch,
-//             constant sums S_w, S_d, S_dd, S_gg         (p = power * FCphasor)
-//   per objective call, one pass over the rows (16 B basis + 16 B z per row):
-//             e_n = exp(j b sin(theta_n + q));  S_gd = sum conj(e_n) z_n
-//             [offsets: S_g = sum e_n y_n]
-//             (c, a) in closed form, chi2 = (S_dd - Re(conj(c) S_d + conj(a) S_gd)) / N
-//   which is the reference's  sum w |c + a g - d|^2 / N  at its own least-squares
-//   (c, a), with g = p e.  Reductions run in a fixed order (deterministic).
+// Two evaluators of chi2(b, phi) drive the same fit procedure (fit_driver.cuh):
+//
+//  k_fit_harmonic  one THREAD per fit.  chi2 from the per-fit harmonic table
+//                  (harm_kernels.cu): S_gd = sum_k J_k(b) e^{-jkq} Z_k in O(HK)
+//                  flops per call.  All fits of a warp evaluate in lock step
+//                  (the solver is a resumable state machine), the solver algebra
+//                  in between diverges.  Gives up (fallback flag) when |b| > 5 or
+//                  the job has no uniform phase quantum for the requested phi.
+//
+//  k_fit_direct    one BLOCK per fit, the reference's own formulation: one pass
+//                  over the rows per objective call,
+//                      e_n = exp(j b sin(theta_n + q)),  S_gd = sum conj(e_n) z_n
+//                  with z_n = w_n conj(p_n)(d_n - mu) either staged in HBM scratch
+//                  (method = direct) or recomputed from the table (fallback of
+//                  the harmonic path: no scratch needed).  Fixed-order block
+//                  reductions (deterministic).
+//
+// Both compute chi2 = (S_dd - Re(conj(c') S_d' + conj(a) S_gd)) / N, the
+// reference's sum w |c + a g - d|^2 / N at its own least-squares (c, a).
 #include "fit_driver.cuh"
+#include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
 
@@ -44,119 +55,247 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *red /* [N
     }
 }
 
-// Constant (b, phi independent) sums of one fit.
-struct FitConsts {
-    double sw, sdd, sgg;   // sum w, sum w|d-mu|^2, sum w |p|^2
-    double sdr, sdi;       // sum w (d - mu)
-    double mur, mui;       // mu = weighted mean of d (offsets mode), else 0
-    double nvalid;
-};
+__device__ __forceinline__ void store_result(FitResult *results, int fit, const FitDriver &drv,
+                                             const JobInfo &ji, double cre, double cim, double are,
+                                             double aim, int method) {
+    FitResult r;
+    r.cre = cre; r.cim = cim; r.are = are; r.aim = aim;
+    r.b = drv.b; r.phi = drv.phi;
+    r.alpha = atan2(aim, are);
+    r.chi2 = drv.chi2;
+    PhaseQ pq = make_phaseq(drv.phi, ji.thmin, ji.thmax);
+    r.q = pq.q; r.cq = pq.cq; r.sq = pq.sq; r.uniform = pq.uniform;
+    r.nfev = drv.nfev; r.status = drv.status; r.method = method; r.second = drv.second;
+    r.fallback = 0; r.pad = 0;
+    results[fit] = r;
+}
 
-// Linear parameters and chi2 from the sums (reference :140-145, :174-215, :325).
-// Offsets mode solves the centred system, c = c' + mu.
-__device__ __forceinline__ double solve_linear(const FitConsts &k, bool offs, double sgdr,
-                                               double sgdi, double sgr, double sgi, double &cre,
-                                               double &cim, double &are, double &aim) {
-    if (!offs) {
-        // a = (mw . d) / (mw . model) with mw . model = sum w |g|^2 (real)
-        are = sgdr / k.sgg;
-        aim = sgdi / k.sgg;
-        cre = 0.0;
-        cim = 0.0;
-        double num = fma(sgdr, sgdr, sgdi * sgdi);
-        return (k.sdd - num / k.sgg) / k.nvalid;
+// ===========================================================================
+// Harmonic evaluator: one thread per fit
+// ===========================================================================
+// Phase quantum usable by the harmonic form: the job's uniform q, or phi itself
+// when every |theta| < 4096 (ulp <= 2^-41: the per-row rounding of theta + phi
+// is below 2.3e-13 rad and is neglected).
+__device__ __forceinline__ bool harm_quantum(double phi, const JobInfo &ji, double &q) {
+    PhaseQ pq = make_phaseq(phi, ji.thmin, ji.thmax);
+    if (pq.uniform) {
+        q = pq.q;
+        return true;
     }
-    // [sw  S_g; conj(S_g)  sgg] [c'; a] = [S_d'; S_gd]   (Cramer, StaticArrays 2x2)
-    double det = fma(k.sw, k.sgg, -fma(sgr, sgr, sgi * sgi));
-    // c' = (sgg S_d' - S_g S_gd) / det
-    double t1r = fma(sgr, sgdr, -(sgi * sgdi)), t1i = fma(sgr, sgdi, sgi * sgdr);
-    double cpr = (k.sgg * k.sdr - t1r) / det, cpi = (k.sgg * k.sdi - t1i) / det;
-    // a = (sw S_gd - conj(S_g) S_d') / det
-    double t2r = fma(sgr, k.sdr, sgi * k.sdi), t2i = fma(sgr, k.sdi, -(sgi * k.sdr));
-    are = (k.sw * sgdr - t2r) / det;
-    aim = (k.sw * sgdi - t2i) / det;
-    cre = cpr + k.mur;
-    cim = cpi + k.mui;
-    // chi2 N = S_dd - Re(conj(c') S_d' + conj(a) S_gd)
-    double proj = fma(cpr, k.sdr, cpi * k.sdi) + fma(are, sgdr, aim * sgdi);
-    return (k.sdd - proj) / k.nvalid;
+    if (fabs(ji.thmin) < 4096.0 && fabs(ji.thmax) < 4096.0 && fabs(phi) < 4096.0) {
+        q = phi;
+        return true;
+    }
+    return false;
 }
 
 template <bool OFFS>
-__global__ void __launch_bounds__(FIT_THREADS)
-k_fit_direct(TableView tv, const JobInfo *jobs, const int8_t *state, const double2 *stats,
-             const double2 *basis, double2 *zbuf, double2 *ybuf, FitOptions opt,
-             const int *fit_list, FitResult *results, double *trace) {
-    __shared__ double red[5 * 8];
-    const int fit = fit_list ? fit_list[blockIdx.x] : blockIdx.x;
-    const int job = fit / NDIODE, ch = fit % NDIODE;
-    const int fcch = fc_channel(ch / 4);
-    const JobInfo ji = jobs[job];
-    const unsigned flags = opt.flags;
-    double2 *z = zbuf + (long long)ch * tv.n + ji.row0;
-    double2 *y = OFFS ? ybuf + (long long)ch * tv.n + ji.row0 : nullptr;
-    const double2 *bas = basis + ji.row0;
+__device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const FitConsts &kc,
+                                              const JobInfo &ji, double b, double phi, double &f,
+                                              double &cre, double &cim, double &are, double &aim) {
+    double q;
+    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;
+    double J[HK + 1];
+    bessel_j(b, J);
+    double sq, cq;
+    sincos(q, &sq, &cq);
+    double sgdr = J[0] * H[(long long)HV_Z0R * nfits], sgdi = J[0] * H[(long long)HV_Z0I * nfits];
+    double sgr = 0.0, sgi = 0.0;
+    if (OFFS) {
+        sgr = J[0] * H[(long long)HV_Y0R * nfits];
+        sgi = J[0] * H[(long long)HV_Y0I * nfits];
+    }
+    double ck = 1.0, sk = 0.0;
+#pragma unroll 1
+    for (int k = 1; k <= HK; ++k) {
+        // (ck, sk) <- (cos kq, sin kq)
+        double cn = fma(ck, cq, -(sk * sq)), sn = fma(sk, cq, ck * sq);
+        ck = cn;
+        sk = sn;
+        const double tj = 2.0 * J[k];
+        const double *z = H + (long long)(HV_ZK + 4 * (k - 1)) * nfits;
+        const double A = z[0], B = z[nfits], C = z[2 * (long long)nfits], D = z[3 * (long long)nfits];
+        if ((k & 1) == 0) {
+            sgdr = fma(tj, fma(ck, A, -(sk * D)), sgdr);
+            sgdi = fma(tj, fma(ck, C, -(sk * B)), sgdi);
+        } else {
+            sgdr = fma(tj, fma(ck, B, sk * C), sgdr);
+            sgdi = fma(tj, -fma(ck, D, sk * A), sgdi);
+        }
+        if (OFFS) {
+            const double *y = H + (long long)(HV_YK + 4 * (k - 1)) * nfits;
+            const double Ay = y[0], By = y[nfits], Cy = y[2 * (long long)nfits],
+                         Dy = y[3 * (long long)nfits];
+            if ((k & 1) == 0) {
+                sgr = fma(tj, fma(ck, Ay, -(sk * Dy)), sgr);
+                sgi = fma(tj, fma(ck, Cy, -(sk * By)), sgi);
+            } else {
+                sgr = fma(tj, -fma(ck, By, sk * Cy), sgr);
+                sgi = fma(tj, fma(ck, Dy, sk * Ay), sgi);
+            }
+        }
+    }
+    f = solve_linear(kc, OFFS, sgdr, sgdi, sgr, sgi, cre, cim, are, aim);
+    return true;
+}
 
-    // per-state (mean |d|, 1/var |d|), reference compute_mean_var_power
-    double2 st4[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-        st4[s] = state ? stats[(long long)fit * 4 + s] : make_double2(1.0, 1.0);
+template <bool OFFS>
+__global__ void __launch_bounds__(128)
+k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, int nfits,
+               FitOptions opt, FitResult *results, double *trace) {
+    const int fit = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = fit < nfits;
+    const int fidx = live ? fit : 0;
+    const int job = fidx / NDIODE, ch = fidx % NDIODE;
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    const double *H = htab + fidx;
 
     FitConsts kc;
-    kc.mur = kc.mui = 0.0;
+    kc.sw = H[(long long)HV_SW * nfits];
+    kc.sdd = H[(long long)HV_SDD * nfits];
+    kc.sgg = H[(long long)HV_SGG * nfits];
+    kc.sdr = H[(long long)HV_SDR * nfits];
+    kc.sdi = H[(long long)HV_SDI * nfits];
     kc.nvalid = (double)ji.nvalid;
-    if (OFFS) {  // weighted mean of d, to centre the 2x2 system
-        double acc[3] = {0, 0, 0};
-        for (int i = threadIdx.x; i < ji.nrows; i += FIT_THREADS) {
-            long long r = ji.row0 + i;
-            double w = 1.0;
-            if (state) {
-                int st = state[r];
-                if (!row_valid(st, flags)) continue;
-                w = st4[st & 3].y;
-            }
-            double2 d = row_sample(tv, r, ch);
-            acc[0] += w;
-            acc[1] = fma(w, d.x, acc[1]);
-            acc[2] = fma(w, d.y, acc[2]);
-        }
-        block_sum_vec<3>(acc, red);
-        kc.mur = acc[1] / acc[0];
-        kc.mui = acc[2] / acc[0];
+    kc.mur = kc.mui = 0.0;
+    if (OFFS) {
+        double2 mu = row_sample(tb.tv, ji.row0, ch);
+        kc.mur = mu.x;
+        kc.mui = mu.y;
     }
+
+    FitDriver drv;
+    drv.start(opt);
+    double cre = 0, cim = 0, are = 0, aim = 0, f = 0;
+    double *tr = (trace && live) ? trace + (long long)fit * (3 * 160) : nullptr;
+    bool running = live, failed = false;
+    // lock-step loop: every fit of the warp evaluates, then advances its solver
+    while (__any_sync(0xffffffffu, running)) {
+        if (running) {
+            const double b = drv.b, phi = drv.phi;
+            if (!eval_harmonic<OFFS>(H, nfits, kc, ji, b, phi, f, cre, cim, are, aim)) {
+                failed = true;
+                running = false;
+            } else {
+                if (tr && drv.nfev < 160) {
+                    tr[3 * drv.nfev] = b;
+                    tr[3 * drv.nfev + 1] = phi;
+                    tr[3 * drv.nfev + 2] = f;
+                }
+                running = drv.step(opt, f);
+            }
+        }
+    }
+    if (!live) return;
+    if (failed) {
+        FitResult r;
+        r.cre = r.cim = r.are = r.aim = r.b = r.phi = r.alpha = r.chi2 = 0.0;
+        r.q = r.cq = r.sq = 0.0;
+        r.uniform = 0; r.nfev = 0; r.status = 0; r.method = 0; r.second = 0;
+        r.fallback = 1; r.pad = 0;
+        results[fit] = r;
+        return;
+    }
+    store_result(results, fit, drv, ji, cre, cim, are, aim, 2);
+}
+
+void launch_fit_harmonic(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,
+                         const double *d_htab, int nfits, const FitOptions &opt,
+                         FitResult *d_results, double *d_trace) {
+    if (nfits <= 0) return;
+    const int blocks = (nfits + 127) / 128;
+    if (opt.flags & 2u)
+        k_fit_harmonic<true><<<blocks, 128, 0, L.stream>>>(d_tabs, d_jobs, d_htab, nfits, opt,
+                                                          d_results, d_trace);
+    else
+        k_fit_harmonic<false><<<blocks, 128, 0, L.stream>>>(d_tabs, d_jobs, d_htab, nfits, opt,
+                                                           d_results, d_trace);
+    *L.counter += 1;
+}
+
+// ===========================================================================
+// Direct evaluator: one block per fit
+// ===========================================================================
+// SCRATCH = true : z / y staged in HBM by the prologue (method = direct)
+// SCRATCH = false: z / y recomputed from the table at every call (fallback of the
+//                  harmonic path; only fits flagged `fallback` run)
+template <bool OFFS, bool SCRATCH>
+__global__ void __launch_bounds__(FIT_THREADS)
+k_fit_direct(const TableDesc *tabs, const JobInfo *jobs, int SP, const double *spart1,
+             const double *spart2, FitOptions opt, FitResult *results, double *trace) {
+    __shared__ double red[7 * 8];
+    __shared__ double2 st4[4];
+    const int fit = blockIdx.x;
+    if (!SCRATCH && !results[fit].fallback) return;
+    const int job = fit / NDIODE, ch = fit % NDIODE;
+    const int group = ch >> 2, fcch = fc_channel(group);
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    const int8_t *state = tb.state;
+    const unsigned flags = opt.flags;
+    double2 *z = SCRATCH ? tb.z + (long long)ch * tb.tv.n + ji.row0 : nullptr;
+    double2 *y = (SCRATCH && OFFS) ? tb.y + (long long)ch * tb.tv.n + ji.row0 : nullptr;
+    const double2 *bas = tb.basis + ji.row0;
+
+    // per-state (mean |d|, 1/var |d|), reference compute_mean_var_power
+    if (threadIdx.x < 4)
+        st4[threadIdx.x] = state ? stats_mean_weight(spart1, spart2, job * NGROUP + group, SP,
+                                                     stats_segments(ji.nrows), ch & 3, threadIdx.x)
+                                 : make_double2(1.0, 1.0);
+    __syncthreads();
+
+    FitConsts kc;
+    kc.nvalid = (double)ji.nvalid;
+    kc.mur = kc.mui = 0.0;
+    if (OFFS) {
+        double2 mu = row_sample(tb.tv, ji.row0, ch);
+        kc.mur = mu.x;
+        kc.mui = mu.y;
+    }
+
+    // z_n = w conj(p)(d - mu), y_n = w p, p = power .* FCphasor (:396)
+    auto row_zy = [&](int i, double2 &zz, double2 &yy, double &w, double &dr, double &di,
+                      double &pp) -> bool {
+        const long long r = ji.row0 + i;
+        double m = 1.0;
+        w = 1.0;
+        if (state) {
+            const int st = state[r];
+            if (!row_valid(st, flags)) return false;
+            w = st4[st & 3].y;
+            m = st4[st & 3].x;
+        }
+        const double2 d = row_sample(tb.tv, r, ch);
+        const double2 fc = fc_phasor(row_sample(tb.tv, r, fcch));
+        dr = d.x - kc.mur;
+        di = d.y - kc.mui;
+        const double pr = m * fc.x, pi = m * fc.y;
+        const double wpr = w * pr, wpi = w * pi;
+        zz.x = fma(wpr, dr, wpi * di);
+        zz.y = fma(wpr, di, -(wpi * dr));
+        yy.x = wpr;
+        yy.y = wpi;
+        pp = fma(pr, pr, pi * pi);
+        return true;
+    };
+
     {
         double acc[5] = {0, 0, 0, 0, 0};  // sw, sdd, sgg, sdr, sdi
         for (int i = threadIdx.x; i < ji.nrows; i += FIT_THREADS) {
-            long long r = ji.row0 + i;
-            double w = 1.0, m = 1.0;
-            bool valid = true;
-            if (state) {
-                int st = state[r];
-                valid = row_valid(st, flags);
-                w = st4[st & 3].y;
-                m = st4[st & 3].x;
-            }
             double2 zz = make_double2(0.0, 0.0), yy = zz;
-            if (valid) {
-                double2 d = row_sample(tv, r, ch);
-                double2 fc = fc_phasor(row_sample(tv, r, fcch));
-                double dr = d.x - kc.mur, di = d.y - kc.mui;
-                double pr = m * fc.x, pi = m * fc.y;  // p = power .* FCphasor, :396
-                double wpr = w * pr, wpi = w * pi;
-                // z = w conj(p) (d - mu)
-                zz.x = fma(wpr, dr, wpi * di);
-                zz.y = fma(wpr, di, -(wpi * dr));
-                yy.x = wpr;
-                yy.y = wpi;
+            double w, dr, di, pp;
+            if (row_zy(i, zz, yy, w, dr, di, pp)) {
                 acc[0] += w;
                 acc[1] = fma(w, fma(dr, dr, di * di), acc[1]);
-                acc[2] = fma(w, fma(pr, pr, pi * pi), acc[2]);
+                acc[2] = fma(w, pp, acc[2]);
                 acc[3] = fma(w, dr, acc[3]);
                 acc[4] = fma(w, di, acc[4]);
             }
-            z[i] = zz;
-            if (OFFS) y[i] = yy;
+            if (SCRATCH) {
+                z[i] = zz;
+                if (OFFS) y[i] = yy;
+            }
         }
         block_sum_vec<5>(acc, red);
         kc.sw = acc[0];
@@ -165,7 +304,7 @@ k_fit_direct(TableView tv, const JobInfo *jobs, const int8_t *state, const doubl
         kc.sdr = acc[3];
         kc.sdi = acc[4];
     }
-    __syncthreads();  // z/y visible to the whole block
+    __syncthreads();  // z / y visible to the whole block
 
     FitDriver drv;
     drv.start(opt);
@@ -176,13 +315,21 @@ k_fit_direct(TableView tv, const JobInfo *jobs, const int8_t *state, const doubl
         const PhaseQ pq = make_phaseq(phi, ji.thmin, ji.thmax);
         double acc[4] = {0, 0, 0, 0};
         for (int i = threadIdx.x; i < ji.nrows; i += FIT_THREADS) {
-            double2 sc = bas[i];
-            double2 zz = z[i];
+            double2 zz, yy = make_double2(0.0, 0.0);
+            if (SCRATCH) {
+                zz = z[i];
+                if (OFFS) yy = y[i];
+            } else {
+                double w, dr, di, pp;
+                zz = make_double2(0.0, 0.0);
+                if (!row_zy(i, zz, yy, w, dr, di, pp)) continue;
+            }
+            const double2 sc = bas[i];
             double sn;
             if (pq.uniform) {
                 sn = fma(sc.x, pq.cq, sc.y * pq.sq);
             } else {
-                sn = sin_arg(pq, phi, row_theta(tv, ji.row0 + i), sc);
+                sn = sin_arg(pq, phi, row_theta(tb.tv, ji.row0 + i), sc);
             }
             double su, cu;
             sincos(b * sn, &su, &cu);
@@ -190,19 +337,11 @@ k_fit_direct(TableView tv, const JobInfo *jobs, const int8_t *state, const doubl
             acc[0] = fma(cu, zz.x, fma(su, zz.y, acc[0]));
             acc[1] = fma(cu, zz.y, fma(-su, zz.x, acc[1]));
             if (OFFS) {  // e y
-                double2 yy = y[i];
                 acc[2] = fma(cu, yy.x, fma(-su, yy.y, acc[2]));
                 acc[3] = fma(cu, yy.y, fma(su, yy.x, acc[3]));
             }
         }
-        if (OFFS) {
-            block_sum_vec<4>(acc, red);
-        } else {
-            double a2[2] = {acc[0], acc[1]};
-            block_sum_vec<2>(a2, red);
-            acc[0] = a2[0];
-            acc[1] = a2[1];
-        }
+        block_sum_vec<4>(acc, red);
         f = solve_linear(kc, OFFS, acc[0], acc[1], acc[2], acc[3], cre, cim, are, aim);
         if (tr && threadIdx.x == 0 && drv.nfev < 160) {
             tr[3 * drv.nfev] = b;
@@ -211,32 +350,22 @@ k_fit_direct(TableView tv, const JobInfo *jobs, const int8_t *state, const doubl
         }
         if (!drv.step(opt, f)) break;
     }
-    if (threadIdx.x == 0) {
-        FitResult r;
-        r.cre = cre; r.cim = cim; r.are = are; r.aim = aim;
-        r.b = drv.b; r.phi = drv.phi;
-        r.alpha = atan2(aim, are);
-        r.chi2 = drv.chi2;
-        PhaseQ pq = make_phaseq(drv.phi, ji.thmin, ji.thmax);
-        r.q = pq.q; r.cq = pq.cq; r.sq = pq.sq; r.uniform = pq.uniform;
-        r.nfev = drv.nfev; r.status = drv.status; r.method = 1; r.second = drv.second;
-        results[fit] = r;
-    }
+    if (threadIdx.x == 0) store_result(results, fit, drv, ji, cre, cim, are, aim, 1);
 }
 
-void launch_fit_direct(const Launcher &L, const TableView &tv, int nfits, const JobInfo *d_jobs,
-                       const int8_t *d_state, const double2 *d_stats, const double2 *d_basis,
-                       double2 *d_z, double2 *d_y, const FitOptions &opt, const int *d_fit_list,
-                       FitResult *d_results, double *d_trace) {
+void launch_fit_direct(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,
+                       int nfits, int SP, const double *d_spart1, const double *d_spart2,
+                       const FitOptions &opt, bool scratch, FitResult *d_results, double *d_trace) {
     if (nfits <= 0) return;
-    if (opt.flags & 2u)
-        k_fit_direct<true><<<nfits, FIT_THREADS, 0, L.stream>>>(tv, d_jobs, d_state, d_stats,
-                                                               d_basis, d_z, d_y, opt, d_fit_list,
-                                                               d_results, d_trace);
-    else
-        k_fit_direct<false><<<nfits, FIT_THREADS, 0, L.stream>>>(tv, d_jobs, d_state, d_stats,
-                                                                d_basis, d_z, d_y, opt, d_fit_list,
-                                                                d_results, d_trace);
+    const bool offs = (opt.flags & 2u) != 0;
+#define GPPD_LAUNCH_DIRECT(O, S)                                                            \
+    k_fit_direct<O, S><<<nfits, FIT_THREADS, 0, L.stream>>>(d_tabs, d_jobs, SP, d_spart1,   \
+                                                            d_spart2, opt, d_results, d_trace)
+    if (offs && scratch) GPPD_LAUNCH_DIRECT(true, true);
+    else if (offs) GPPD_LAUNCH_DIRECT(true, false);
+    else if (scratch) GPPD_LAUNCH_DIRECT(false, true);
+    else GPPD_LAUNCH_DIRECT(false, false);
+#undef GPPD_LAUNCH_DIRECT
     *L.counter += 1;
 }
 

@@ -1,0 +1,281 @@
+// harm_kernels.cu -- the Jacobi-Anger ("harmonic") form of the objective.
+//
+// The reference evaluates, ~35 times per fit, sums over all rows of
+//     conj(e_n) z_n,   e_n = exp(j b sin(theta_n + q))
+// (reference src/Modulation.jl:137-145; z_n = w_n conj(p_n) d_n).  With
+//     exp(j b sin x) = sum_k J_k(b) exp(j k x)
+// the row sums factor:  sum_n conj(e_n) z_n = sum_k J_k(b) e^{-jkq} Z_k,
+//     Z_k = sum_n z_n exp(-j k theta_n),   k = -HK..HK
+// so ONE pass over the rows (this file) yields 2*HK+1 complex harmonics per fit
+// and every later objective call costs O(HK) instead of O(N) (fit_kernels.cu,
+// k_fit_harmonic).  Truncation at HK = 24: |error| <= 2 sum_{k>24} |J_k(b)| < 1.3e-15
+// for |b| <= 5; larger |b| (or a job without a uniform phase quantum) falls back to
+// the direct evaluator.
+//
+// Z_k and Z_{-k} share four real sums (c = cos k theta, s = sin k theta, z = x + j y):
+//     A = sum c x, B = sum s y, C = sum c y, D = sum s x
+//     Z_k = (A + B) + j (C - D),   Z_{-k} = (A - B) + j (C + D)
+// i.e. 4 FMAs per (row, diode, |k|) for two harmonics.
+//
+// Kernel structure (k_harm_accumulate): one block per (job, group, part),
+// persistent over the part's row tiles of TR rows.  Two PRODUCER warps stage a
+// tile in shared memory: e^{j theta} from the basis, the four diodes' z (or y)
+// values, and per consumer warp the tile's start phasor e^{j k0 theta}.  Six
+// CONSUMER warps own KC = 4 harmonics each for the 4 diodes of the group:
+// 64 FP64 accumulators per thread, advanced by complex rotation (3 per row).
+// Tiles are double buffered, one __syncthreads per tile.  A part is a FIXED
+// segment of HARM_SEG_TILES tiles of the job (independent of the batch and of
+// the launch shape) and k_harm_reduce adds the segments in index order, so a
+// fit's sums -- hence its whole NEWUOA trajectory -- do not depend on what else
+// is in the batch.
+#include "fit_math.cuh"
+#include "gppd_device.cuh"
+#include "kernels.h"
+
+namespace gppd {
+
+constexpr int TR = 192;                       // rows per tile
+constexpr int HARM_SEG_TILES = 32;            // tiles per segment (6144 rows)
+constexpr int KC = 4;                         // harmonics per consumer warp
+constexpr int NCH = HK / KC;                  // consumer warps
+constexpr int NPROD = 2;                      // producer warps
+constexpr int HARM_THREADS = (NCH + NPROD) * 32;
+static_assert(NCH * KC == HK, "HK must be a multiple of KC");
+
+struct HarmTile {
+    double2 e1[TR];            // (cos theta, sin theta)
+    double2 start[NCH][TR];    // (cos, sin)((KC*ch + 1) theta)
+    double2 v[4][TR];          // stream values of the group's 4 diodes
+};
+
+__host__ __device__ inline int harm_segments(long long nrows) {
+    long long ntiles = (nrows + TR - 1) / TR;
+    return (int)((ntiles + HARM_SEG_TILES - 1) / HARM_SEG_TILES);
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+
+template <int KIND>  // 0: z = w conj(p) (d - mu);  1: y = w p
+__global__ void __launch_bounds__(HARM_THREADS, 1)
+k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, int SP,
+                  const double *spart1, const double *spart2, double *partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HarmTile *tiles = reinterpret_cast<HarmTile *>(smem_raw);
+    __shared__ double2 s_stats[16];
+    __shared__ double s_red[NPROD][32];
+
+    constexpr int NCONST = KIND == 0 ? 7 : 2;
+    constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
+    const int jg = blockIdx.y, p = blockIdx.x;
+    const int job = jg >> 3, group = jg & 7;
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool producer = warp >= NCH;
+    // segment p of the job: tiles [p*HARM_SEG_TILES, ...)
+    const int ntiles = (ji.nrows + TR - 1) / TR;
+    const int tile0 = p * HARM_SEG_TILES;
+    if (tile0 >= ntiles) return;
+    const int nt = (ntiles - tile0) < HARM_SEG_TILES ? (ntiles - tile0) : HARM_SEG_TILES;
+
+    if (threadIdx.x < 16) {
+        s_stats[threadIdx.x] = tb.state
+            ? stats_mean_weight(spart1, spart2, jg, SP, stats_segments(ji.nrows), threadIdx.x >> 2,
+                                threadIdx.x & 3)
+            : make_double2(1.0, 1.0);
+    }
+    __syncthreads();
+
+    double acc[KC][4][4];
+    double cst[NCONST * 4];
+#pragma unroll
+    for (int a = 0; a < KC; ++a)
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][d][c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCONST * 4; ++c) cst[c] = 0.0;
+
+    double2 mu[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+        mu[d] = (flags & 2u) ? row_sample(tb.tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
+
+    auto produce = [&](int tile, HarmTile &T) {
+        const int ptid = threadIdx.x - NCH * 32;
+        for (int rr = ptid; rr < TR; rr += NPROD * 32) {
+            const int i = tile * TR + rr;
+            double2 e1 = make_double2(1.0, 0.0);
+            double2 vv[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
+            if (i < ji.nrows) {
+                const long long r = ji.row0 + i;
+                const double2 sc = tb.basis[r];
+                e1 = make_double2(sc.y, sc.x);
+                int st = ST_NORMAL;
+                bool valid = true;
+                if (tb.state) {
+                    st = tb.state[r];
+                    valid = row_valid(st, flags);
+                }
+                if (valid) {
+                    const double2 fc = fc_phasor(row_sample(tb.tv, r, fc_channel(group)));
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const double2 mw = s_stats[d * 4 + (st & 3)];
+                        const double pr = mw.x * fc.x, pi = mw.x * fc.y;   // p = power .* FCphasor
+                        const double wpr = mw.y * pr, wpi = mw.y * pi;
+                        if (KIND == 0) {
+                            const double2 dd = row_sample(tb.tv, r, group * 4 + d);
+                            const double dr = dd.x - mu[d].x, di = dd.y - mu[d].y;
+                            vv[d].x = fma(wpr, dr, wpi * di);
+                            vv[d].y = fma(wpr, di, -(wpi * dr));
+                            cst[d * 7 + 0] += mw.y;
+                            cst[d * 7 + 1] = fma(mw.y, fma(dr, dr, di * di), cst[d * 7 + 1]);
+                            cst[d * 7 + 2] = fma(mw.y, fma(pr, pr, pi * pi), cst[d * 7 + 2]);
+                            cst[d * 7 + 3] = fma(mw.y, dr, cst[d * 7 + 3]);
+                            cst[d * 7 + 4] = fma(mw.y, di, cst[d * 7 + 4]);
+                            cst[d * 7 + 5] += vv[d].x;
+                            cst[d * 7 + 6] += vv[d].y;
+                        } else {
+                            vv[d].x = wpr;
+                            vv[d].y = wpi;
+                            cst[d * 2 + 0] += wpr;
+                            cst[d * 2 + 1] += wpi;
+                        }
+                    }
+                }
+            }
+            T.e1[rr] = e1;
+            const double2 e2 = cmul(e1, e1);
+            const double2 e4 = cmul(e2, e2);
+            double2 pc = e1;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                T.start[ch][rr] = pc;
+                pc = cmul(pc, e4);
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) T.v[d][rr] = vv[d];
+        }
+    };
+
+    auto consume = [&](const HarmTile &T) {
+#pragma unroll 2
+        for (int i = 0; i < TR / 32; ++i) {
+            const int rr = lane + 32 * i;
+            const double2 e1 = T.e1[rr];
+            double2 cs = T.start[warp][rr];
+            double2 v[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) v[d] = T.v[d][rr];
+#pragma unroll
+            for (int a = 0; a < KC; ++a) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    acc[a][d][0] = fma(cs.x, v[d].x, acc[a][d][0]);
+                    acc[a][d][1] = fma(cs.y, v[d].y, acc[a][d][1]);
+                    acc[a][d][2] = fma(cs.x, v[d].y, acc[a][d][2]);
+                    acc[a][d][3] = fma(cs.y, v[d].x, acc[a][d][3]);
+                }
+                if (a + 1 < KC) cs = cmul(cs, e1);
+            }
+        }
+    };
+
+    if (producer) produce(tile0, tiles[0]);
+    __syncthreads();
+    for (int it = 0; it < nt; ++it) {
+        if (producer) {
+            if (it + 1 < nt) produce(tile0 + it + 1, tiles[(it + 1) & 1]);
+        } else {
+            consume(tiles[it & 1]);
+        }
+        __syncthreads();
+    }
+
+    double *out = partial + ((long long)jg * P + p) * 4 * HP;
+    if (!producer) {
+#pragma unroll
+        for (int a = 0; a < KC; ++a)
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double s = acc[a][d][c];
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) out[d * HP + NCONST + (warp * KC + a) * 4 + c] = s;
+                }
+    } else {
+        const int pw = warp - NCH;
+#pragma unroll
+        for (int c = 0; c < NCONST * 4; ++c) {
+            double s = cst[c];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) s_red[pw][c] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NCONST * 4) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NPROD; ++w) s += s_red[w][threadIdx.x];
+        const int d = threadIdx.x / NCONST, c = threadIdx.x % NCONST;
+        out[d * HP + c] = s;
+    }
+}
+
+// partial sums -> per-fit harmonic table, the job's segments added in index order
+__global__ void k_harm_reduce(const JobInfo *jobs, const double *partZ, const double *partY, int P,
+                              int nfits, double *htab) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nvals = partY ? HV_COUNT : HV_Y0R;
+    if (idx >= (long long)nfits * nvals) return;
+    const int v = (int)(idx / nfits), fit = (int)(idx % nfits);
+    const int job = fit / NDIODE, ch = fit % NDIODE;
+    const int jg = job * NGROUP + ch / 4, d = ch & 3;
+    const int nseg = harm_segments(jobs[job].nrows);
+    double s = 0.0;
+    if (v < HV_Y0R) {
+        for (int p = 0; p < nseg; ++p) s += partZ[(((long long)jg * P + p) * 4 + d) * HP_Z + v];
+    } else {
+        const int vy = v - HV_Y0R;
+        for (int p = 0; p < nseg; ++p) s += partY[(((long long)jg * P + p) * 4 + d) * HP_Y + vy];
+    }
+    htab[(long long)v * nfits + fit] = s;
+}
+
+int harm_max_segments(long long max_rows_per_job) { return harm_segments(max_rows_per_job); }
+
+void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                      unsigned flags, int P, int SP, const double *d_spart1,
+                      const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab) {
+    static bool attr_set = false;
+    const int smem = 2 * (int)sizeof(HarmTile);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_harm_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_harm_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    dim3 grid(P, njobs * NGROUP);
+    k_harm_accumulate<0><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
+                                                                 d_spart1, d_spart2, d_partZ);
+    *L.counter += 1;
+    const bool offs = (flags & 2u) != 0;
+    if (offs) {
+        k_harm_accumulate<1><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
+                                                                     d_spart1, d_spart2, d_partY);
+        *L.counter += 1;
+    }
+    const int nfits = njobs * NDIODE;
+    const long long tot = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
+    k_harm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
+        d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, d_htab);
+    *L.counter += 1;
+}
+
+}  // namespace gppd

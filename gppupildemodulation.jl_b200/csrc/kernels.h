@@ -1,39 +1,58 @@
-// kernels.h -- host-callable launchers of the device passes (one per pass).
+// kernels.h -- host-callable launchers of the device passes.  Every pass is
+// batched: one launch covers all tables (or all jobs / fits) of a batch.
 #pragma once
 #include "gppd_device.cuh"
 
 namespace gppd {
 
-// FAINT segmentation (reference buildstates, src/Faint.jl:21-73)
-void launch_segmentation(const Launcher &L, const TableView &tv, const double *d_timer1,
-                         int n1, const double *d_timer2, int n2, long long lag, double pre,
-                         double post, long long *d_lb, void *d_events, int max_events,
-                         int *d_flags, int8_t *d_state);
 constexpr int SEG_EVENT_BYTES = 24;
 
+// where one table's fit results go in the caller's layout
+struct ExportDesc {
+    int fit0, nfits;      // this table's fits in the batch result array
+    double *params;       // [nfits][6]
+    double *chi2;         // [nfits]
+    int *info;            // [nfits][4] or nullptr
+};
+
+// FAINT segmentation (reference buildstates, src/Faint.jl:21-73)
+void launch_segmentation(const Launcher &L, const TableDesc *d_tabs, int ntables,
+                         long long max_rows, int max_timers);
+
 // per-row basis + per-job theta range / valid count
-void launch_basis(const Launcher &L, const TableView &tv, long long wrows, int njobs,
-                  const int8_t *d_state, unsigned flags, double2 *d_basis,
+void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
+                  int max_jobs_per_table, int njobs, unsigned flags,
                   unsigned long long *d_thkeys, int *d_nvalid, JobInfo *d_jobs);
 
-// per-state mean / weight (reference compute_mean_var_power, src/Faint.jl:89-100)
-void launch_stats(const Launcher &L, const TableView &tv, int njobs, const JobInfo *d_jobs,
-                  const int8_t *d_state, unsigned flags, double2 *d_stats);
+// per-state sums (reference compute_mean_var_power, src/Faint.jl:89-100), two passes
+void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                  unsigned flags, int P, double *d_part1, double *d_part2);
 
-// the fit with the direct O(N)-per-call evaluator (one block per fit);
-// d_fit_list == nullptr: fits 0..nfits-1, else the listed fit ids
-void launch_fit_direct(const Launcher &L, const TableView &tv, int nfits, const JobInfo *d_jobs,
-                       const int8_t *d_state, const double2 *d_stats, const double2 *d_basis,
-                       double2 *d_z, double2 *d_y, const FitOptions &opt, const int *d_fit_list,
-                       FitResult *d_results, double *d_trace);
+// Jacobi-Anger harmonic sums of every fit + reduction into the harmonic table
+int harm_max_segments(long long max_rows_per_job);   // fixed 6144-row segments
+int stats_max_segments(long long max_rows_per_job);  // fixed 4096-row segments
+void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                      unsigned flags, int P, int SP, const double *d_spart1,
+                      const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab);
+
+// the fit, harmonic evaluator (one thread per fit)
+void launch_fit_harmonic(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,
+                         const double *d_htab, int nfits, const FitOptions &opt,
+                         FitResult *d_results, double *d_trace);
+
+// the fit, direct evaluator (one block per fit); scratch = false: only fits whose
+// result is flagged `fallback` run, recomputing z / y from the table
+void launch_fit_direct(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,
+                       int nfits, int SP, const double *d_spart1, const double *d_spart2,
+                       const FitOptions &opt, bool scratch, FitResult *d_results, double *d_trace);
 
 // demodulation + repack (reference src/Modulation.jl:417-425)
-void launch_demod(const Launcher &L, const TableView &tv, const OutView &ov, long long wrows,
-                  const double2 *d_basis, const FitResult *d_results, unsigned flags);
+void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
+                  const FitResult *d_results, unsigned flags);
 
 // FitResult -> params / chi2 / info in the caller's layout
-void launch_export(const Launcher &L, int nfits, const FitResult *d_results, double *d_params,
-                   double *d_chi2, int *d_info);
+void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int max_fits,
+                   const FitResult *d_results);
 
 // measured FP64 FMA throughput of the device (TFLOP/s), for the fit's roofline
 double measure_dfma_tflops(cudaStream_t stream, double *d_scratch);

@@ -1,10 +1,12 @@
-// stream_kernels.cu -- the HBM-bound passes around the fit:
+// stream_kernels.cu -- the HBM-bound passes around the fit, batched over the
+// tables of one launch sequence (blockIdx.y selects the table or the job group):
 //   * FAINT segmentation (reference buildstates, src/Faint.jl:21-73)
 //   * per-row sin/cos basis of theta = fl(omega t) and per-job theta range
 //   * per-state mean/variance of |d| (reference compute_mean_var_power,
-//     src/Faint.jl:89-100)
+//     src/Faint.jl:89-100), two partial-sum passes like the reference's two passes
 //   * demodulation + repack (reference src/Modulation.jl:417-425 and
 //     src/GPPupilDemodulation.jl:163-171,253)
+#include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
 
@@ -16,15 +18,9 @@ __device__ __forceinline__ unsigned long long f64_key(double x) {
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
-__host__ __device__ inline double f64_unkey(unsigned long long k) {
+__device__ __forceinline__ double f64_unkey(unsigned long long k) {
     unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
-#ifdef __CUDA_ARCH__
     return __longlong_as_double((long long)b);
-#else
-    double d;
-    memcpy(&d, &b, 8);
-    return d;
-#endif
 }
 
 // ===========================================================================
@@ -36,37 +32,30 @@ __host__ __device__ inline double f64_unkey(unsigned long long k) {
 // (2) a serial merge over the O(100) events, (3) a parallel fill.
 // Non-monotonic timestamps take the serial path, statement for statement.
 // ===========================================================================
-struct SegParams {
-    long long n;
-    const double *timer1, *timer2;  // device copies (HIGH series, LOW series)
-    int n1, n2;
-    long long lag;
-    double pre, post;
-};
-
 struct SegEvent {
     long long row;
     long long forget;
     int state;
     int pad;
 };
+static_assert(sizeof(SegEvent) == SEG_EVENT_BYTES, "SegEvent size");
 
-struct SegWork {
-    long long *lb1, *lb2;   // lower bounds of timer values (+ sentinel at index n1 / n2)
-    SegEvent *events;
-    int max_events;
-    int *nevents;           // [0] count, [1] fallback flag (non-monotone / overflow)
-};
+__global__ void k_seg_init(const TableDesc *tabs) {
+    const TableDesc &tb = tabs[blockIdx.x];
+    if (tb.seg.n1 > 0 && threadIdx.x < 2) tb.seg.flags[threadIdx.x] = 0;
+}
 
-__global__ void k_seg_monotone(TableView tv, int *flags) {
+__global__ void k_seg_monotone(const TableDesc *tabs) {
+    const TableDesc &tb = tabs[blockIdx.y];
+    if (tb.seg.n1 <= 0) return;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     bool bad = false;
-    for (; i + 1 < tv.n; i += stride) {
-        double a = row_time(tv, i), b = row_time(tv, i + 1);
+    for (; i + 1 < tb.tv.n; i += stride) {
+        double a = row_time(tb.tv, i), b = row_time(tb.tv, i + 1);
         if (!(b >= a)) bad = true;
     }
-    if (bad) flags[1] = 1;
+    if (bad) tb.seg.flags[1] = 1;
 }
 
 __device__ long long seg_lower_bound(const TableView &tv, double v) {
@@ -78,20 +67,24 @@ __device__ long long seg_lower_bound(const TableView &tv, double v) {
     return lo;
 }
 
-__global__ void k_seg_lower_bounds(TableView tv, SegParams sp, SegWork wk) {
+__global__ void k_seg_lower_bounds(const TableDesc *tabs) {
+    const TableDesc &tb = tabs[blockIdx.y];
+    const SegDesc &sp = tb.seg;
+    if (sp.n1 <= 0) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int tot = sp.n1 + 1 + sp.n2 + 1;
     if (k >= tot) return;
-    double timestep = row_time(tv, 1) - row_time(tv, 0);        // src/Faint.jl:24
-    double shift = (double)sp.lag * timestep;                   // :25-26
-    double tlast = row_time(tv, tv.n - 1);
+    double timestep = row_time(tb.tv, 1) - row_time(tb.tv, 0);   // src/Faint.jl:24
+    double shift = (double)sp.lag * timestep;                    // :25-26
+    double tlast = row_time(tb.tv, tb.tv.n - 1);
+    long long *lb1 = sp.lb, *lb2 = sp.lb + (sp.n1 + 1);
     if (k <= sp.n1) {
         double v = (k < sp.n1) ? __dadd_rn(sp.timer1[k], shift) : tlast;
-        wk.lb1[k] = seg_lower_bound(tv, v);
+        lb1[k] = seg_lower_bound(tb.tv, v);
     } else {
         int j = k - sp.n1 - 1;
         double v = (j < sp.n2) ? __dadd_rn(sp.timer2[j], shift) : tlast;
-        wk.lb2[j] = seg_lower_bound(tv, v);
+        lb2[j] = seg_lower_bound(tb.tv, v);
     }
 }
 
@@ -102,19 +95,24 @@ __device__ __forceinline__ long long seg_ceil_count(double delay, double timeste
     return (long long)r;
 }
 
-// serial merge of the two event queues (one thread)
-__global__ void k_seg_events(TableView tv, SegParams sp, SegWork wk) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (wk.nevents[1]) return;  // non-monotone: serial path
+// serial merge of the two event queues (one thread per table)
+__global__ void k_seg_events(const TableDesc *tabs) {
+    if (threadIdx.x != 0) return;
+    const TableDesc &tb = tabs[blockIdx.x];
+    const SegDesc &sp = tb.seg;
+    if (sp.n1 <= 0 || sp.flags[1]) return;  // bright, or non-monotone: serial path
+    const TableView &tv = tb.tv;
+    SegEvent *events = reinterpret_cast<SegEvent *>(sp.events);
+    const long long *lb1 = sp.lb, *lb2 = sp.lb + (sp.n1 + 1);
     double timestep = row_time(tv, 1) - row_time(tv, 0);
     double shift = (double)sp.lag * timestep;
     double tlast = row_time(tv, tv.n - 1);
     long long premax = seg_ceil_count(sp.pre, timestep);
     long long postmax = seg_ceil_count(sp.post, timestep);
-    long long lb_last = wk.lb1[sp.n1];
+    long long lb_last = lb1[sp.n1];
     int i1 = 0, i2 = 0;                       // next queue element to pop
-    double first1 = __dadd_rn(sp.timer1[i1], shift); long long lbh1 = wk.lb1[i1]; ++i1;
-    double first2 = __dadd_rn(sp.timer2[i2], shift); long long lbh2 = wk.lb2[i2]; ++i2;
+    double first1 = __dadd_rn(sp.timer1[i1], shift); long long lbh1 = lb1[i1]; ++i1;
+    double first2 = __dadd_rn(sp.timer2[i2], shift); long long lbh2 = lb2[i2]; ++i2;
     long long last1 = -1, last2 = -1;
     int cur = ST_NORMAL;
     int ne = 0;
@@ -133,7 +131,7 @@ __global__ void k_seg_events(TableView tv, SegParams sp, SegWork wk) {
                 first1 = tlast; lbh1 = lb_last;
                 if (first2 == tlast) cur = ST_NORMAL;
             } else {
-                first1 = __dadd_rn(sp.timer1[i1], shift); lbh1 = wk.lb1[i1]; ++i1;
+                first1 = __dadd_rn(sp.timer1[i1], shift); lbh1 = lb1[i1]; ++i1;
             }
             last1 = row;
         }
@@ -145,41 +143,47 @@ __global__ void k_seg_events(TableView tv, SegParams sp, SegWork wk) {
                 first2 = tlast; lbh2 = lb_last;
                 if (first1 == tlast) cur = ST_NORMAL;
             } else {
-                first2 = __dadd_rn(sp.timer2[i2], shift); lbh2 = wk.lb2[i2]; ++i2;
+                first2 = __dadd_rn(sp.timer2[i2], shift); lbh2 = lb2[i2]; ++i2;
             }
             last2 = row;
         }
         if (fired) {
-            if (ne >= wk.max_events) { wk.nevents[1] = 1; return; }
+            if (ne >= sp.max_events) { sp.flags[1] = 1; return; }
             SegEvent ev; ev.row = row; ev.forget = forget; ev.state = cur; ev.pad = 0;
-            wk.events[ne++] = ev;
+            events[ne++] = ev;
         }
     }
-    wk.nevents[0] = ne;
+    sp.flags[0] = ne;
 }
 
-__global__ void k_seg_fill(long long n, SegWork wk, int8_t *state) {
-    if (wk.nevents[1]) return;
+__global__ void k_seg_fill(const TableDesc *tabs) {
+    const TableDesc &tb = tabs[blockIdx.y];
+    const SegDesc &sp = tb.seg;
+    if (sp.n1 <= 0 || sp.flags[1]) return;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int ne = wk.nevents[0];
+    if (i >= tb.tv.n) return;
+    const SegEvent *events = reinterpret_cast<const SegEvent *>(sp.events);
+    int ne = sp.flags[0];
     int lo = 0, hi = ne;  // last event with row <= i
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (wk.events[mid].row <= i) lo = mid + 1; else hi = mid;
+        if (events[mid].row <= i) lo = mid + 1; else hi = mid;
     }
     int st = ST_NORMAL;
     if (lo > 0) {
-        SegEvent ev = wk.events[lo - 1];
+        SegEvent ev = events[lo - 1];
         st = (i - ev.row < ev.forget) ? ST_TRANSIENT : ev.state;   // :66-71
     }
-    state[i] = (int8_t)st;
+    tb.state[i] = (int8_t)st;
 }
 
-// the reference's loop, statement for statement (fallback, one thread)
-__global__ void k_seg_serial(TableView tv, SegParams sp, SegWork wk, int8_t *state) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!wk.nevents[1]) return;
+// the reference's loop, statement for statement (fallback, one thread per table)
+__global__ void k_seg_serial(const TableDesc *tabs) {
+    if (threadIdx.x != 0) return;
+    const TableDesc &tb = tabs[blockIdx.x];
+    const SegDesc &sp = tb.seg;
+    if (sp.n1 <= 0 || !sp.flags[1]) return;
+    const TableView &tv = tb.tv;
     double timestep = row_time(tv, 1) - row_time(tv, 0);
     double shift = (double)sp.lag * timestep;
     double tlast = row_time(tv, tv.n - 1);
@@ -202,27 +206,22 @@ __global__ void k_seg_serial(TableView tv, SegParams sp, SegWork wk, int8_t *sta
             if (i2 >= sp.n2) { first2 = tlast; if (first1 == tlast) cur = ST_NORMAL; }
             else first2 = __dadd_rn(sp.timer2[i2++], shift);
         }
-        if (forget > 0) { state[k] = (int8_t)ST_TRANSIENT; --forget; }
-        else state[k] = (int8_t)cur;
+        if (forget > 0) { tb.state[k] = (int8_t)ST_TRANSIENT; --forget; }
+        else tb.state[k] = (int8_t)cur;
     }
 }
 
-void launch_segmentation(const Launcher &L, const TableView &tv, const double *d_timer1,
-                         int n1, const double *d_timer2, int n2, long long lag, double pre,
-                         double post, long long *d_lb, void *d_events, int max_events,
-                         int *d_flags, int8_t *d_state) {
-    SegParams sp{tv.n, d_timer1, d_timer2, n1, n2, lag, pre, post};
-    SegWork wk{d_lb, d_lb + (n1 + 1), reinterpret_cast<SegEvent *>(d_events), max_events, d_flags};
-    cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), L.stream);
-    int blocks = (int)((tv.n + 255) / 256);
-    if (blocks > 1184) blocks = 1184;
-    k_seg_monotone<<<blocks, 256, 0, L.stream>>>(tv, d_flags);
-    int tot = n1 + n2 + 2;
-    k_seg_lower_bounds<<<(tot + 127) / 128, 128, 0, L.stream>>>(tv, sp, wk);
-    k_seg_events<<<1, 32, 0, L.stream>>>(tv, sp, wk);
-    k_seg_fill<<<(int)((tv.n + 255) / 256), 256, 0, L.stream>>>(tv.n, wk, d_state);
-    k_seg_serial<<<1, 32, 0, L.stream>>>(tv, sp, wk, d_state);
-    *L.counter += 5;
+void launch_segmentation(const Launcher &L, const TableDesc *d_tabs, int ntables,
+                         long long max_rows, int max_timers) {
+    int rb = (int)((max_rows + 255) / 256);
+    int mono = rb > 296 ? 296 : rb;
+    k_seg_init<<<ntables, 32, 0, L.stream>>>(d_tabs);
+    k_seg_monotone<<<dim3(mono, ntables), 256, 0, L.stream>>>(d_tabs);
+    k_seg_lower_bounds<<<dim3((max_timers + 2 + 127) / 128, ntables), 128, 0, L.stream>>>(d_tabs);
+    k_seg_events<<<ntables, 32, 0, L.stream>>>(d_tabs);
+    k_seg_fill<<<dim3(rb, ntables), 256, 0, L.stream>>>(d_tabs);
+    k_seg_serial<<<ntables, 32, 0, L.stream>>>(d_tabs);
+    *L.counter += 6;
 }
 
 // ===========================================================================
@@ -230,17 +229,26 @@ void launch_segmentation(const Launcher &L, const TableView &tv, const double *d
 // ~3e10 rad argument, done ONCE per row instead of once per objective call,
 // plus the per-job theta range and valid-row count.
 // ===========================================================================
-__global__ void k_basis(TableView tv, long long wrows, const int8_t *state, unsigned flags,
-                        double2 *basis, unsigned long long *thkeys, int *nvalid) {
+__global__ void k_init_thkeys(unsigned long long *thkeys, int *nvalid, int njobs) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    thkeys[2 * j] = ~0ull;
+    thkeys[2 * j + 1] = 0ull;
+    nvalid[j] = 0;
+}
+
+__global__ void k_basis(const TableDesc *tabs, unsigned flags, unsigned long long *thkeys,
+                        int *nvalid) {
+    const TableDesc &tb = tabs[blockIdx.y];
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= tv.n) return;
-    double th = row_theta(tv, i);
+    if (i >= tb.tv.n) return;
+    double th = row_theta(tb.tv, i);
     double s, c;
     sincos(th, &s, &c);
-    basis[i] = make_double2(s, c);
-    long long job = i / wrows;
+    tb.basis[i] = make_double2(s, c);
+    long long job = tb.job0 + i / tb.wrows;
     unsigned long long key = f64_key(th);
-    int valid = state ? (row_valid(state[i], flags) ? 1 : 0) : 1;
+    int valid = tb.state ? (row_valid(tb.state[i], flags) ? 1 : 0) : 1;
     // warp-aggregate when a full warp sits in one job
     unsigned mask = __activemask();
     if (mask == 0xffffffffu) {
@@ -268,105 +276,138 @@ __global__ void k_basis(TableView tv, long long wrows, const int8_t *state, unsi
     if (valid) atomicAdd(nvalid + job, 1);
 }
 
-__global__ void k_init_thkeys(unsigned long long *thkeys, int njobs) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
-    thkeys[2 * j] = ~0ull;
-    thkeys[2 * j + 1] = 0ull;
-}
-
-__global__ void k_jobinfo(long long n, long long wrows, int njobs, const unsigned long long *thkeys,
+__global__ void k_jobinfo(const TableDesc *tabs, const unsigned long long *thkeys,
                           const int *nvalid, JobInfo *jobs) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
+    int t = blockIdx.y;
+    const TableDesc &tb = tabs[t];
+    int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= tb.njobs) return;
+    int j = tb.job0 + jl;
     JobInfo ji;
     ji.thmin = f64_unkey(thkeys[2 * j]);
     ji.thmax = f64_unkey(thkeys[2 * j + 1]);
-    ji.row0 = (long long)j * wrows;
-    long long rem = n - ji.row0;
-    ji.nrows = (int)(rem < wrows ? rem : wrows);
+    ji.row0 = (long long)jl * tb.wrows;
+    long long rem = tb.tv.n - ji.row0;
+    ji.nrows = (int)(rem < tb.wrows ? rem : tb.wrows);
     ji.nvalid = nvalid[j];
+    ji.table = t;
+    ji.pad = 0;
     jobs[j] = ji;
 }
 
-void launch_basis(const Launcher &L, const TableView &tv, long long wrows, int njobs,
-                  const int8_t *d_state, unsigned flags, double2 *d_basis,
+void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
+                  int max_jobs_per_table, int njobs, unsigned flags,
                   unsigned long long *d_thkeys, int *d_nvalid, JobInfo *d_jobs) {
-    // keys: min slot = all ones, max slot = 0
-    cudaMemsetAsync(d_nvalid, 0, sizeof(int) * (size_t)njobs, L.stream);
-    k_init_thkeys<<<(njobs + 255) / 256, 256, 0, L.stream>>>(d_thkeys, njobs);
-    k_basis<<<(int)((tv.n + 255) / 256), 256, 0, L.stream>>>(tv, wrows, d_state, flags, d_basis,
-                                                             d_thkeys, d_nvalid);
-    k_jobinfo<<<(njobs + 255) / 256, 256, 0, L.stream>>>(tv.n, wrows, njobs, d_thkeys, d_nvalid,
-                                                         d_jobs);
+    k_init_thkeys<<<(njobs + 255) / 256, 256, 0, L.stream>>>(d_thkeys, d_nvalid, njobs);
+    k_basis<<<dim3((unsigned)((max_rows + 255) / 256), ntables), 256, 0, L.stream>>>(
+        d_tabs, flags, d_thkeys, d_nvalid);
+    k_jobinfo<<<dim3((max_jobs_per_table + 127) / 128, ntables), 128, 0, L.stream>>>(
+        d_tabs, d_thkeys, d_nvalid, d_jobs);
     *L.counter += 3;
 }
 
 // ===========================================================================
-// Per-state statistics of |d| (FAINT): mean and 1/var with the n-1 divisor,
-// two passes like the reference so that var is a sum of squared deviations.
-// One thread block per fit; fixed reduction order (deterministic).
+// Per-state statistics of |d| (FAINT), as two partial-sum passes over row
+// tiles: pass 1 sums |d| and counts per state, pass 2 sums (|d| - mean)^2 with
+// the pass-1 mean (the reference's mean / var(...; mean) pair).  One block per
+// (job, group, part); parts are combined in index order by the consumers
+// (stats_mean / stats_mean_weight).  A part is a FIXED segment of
+// STATS_SEG_ROWS rows of the job, so results are deterministic and independent of
+// the batch the job is in.
 // ===========================================================================
-template <int NT>
-__device__ __forceinline__ double block_sum(double v, double *red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+constexpr int STATS_THREADS = 128;
+
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double *red, int nwarps) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     int w = threadIdx.x >> 5;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[w] = v;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[k * 8 + w] = v[k];
+    }
     __syncthreads();
-    double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < NT / 32; ++k) s += red[k];
-    return s;
-}
-
-__global__ void __launch_bounds__(256) k_stats(TableView tv, const JobInfo *jobs,
-                                               const int8_t *state, unsigned flags,
-                                               double2 *stats /* [fit][4] = (mean, weight) */) {
-    __shared__ double red[8];
-    int fit = blockIdx.x;
-    int job = fit / NDIODE, ch = fit % NDIODE;
-    JobInfo ji = jobs[job];
-    double sum[4] = {0, 0, 0, 0};
-    double cnt[4] = {0, 0, 0, 0};
-    for (int i = threadIdx.x; i < ji.nrows; i += 256) {
-        long long r = ji.row0 + i;
-        int st = state[r];
-        if (!row_valid(st, flags) || st < 0 || st > 3) continue;
-        double2 d = row_sample(tv, r, ch);
-        double a = hypot(d.x, d.y);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-            if (st == s) { sum[s] += a; cnt[s] += 1.0; }
-    }
-    double mean[4], tot[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        tot[s] = block_sum<256>(cnt[s], red);
-        mean[s] = block_sum<256>(sum[s], red) / tot[s];
-    }
-    double ssq[4] = {0, 0, 0, 0};
-    for (int i = threadIdx.x; i < ji.nrows; i += 256) {
-        long long r = ji.row0 + i;
-        int st = state[r];
-        if (!row_valid(st, flags) || st < 0 || st > 3) continue;
-        double2 d = row_sample(tv, r, ch);
-        double a = hypot(d.x, d.y);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-            if (st == s) { double e = a - mean[s]; ssq[s] += e * e; }
-    }
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        double v = block_sum<256>(ssq[s], red) / (tot[s] - 1.0);  // n == 1 -> 0/0 = NaN as in Julia
-        if (threadIdx.x == 0) stats[(long long)fit * 4 + s] = make_double2(mean[s], 1.0 / v);
+    for (int k = 0; k < NV; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < nwarps; ++j) s += red[k * 8 + j];
+        v[k] = s;
     }
 }
 
-void launch_stats(const Launcher &L, const TableView &tv, int njobs, const JobInfo *d_jobs,
-                  const int8_t *d_state, unsigned flags, double2 *d_stats) {
-    k_stats<<<njobs * NDIODE, 256, 0, L.stream>>>(tv, d_jobs, d_state, flags, d_stats);
-    *L.counter += 1;
+template <int PASS>
+__global__ void __launch_bounds__(STATS_THREADS)
+k_stats(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, double *part1,
+        double *part2) {
+    __shared__ double red[20 * 8];
+    __shared__ double mean_s[16];
+    const int jg = blockIdx.y, p = blockIdx.x;
+    const int job = jg >> 3, group = jg & 7;
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    if (!tb.state) return;
+    const int nseg = stats_segments(ji.nrows);
+    if (PASS == 2) {
+        if (threadIdx.x < 16)
+            mean_s[threadIdx.x] = stats_mean(part1, jg, P, nseg, threadIdx.x >> 2, threadIdx.x & 3);
+        __syncthreads();
+    }
+    double acc[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) acc[k] = 0.0;
+    // rows of segment p of the job
+    const long long seg_end = (long long)(p + 1) * STATS_SEG_ROWS < ji.nrows
+                                  ? (long long)(p + 1) * STATS_SEG_ROWS : ji.nrows;
+    if ((long long)p * STATS_SEG_ROWS >= ji.nrows) return;
+    for (long long i = (long long)p * STATS_SEG_ROWS + threadIdx.x; i < seg_end;
+         i += STATS_THREADS) {
+        long long r = ji.row0 + i;
+        int st = tb.state[r];
+        if (!row_valid(st, flags) || st < 0 || st > 3) continue;
+#pragma unroll
+        for (int dio = 0; dio < 4; ++dio) {
+            double2 d = row_sample(tb.tv, r, group * 4 + dio);
+            double a = hypot(d.x, d.y);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (st == s) {
+                    if (PASS == 1) {
+                        acc[dio * 4 + s] += a;
+                    } else {
+                        double e = a - mean_s[dio * 4 + s];
+                        acc[dio * 4 + s] = fma(e, e, acc[dio * 4 + s]);
+                    }
+                }
+            }
+        }
+        if (PASS == 1) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (st == s) acc[16 + s] += 1.0;
+        }
+    }
+    block_sum_n<20>(acc, red, STATS_THREADS / 32);
+    if (threadIdx.x < (PASS == 1 ? 20 : 16)) {
+        double *dst = PASS == 1 ? part1 + ((long long)jg * P + p) * STATS_VALS
+                                : part2 + ((long long)jg * P + p) * 16;
+        double v = 0.0;  // select chain instead of a dynamic register-array index
+#pragma unroll
+        for (int k = 0; k < 20; ++k)
+            if (threadIdx.x == k) v = acc[k];
+        dst[threadIdx.x] = v;
+    }
+}
+
+int stats_max_segments(long long max_rows_per_job) { return stats_segments(max_rows_per_job); }
+
+void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                  unsigned flags, int P, double *d_part1, double *d_part2) {
+    dim3 grid(P, njobs * NGROUP);
+    k_stats<1><<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, flags, P, d_part1, d_part2);
+    k_stats<2><<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, flags, P, d_part1, d_part2);
+    *L.counter += 2;
 }
 
 // ===========================================================================
@@ -405,51 +446,106 @@ __device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned fl
                         __dadd_rn(__dmul_rn(d.y, ca), -__dmul_rn(d.x, sa)));
 }
 
-__global__ void __launch_bounds__(128) k_demod(TableView tv, OutView ov, long long wrows,
-                                               const double2 *basis, const FitResult *results,
+// One thread per (row, group): 4 diodes + the group's FC channel.
+// Table rows are staged through shared memory so that global loads and stores
+// are full 320-byte rows (coalesced), whatever the per-thread access pattern.
+constexpr int DEMOD_ROWS = 32;   // rows per block; 8 threads (groups) per row
+
+__global__ void __launch_bounds__(256) k_demod(const TableDesc *tabs, const FitResult *results,
                                                unsigned flags) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= tv.n) return;
-    long long job = i / wrows;
-    const FitResult *fr = results + job * NDIODE;
-    double theta = row_theta(tv, i);
-    double2 sc = basis[i];
-    if (ov.kind == 1) {
-        for (int ch = 0; ch < NDIODE; ++ch) {
-            double2 d = row_sample(tv, i, ch);
-            ov.out[(long long)ch * tv.n + i] = demod_sample(fr[ch], flags, theta, sc, d);
+    const TableDesc &tb = tabs[blockIdx.y];
+    const TableView &tv = tb.tv;
+    const OutView &ov = tb.ov;
+    const long long row_base = (long long)blockIdx.x * DEMOD_ROWS;
+    if (row_base >= tv.n) return;
+    const int nrow = (int)((tv.n - row_base) < DEMOD_ROWS ? (tv.n - row_base) : DEMOD_ROWS);
+    const int rl = threadIdx.x >> 3, group = threadIdx.x & 7;
+    const long long i = row_base + rl;
+    const bool active = rl < nrow;
+
+    if (ov.kind == 1) {  // complex128, channel-major: already unit stride along rows
+        if (!active) return;
+        const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
+        double theta = row_theta(tv, i);
+        double2 sc = tb.basis[i];
+        for (int dio = 0; dio < 4; ++dio) {
+            int ch = group * 4 + dio;
+            ov.out[(long long)ch * tv.n + i] =
+                demod_sample(fr[ch], flags, theta, sc, row_sample(tv, i, ch));
         }
-        for (int ch = NDIODE; ch < NCHAN; ++ch)
-            ov.out[(long long)ch * tv.n + i] = row_sample(tv, i, ch);  // output = copy(data), :353
+        int fcch = fc_channel(group);
+        ov.out[(long long)fcch * tv.n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
         return;
     }
-    float *orow = reinterpret_cast<float *>(reinterpret_cast<char *>(ov.volt) + i * ov.volt_stride);
-    int base = 0;
-    if (ov.keepraw) {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
-        const float *irow = reinterpret_cast<const float *>(
-            reinterpret_cast<const char *>(tv.volt) + i * tv.volt_stride);
-        for (int k = 0; k < 2 * NCHAN; ++k)
-            reinterpret_cast<uint32_t *>(orow)[k] = __ldg(reinterpret_cast<const uint32_t *>(irow) + k);
-        base = 2 * NCHAN;
+
+    __shared__ __align__(16) uint32_t s_in[DEMOD_ROWS * 80];
+    __shared__ __align__(16) uint32_t s_out[DEMOD_ROWS * 80];
+    // coalesced load of nrow input rows (raw 32-bit words, byte order untouched)
+    const bool dense_in = tv.volt_stride == 320;
+    for (int w = threadIdx.x; w < nrow * 80; w += 256) {
+        int r = w / 80, c = w - r * 80;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(
+            reinterpret_cast<const char *>(tv.volt) + (row_base + r) * tv.volt_stride);
+        s_in[w] = dense_in ? __ldg(reinterpret_cast<const uint32_t *>(tv.volt) + row_base * 80 + w)
+                           : __ldg(src + c);
     }
-    for (int ch = 0; ch < NDIODE; ++ch) {
-        double2 d = row_sample(tv, i, ch);
-        double2 o = demod_sample(fr[ch], flags, theta, sc, d);
-        store_f32(orow + base + 2 * ch, __double2float_rn(o.x), ov.big_endian);
-        store_f32(orow + base + 2 * ch + 1, __double2float_rn(o.y), ov.big_endian);
+    __syncthreads();
+    if (active) {
+        const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
+        double theta = row_theta(tv, i);
+        double2 sc = tb.basis[i];
+        const uint32_t *irow = s_in + rl * 80;
+        uint32_t *orow = s_out + rl * 80;
+        auto ld = [&](int ch) {
+            uint32_t a = irow[2 * ch], b = irow[2 * ch + 1];
+            if (tv.big_endian) { a = bswap32(a); b = bswap32(b); }
+            double re = (double)__uint_as_float(a), im = (double)__uint_as_float(b);
+            if (tv.offsets) {
+                double2 o = __ldg(tv.offsets + ch);
+                re -= o.x;
+                im -= o.y;
+            }
+            return make_double2(re, im);
+        };
+        auto st = [&](int ch, double2 v) {
+            uint32_t a = __float_as_uint(__double2float_rn(v.x));
+            uint32_t b = __float_as_uint(__double2float_rn(v.y));
+            if (ov.big_endian) { a = bswap32(a); b = bswap32(b); }
+            orow[2 * ch] = a;
+            orow[2 * ch + 1] = b;
+        };
+        for (int dio = 0; dio < 4; ++dio) {
+            int ch = group * 4 + dio;
+            st(ch, demod_sample(fr[ch], flags, theta, sc, ld(ch)));
+        }
+        int fcch = fc_channel(group);
+        st(fcch, ld(fcch));  // centred FC channels, :170-171
     }
+    __syncthreads();
+    // coalesced store
     if (!ov.keepraw) {
-        for (int ch = NDIODE; ch < NCHAN; ++ch) {  // centred FC channels, :170-171
-            double2 d = row_sample(tv, i, ch);
-            store_f32(orow + 2 * ch, __double2float_rn(d.x), ov.big_endian);
-            store_f32(orow + 2 * ch + 1, __double2float_rn(d.y), ov.big_endian);
+        const bool dense_out = ov.volt_stride == 320;
+        for (int w = threadIdx.x; w < nrow * 80; w += 256) {
+            int r = w / 80, c = w - r * 80;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(
+                reinterpret_cast<char *>(ov.volt) + (row_base + r) * ov.volt_stride);
+            if (dense_out) reinterpret_cast<uint32_t *>(ov.volt)[row_base * 80 + w] = s_out[w];
+            else dst[c] = s_out[w];
+        }
+    } else {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
+        for (int w = threadIdx.x; w < nrow * 144; w += 256) {
+            int r = w / 144, c = w - r * 144;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(
+                reinterpret_cast<char *>(ov.volt) + (row_base + r) * ov.volt_stride);
+            dst[c] = c < 80 ? s_in[r * 80 + c] : s_out[r * 80 + (c - 80)];
         }
     }
 }
 
-void launch_demod(const Launcher &L, const TableView &tv, const OutView &ov, long long wrows,
-                  const double2 *d_basis, const FitResult *d_results, unsigned flags) {
-    k_demod<<<(int)((tv.n + 127) / 128), 128, 0, L.stream>>>(tv, ov, wrows, d_basis, d_results, flags);
+void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
+                  const FitResult *d_results, unsigned flags) {
+    k_demod<<<dim3((unsigned)((max_rows + DEMOD_ROWS - 1) / DEMOD_ROWS), ntables), 256, 0,
+              L.stream>>>(d_tabs, d_results, flags);
     *L.counter += 1;
 }
 
@@ -457,28 +553,28 @@ void launch_demod(const Launcher &L, const TableView &tv, const OutView &ov, lon
 // results -> caller layout: params (c.re,c.im,a.re,a.im,b,phi) with the sign
 // normalisation of reference src/Modulation.jl:426-431, chi2, info
 // ===========================================================================
-__global__ void k_export(int nfits, const FitResult *results, double *params, double *chi2,
-                         int *info) {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nfits) return;
-    FitResult r = results[f];
+__global__ void k_export(const ExportDesc *exps, const FitResult *results) {
+    const ExportDesc &e = exps[blockIdx.y];
+    int fl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fl >= e.nfits) return;
+    FitResult r = results[e.fit0 + fl];
     double b = r.b, phi = r.phi;
     if (b < 0) {
         b = -b;
         phi += (phi < 0 ? PI_F64 : -PI_F64);
     }
-    double *p = params + 6ll * f;
+    double *p = e.params + 6ll * fl;
     p[0] = r.cre; p[1] = r.cim; p[2] = r.are; p[3] = r.aim; p[4] = b; p[5] = phi;
-    chi2[f] = r.chi2;
-    if (info) {
-        info[4 * f] = r.nfev; info[4 * f + 1] = r.status;
-        info[4 * f + 2] = r.method; info[4 * f + 3] = r.second;
+    e.chi2[fl] = r.chi2;
+    if (e.info) {
+        e.info[4 * fl] = r.nfev; e.info[4 * fl + 1] = r.status;
+        e.info[4 * fl + 2] = r.method; e.info[4 * fl + 3] = r.second;
     }
 }
 
-void launch_export(const Launcher &L, int nfits, const FitResult *d_results, double *d_params,
-                   double *d_chi2, int *d_info) {
-    k_export<<<(nfits + 127) / 128, 128, 0, L.stream>>>(nfits, d_results, d_params, d_chi2, d_info);
+void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int max_fits,
+                   const FitResult *d_results) {
+    k_export<<<dim3((max_fits + 127) / 128, ntables), 128, 0, L.stream>>>(d_exps, d_results);
     *L.counter += 1;
 }
 

@@ -180,6 +180,24 @@ int gppd_process_table_f32_dev(gppd_handle h, int slot, void *stream, int64_t n,
                                double *d_params, double *d_chi2, int32_t *d_info,
                                int8_t *d_state_out);
 
+/*
+ * Batch of tables (a night, or a chunk of one) in ONE launch sequence: every
+ * pass covers all tables, so the GPU stays full even though one table holds
+ * only 32 fits.  Arrays have `ntables` entries; pointer arrays hold device
+ * pointers, timer arrays hold HOST pointers (NULL entry / NULL array = bright
+ * table); nwindow_rows may be NULL (whole-table fits); d_info / d_state_out may
+ * be NULL.  d_offsets (40 complex128, shared) may be NULL (fit the centres).
+ */
+int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t ntables,
+                                const int64_t *n, const int64_t *nwindow_rows,
+                                const int32_t *const *d_time_us, const double *mjd,
+                                const float *const *d_volt, const double *d_offsets,
+                                const double *const *timer1, const int64_t *n1,
+                                const double *const *timer2, const int64_t *n2,
+                                const gppd_options *opt, float *const *d_volt_out,
+                                double *const *d_params, double *const *d_chi2,
+                                int32_t *const *d_info, int8_t *const *d_state_out);
+
 /* number of kernels this library has launched on the handle so far */
 int64_t gppd_launch_count(gppd_handle h);
 
@@ -193,6 +211,7 @@ int64_t gppd_launch_count(gppd_handle h);
 #define GPPD_PASS_DEMOD 4   /* demodulation + repack                      */
 #define GPPD_PASS_EXPORT 5  /* parameter export                           */
 #define GPPD_PASS_HARMONICS 6 /* Jacobi-Anger harmonic sums (harmonic evaluator) */
+#define GPPD_PASS_FALLBACK 7  /* direct re-fit of the fits the harmonic evaluator gave up on */
 #define GPPD_NPASS 8
 int gppd_enable_timing(gppd_handle h, int on);
 /* measured FP64 FMA throughput of the device in TFLOP/s (a DFMA micro-benchmark):

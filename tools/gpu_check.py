@@ -7,12 +7,14 @@ import oracle
 from gppd_b200 import synthetic as syn
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+method = sys.argv[2] if len(sys.argv) > 2 else "auto"
 tab = syn.make_table(n, k=0)
 t, z = syn.to_complex(tab, syn.stefan_centres())
 t0 = time.time(); oo, op, ol, onf = oracle.demodulateall(t, z, nthreads=8, return_nfev=True); t_or = time.time() - t0
-t0 = time.time(); go, gpar, gl, info, trace = gp.demodulateall(t, z, raw=True, return_info=True, return_trace=True); t_g = time.time() - t0
-t0 = time.time(); go, gpar, gl, info = gp.demodulateall(t, z, raw=True, return_info=True); t_g2 = time.time() - t0
+t0 = time.time(); go, gpar, gl, info, trace = gp.demodulateall(t, z, raw=True, return_info=True, return_trace=True, method=method); t_g = time.time() - t0
+t0 = time.time(); go, gpar, gl, info = gp.demodulateall(t, z, raw=True, return_info=True, method=method); t_g2 = time.time() - t0
 print("oracle s", t_or, "gpu s (first)", t_g, "second", t_g2)
+print("method used", info[:, 2].tolist())
 print("nfev oracle", onf.tolist()); print("nfev gpu   ", info[:, 0].tolist())
 rel = lambda a, b: np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
 print("param maxrel b", rel(gpar[:, 4], op[:, 4]).max(), "phi", np.abs(gpar[:, 5] - op[:, 5]).max(),
