@@ -17,14 +17,18 @@
 //     Z_k = (A + B) + j (C - D),   Z_{-k} = (A - B) + j (C + D)
 // i.e. 4 FMAs per (row, diode, |k|) for two harmonics.
 //
-// Kernel structure (k_harm_accumulate): one block per (job, group, part),
-// persistent over the part's row tiles of TR rows.  Two PRODUCER warps stage a
-// tile in shared memory: e^{j theta} from the basis, the four diodes' z (or y)
-// values, and per consumer warp the tile's start phasor e^{j k0 theta}.  Six
-// CONSUMER warps own KC = 4 harmonics each for the 4 diodes of the group:
-// 64 FP64 accumulators per thread, advanced by complex rotation (3 per row).
-// Tiles are double buffered, one __syncthreads per tile.  A part is a FIXED
-// segment of HARM_SEG_TILES tiles of the job (independent of the batch and of
+// Kernel structure (k_harm_accumulate): one block per (job, group, segment),
+// persistent over the segment's row tiles of TR rows.
+//   * Two PRODUCER warps stream the raw table bytes of the next-but-one tile into
+//     a 3-stage shared-memory ring with cp.async (16-byte copies: the group's 8
+//     VOLT floats, its FC pair, the row's basis, the state byte) -- no register
+//     dependency, so the global-memory latency is off the critical path -- and
+//     turn the previous stage into a compute tile: e^{j theta}, the four diodes' z
+//     (or y) values, and per consumer warp the start phasor e^{j k0 theta}.
+//   * Six CONSUMER warps own KC = 4 harmonics each for the 4 diodes of the group:
+//     64 FP64 accumulators per thread, advanced by complex rotation (3 per row).
+// Compute tiles are double buffered, one __syncthreads per tile.  A segment is a
+// FIXED run of HARM_SEG_TILES tiles of the job (independent of the batch and of
 // the launch shape) and k_harm_reduce adds the segments in index order, so a
 // fit's sums -- hence its whole NEWUOA trajectory -- do not depend on what else
 // is in the batch.
@@ -40,12 +44,22 @@ constexpr int KC = 4;                         // harmonics per consumer warp
 constexpr int NCH = HK / KC;                  // consumer warps
 constexpr int NPROD = 2;                      // producer warps
 constexpr int HARM_THREADS = (NCH + NPROD) * 32;
+constexpr int RAW_STAGES = 3;
+constexpr int ROWS_PER_PROD = TR / (NPROD * 32);
 static_assert(NCH * KC == HK, "HK must be a multiple of KC");
+static_assert(ROWS_PER_PROD * NPROD * 32 == TR, "TR must be a multiple of the producer threads");
 
 struct HarmTile {
     double2 e1[TR];            // (cos theta, sin theta)
     double2 start[NCH][TR];    // (cos, sin)((KC*ch + 1) theta)
     double2 v[4][TR];          // stream values of the group's 4 diodes
+};
+
+struct RawStage {              // raw bytes of one tile, as copied by cp.async
+    uint4 dio[4][TR];          // kind 0: [0],[1] = the group's 8 VOLT floats; kind 1: 4 complex128
+    uint4 fc[TR];              // kind 0: 16-byte chunk holding the FC pair; kind 1: the FC complex128
+    uint4 basis[TR];           // (sin theta, cos theta)
+    uint32_t state[TR];        // aligned word holding the row's state byte
 };
 
 __host__ __device__ inline int harm_segments(long long nrows) {
@@ -57,13 +71,39 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// unit phasor of the FC sample: (x, y) / |(x, y)|  (= exp(1im*angle(fc)), :388)
+__device__ __forceinline__ double2 fc_unit(double x, double y) {
+    const double h2 = fma(x, x, y * y);
+    if (h2 > 1.0e-280 && h2 < 1.0e280) {
+        const double inv = rsqrt(h2);
+        return make_double2(x * inv, y * inv);
+    }
+    return fc_phasor(make_double2(x, y));
+}
+
 template <int KIND>  // 0: z = w conj(p) (d - mu);  1: y = w p
 __global__ void __launch_bounds__(HARM_THREADS, 1)
 k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, int SP,
                   const double *spart1, const double *spart2, double *partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarmTile *tiles = reinterpret_cast<HarmTile *>(smem_raw);
+    RawStage *raws = reinterpret_cast<RawStage *>(smem_raw + 2 * sizeof(HarmTile));
     __shared__ double2 s_stats[16];
+    __shared__ double2 s_off[5];      // centres of the 4 diodes + FC (kind-0 tables)
     __shared__ double s_red[NPROD][32];
 
     constexpr int NCONST = KIND == 0 ? 7 : 2;
@@ -72,6 +112,7 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     const int job = jg >> 3, group = jg & 7;
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
+    const TableView &tv = tb.tv;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp >= NCH;
     // segment p of the job: tiles [p*HARM_SEG_TILES, ...)
@@ -79,12 +120,19 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     const int tile0 = p * HARM_SEG_TILES;
     if (tile0 >= ntiles) return;
     const int nt = (ntiles - tile0) < HARM_SEG_TILES ? (ntiles - tile0) : HARM_SEG_TILES;
+    // cp.async needs 16-byte aligned sources
+    const bool async_ok = tv.kind == 1 ||
+        ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
 
     if (threadIdx.x < 16) {
         s_stats[threadIdx.x] = tb.state
             ? stats_mean_weight(spart1, spart2, jg, SP, stats_segments(ji.nrows), threadIdx.x >> 2,
                                 threadIdx.x & 3)
             : make_double2(1.0, 1.0);
+    } else if (threadIdx.x < 21) {
+        const int k = threadIdx.x - 16;
+        const int ch = k < 4 ? group * 4 + k : fc_channel(group);
+        s_off[k] = (tv.kind == 0 && tv.offsets) ? __ldg(tv.offsets + ch) : make_double2(0.0, 0.0);
     }
     __syncthreads();
 
@@ -102,11 +150,49 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     double2 mu[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
-        mu[d] = (flags & 2u) ? row_sample(tb.tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
+        mu[d] = (flags & 2u) ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
 
-    auto produce = [&](int tile, HarmTile &T) {
-        const int ptid = threadIdx.x - NCH * 32;
-        for (int rr = ptid; rr < TR; rr += NPROD * 32) {
+    const int ptid = threadIdx.x - NCH * 32;
+
+    // ---- producer, step 1: raw bytes of a tile -> ring stage (asynchronous) ----
+    auto issue = [&](int tile, RawStage &S) {
+#pragma unroll
+        for (int j = 0; j < ROWS_PER_PROD; ++j) {
+            const int rr = ptid + j * NPROD * 32;
+            const int i = tile * TR + rr;
+            if (i >= ji.nrows) continue;
+            const long long r = ji.row0 + i;
+            cp_async16(&S.basis[rr], tb.basis + r);
+            if (tv.kind == 0) {
+                const char *row = reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride;
+                cp_async16(&S.dio[0][rr], row + 32 * group);
+                cp_async16(&S.dio[1][rr], row + 32 * group + 16);
+                cp_async16(&S.fc[rr], row + 256 + 16 * (group >> 1));
+            } else {
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    cp_async16(&S.dio[d][rr], tv.data + (long long)(group * 4 + d) * tv.n + r);
+                cp_async16(&S.fc[rr], tv.data + (long long)fc_channel(group) * tv.n + r);
+            }
+            if (tb.state) {
+                const int8_t *sp = tb.state + r;
+                const unsigned long long aw = reinterpret_cast<unsigned long long>(sp) & ~3ull;
+                if (aw >= reinterpret_cast<unsigned long long>(tb.state) &&
+                    aw + 4 <= reinterpret_cast<unsigned long long>(tb.state + tv.n)) {
+                    cp_async4(&S.state[rr], reinterpret_cast<const void *>(aw));
+                } else {  // first / last rows: do not read outside the state array
+                    const unsigned sh = 8u * (unsigned)(reinterpret_cast<unsigned long long>(sp) & 3ull);
+                    S.state[rr] = ((unsigned)(unsigned char)*sp) << sh;
+                }
+            }
+        }
+    };
+
+    // ---- producer, step 2: ring stage (or, unaligned tables, global memory) -> compute tile
+    auto produce = [&](int tile, const RawStage &S, HarmTile &T) {
+#pragma unroll
+        for (int j = 0; j < ROWS_PER_PROD; ++j) {
+            const int rr = ptid + j * NPROD * 32;
             const int i = tile * TR + rr;
             double2 e1 = make_double2(1.0, 0.0);
             double2 vv[4];
@@ -114,24 +200,59 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
             for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
             if (i < ji.nrows) {
                 const long long r = ji.row0 + i;
-                const double2 sc = tb.basis[r];
-                e1 = make_double2(sc.y, sc.x);
+                double2 sc, fcs, dd[4];
                 int st = ST_NORMAL;
-                bool valid = true;
-                if (tb.state) {
-                    st = tb.state[r];
-                    valid = row_valid(st, flags);
+                if (async_ok) {
+                    const uint4 bw = S.basis[rr];
+                    sc = make_double2(__hiloint2double(bw.y, bw.x), __hiloint2double(bw.w, bw.z));
+                    if (tv.kind == 0) {
+                        uint4 a = S.dio[0][rr], b = S.dio[1][rr], f = S.fc[rr];
+                        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        uint32_t fx = (group & 1) ? f.z : f.x, fy = (group & 1) ? f.w : f.y;
+                        if (tv.big_endian) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
+                            fx = bswap32(fx);
+                            fy = bswap32(fy);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 4; ++d)
+                            dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - s_off[d].x,
+                                                 (double)__uint_as_float(w[2 * d + 1]) - s_off[d].y);
+                        fcs = make_double2((double)__uint_as_float(fx) - s_off[4].x,
+                                           (double)__uint_as_float(fy) - s_off[4].y);
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            const uint4 q = S.dio[d][rr];
+                            dd[d] = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+                        }
+                        const uint4 q = S.fc[rr];
+                        fcs = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+                    }
+                    if (tb.state) {
+                        const unsigned sh =
+                            8u * (unsigned)(reinterpret_cast<unsigned long long>(tb.state + r) & 3ull);
+                        st = (int)(signed char)((S.state[rr] >> sh) & 0xffu);
+                    }
+                } else {
+                    sc = tb.basis[r];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, r, group * 4 + d);
+                    fcs = row_sample(tv, r, fc_channel(group));
+                    if (tb.state) st = tb.state[r];
                 }
+                e1 = make_double2(sc.y, sc.x);
+                const bool valid = tb.state ? row_valid(st, flags) : true;
                 if (valid) {
-                    const double2 fc = fc_phasor(row_sample(tb.tv, r, fc_channel(group)));
+                    const double2 fc = fc_unit(fcs.x, fcs.y);
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
                         const double2 mw = s_stats[d * 4 + (st & 3)];
                         const double pr = mw.x * fc.x, pi = mw.x * fc.y;   // p = power .* FCphasor
                         const double wpr = mw.y * pr, wpi = mw.y * pi;
                         if (KIND == 0) {
-                            const double2 dd = row_sample(tb.tv, r, group * 4 + d);
-                            const double dr = dd.x - mu[d].x, di = dd.y - mu[d].y;
+                            const double dr = dd[d].x - mu[d].x, di = dd[d].y - mu[d].y;
                             vv[d].x = fma(wpr, dr, wpi * di);
                             vv[d].y = fma(wpr, di, -(wpi * dr));
                             cst[d * 7 + 0] += mw.y;
@@ -187,16 +308,35 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
         }
     };
 
-    if (producer) produce(tile0, tiles[0]);
+    // Pipeline.  Producers: stage (it+2) is being copied while stage (it+1) is turned
+    // into compute tile (it+1) while the consumers work on compute tile it.  Every
+    // producer thread reads back only the ring bytes it copied itself, so its own
+    // cp.async.wait_group is the only synchronisation the ring needs.
+    if (producer) {
+        if (async_ok) {
+            issue(tile0, raws[0]);
+            cp_async_commit();
+            if (nt > 1) issue(tile0 + 1, raws[1]);
+            cp_async_commit();
+            cp_async_wait<1>();
+        }
+        produce(tile0, raws[0], tiles[0]);
+    }
     __syncthreads();
     for (int it = 0; it < nt; ++it) {
         if (producer) {
-            if (it + 1 < nt) produce(tile0 + it + 1, tiles[(it + 1) & 1]);
+            if (async_ok) {
+                if (it + 2 < nt) issue(tile0 + it + 2, raws[(it + 2) % RAW_STAGES]);
+                cp_async_commit();
+                cp_async_wait<1>();
+            }
+            if (it + 1 < nt) produce(tile0 + it + 1, raws[(it + 1) % RAW_STAGES], tiles[(it + 1) & 1]);
         } else {
             consume(tiles[it & 1]);
         }
         __syncthreads();
     }
+    if (producer && async_ok) cp_async_wait<0>();
 
     double *out = partial + ((long long)jg * P + p) * 4 * HP;
     if (!producer) {
@@ -255,7 +395,7 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab) {
     static bool attr_set = false;
-    const int smem = 2 * (int)sizeof(HarmTile);
+    const int smem = 2 * (int)sizeof(HarmTile) + RAW_STAGES * (int)sizeof(RawStage);
     if (!attr_set) {
         cudaFuncSetAttribute(k_harm_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_harm_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
