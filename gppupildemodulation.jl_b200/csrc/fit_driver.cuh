@@ -16,16 +16,19 @@
 
 namespace gppd {
 
-struct FitDriver {
+// WARP: see Newuoa2T (true: the object is shared by the 32 converged lanes of a warp).
+template <bool WARP>
+struct FitDriverT {
     enum { SCAN, NEWUOA1, LKL_X, LKL_FLIP, NEWUOA2, FINAL, DONE };
-    Newuoa2 nu;
+    Newuoa2T<WARP> nu;
     double b, phi;         // point to evaluate next
     double x1, x2;         // current solution
     double best, lklval, phipi, chi2;
     double rhobeg, rhoend;
     int maxfun, phase, k, kbest, have_nan, nfev, second, status;
 
-    __device__ void start(const FitOptions &o) {
+    __device__ void start(const FitOptions &o, const NuSinCos *angles) {
+        nu.ang = angles;
         rhobeg = o.rhobeg;
         rhoend = o.rhoend;
         maxfun = o.maxfun;
@@ -125,5 +128,7 @@ struct FitDriver {
         }
     }
 };
+
+typedef FitDriverT<false> FitDriver;
 
 }  // namespace gppd

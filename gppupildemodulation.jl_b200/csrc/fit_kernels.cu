@@ -8,12 +8,19 @@
 //
 // Two evaluators of chi2(b, phi) drive the same fit procedure (fit_driver.cuh):
 //
-//  k_fit_harmonic  one THREAD per fit.  chi2 from the per-fit harmonic table
-//                  (harm_kernels.cu): S_gd = sum_k J_k(b) e^{-jkq} Z_k in O(HK)
-//                  flops per call.  All fits of a warp evaluate in lock step
-//                  (the solver is a resumable state machine), the solver algebra
-//                  in between diverges.  Gives up (fallback flag) when |b| > 5 or
-//                  the job has no uniform phase quantum for the requested phi.
+//  k_fit_harmonic_warp   one WARP per fit (the default).  chi2 from the per-fit
+//                  harmonic table (harm_kernels.cu): S_gd = sum_k J_k(b) e^{-jkq} Z_k,
+//                  lane k holding harmonic k, butterfly-summed in a fixed order.
+//                  The solver state lives once per warp in shared memory; all
+//                  lanes run the same (uniform) solver algebra and split the
+//                  NEWUOA angle searches between them.  Low latency: a whole-file
+//                  job has only 32 fits.
+//  k_fit_harmonic  one THREAD per fit (very large batches of small windows, where
+//                  throughput matters more than latency).  All fits of a warp
+//                  evaluate in lock step (the solver is a resumable state machine),
+//                  the solver algebra in between diverges.
+//                  Both give up (fallback flag) when |b| > 5 or the job has no
+//                  uniform phase quantum for the requested phi.
 //
 //  k_fit_direct    one BLOCK per fit, the reference's own formulation: one pass
 //                  over the rows per objective call,
@@ -25,6 +32,8 @@
 //
 // Both compute chi2 = (S_dd - Re(conj(c') S_d' + conj(a) S_gd)) / N, the
 // reference's sum w |c + a g - d|^2 / N at its own least-squares (c, a).
+#include <cstdlib>
+
 #include "fit_driver.cuh"
 #include "fit_math.cuh"
 #include "gppd_device.cuh"
@@ -33,6 +42,17 @@
 namespace gppd {
 
 constexpr int FIT_THREADS = 256;
+// up to this many fits per batch the harmonic fit runs one warp per fit; above, one
+// thread per fit (GPPD_FIT_WARP_MAX_FITS overrides, for the tests)
+static int fit_warp_max_fits() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("GPPD_FIT_WARP_MAX_FITS");
+        v = e ? atoi(e) : 400000;
+    }
+    return v;
+}
+#define FIT_WARP_MAX_FITS fit_warp_max_fits()
 
 template <int NV>
 __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *red /* [NV][8] */) {
@@ -55,7 +75,8 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *red /* [N
     }
 }
 
-__device__ __forceinline__ void store_result(FitResult *results, int fit, const FitDriver &drv,
+template <class Driver>
+__device__ __forceinline__ void store_result(FitResult *results, int fit, const Driver &drv,
                                              const JobInfo &ji, double cre, double cim, double are,
                                              double aim, int method) {
     FitResult r;
@@ -139,10 +160,184 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
     return true;
 }
 
+// the solver's 49-angle table (newuoa2.cuh), filled by the first 50 threads of a block
+__device__ __forceinline__ void fill_angle_table(NuSinCos *tab) {
+    if (threadIdx.x <= NU_ANGLES) nu_angle_entry(threadIdx.x, &tab[threadIdx.x]);
+}
+
+// ---- one warp per fit ---------------------------------------------------------
+// J_lane(b) for lane <= HK: every lane runs bessel_j's recurrence (uniform control
+// flow, no array) and keeps the term of its own order.
+__device__ __forceinline__ double bessel_j_lane(double b, int lane) {
+    if (b == 0.0) return lane == 0 ? 1.0 : 0.0;
+    const int M = 56;
+    const double tb = 2.0 / b;
+    double jp = 0.0, jc = 1.0e-250, sum = 0.0, mine = 0.0;
+#pragma unroll 1
+    for (int k = M; k >= 1; --k) {
+        const double jm = fma((double)k * tb, jc, -jp);  // J_{k-1}
+        jp = jc;
+        jc = jm;
+        if (k - 1 == lane) mine = jc;
+        if (((k - 1) & 1) == 0) sum += (k - 1 == 0) ? jc : 2.0 * jc;
+        if (fabs(jc) > 1.0e200) {
+            jc *= 1.0e-200;
+            jp *= 1.0e-200;
+            sum *= 1.0e-200;
+            if (lane >= k - 1) mine *= 1.0e-200;
+        }
+    }
+    return mine * (1.0 / sum);
+}
+
+struct HarmLane {       // lane k = 1..HK: (A, B, C, D) of harmonic k; lane 0: (Z_0.re, Z_0.im)
+    double zA, zB, zC, zD;
+    double yA, yB, yC, yD;
+};
+
+template <bool OFFS>
+__device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitConsts &kc,
+                                                   const JobInfo &ji, int lane, double b, double phi,
+                                                   double &f, double &cre, double &cim, double &are,
+                                                   double &aim) {
+    double q;
+    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;   // warp-uniform
+    const double J = bessel_j_lane(b, lane);
+    double sq, cq;
+    sincos(q, &sq, &cq);
+    // (ck, sk) = (cos lane q, sin lane q), by the rotation recurrence of the serial evaluator
+    double ck = 1.0, sk = 0.0, rc = 1.0, rs = 0.0;
+#pragma unroll 1
+    for (int k = 1; k <= HK; ++k) {
+        const double cn = fma(rc, cq, -(rs * sq)), sn = fma(rs, cq, rc * sq);
+        rc = cn;
+        rs = sn;
+        if (k == lane) { ck = rc; sk = rs; }
+    }
+    double tr = 0.0, ti = 0.0, ur = 0.0, ui = 0.0;
+    if (lane == 0) {
+        tr = J * h.zA;
+        ti = J * h.zB;
+        if (OFFS) { ur = J * h.yA; ui = J * h.yB; }
+    } else if (lane <= HK) {
+        const double tj = 2.0 * J;
+        if ((lane & 1) == 0) {
+            tr = tj * fma(ck, h.zA, -(sk * h.zD));
+            ti = tj * fma(ck, h.zC, -(sk * h.zB));
+            if (OFFS) {
+                ur = tj * fma(ck, h.yA, -(sk * h.yD));
+                ui = tj * fma(ck, h.yC, -(sk * h.yB));
+            }
+        } else {
+            tr = tj * fma(ck, h.zB, sk * h.zC);
+            ti = tj * -fma(ck, h.zD, sk * h.zA);
+            if (OFFS) {
+                ur = tj * -fma(ck, h.yB, sk * h.yC);
+                ui = tj * fma(ck, h.yD, sk * h.yA);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // fixed-order butterfly: every lane gets the same bits
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        ti += __shfl_xor_sync(0xffffffffu, ti, o);
+        if (OFFS) {
+            ur += __shfl_xor_sync(0xffffffffu, ur, o);
+            ui += __shfl_xor_sync(0xffffffffu, ui, o);
+        }
+    }
+    f = solve_linear(kc, OFFS, tr, ti, ur, ui, cre, cim, are, aim);
+    return true;
+}
+
+constexpr int FITW_WARPS = 4;   // fits per block
+
+template <bool OFFS>
+__global__ void __launch_bounds__(FITW_WARPS * 32)
+k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *htab, int nfits,
+                    FitOptions opt, FitResult *results, double *trace) {
+    __shared__ FitDriverT<true> s_drv[FITW_WARPS];
+    __shared__ NuSinCos s_ang[NU_ANGLES + 1];
+    fill_angle_table(s_ang);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fit = blockIdx.x * FITW_WARPS + warp;
+    if (fit >= nfits) return;
+    const int job = fit / NDIODE, ch = fit % NDIODE;
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    const double *H = htab + fit;
+
+    FitConsts kc;
+    kc.sw = H[(long long)HV_SW * nfits];
+    kc.sdd = H[(long long)HV_SDD * nfits];
+    kc.sgg = H[(long long)HV_SGG * nfits];
+    kc.sdr = H[(long long)HV_SDR * nfits];
+    kc.sdi = H[(long long)HV_SDI * nfits];
+    kc.nvalid = (double)ji.nvalid;
+    kc.mur = kc.mui = 0.0;
+    if (OFFS) {
+        double2 mu = row_sample(tb.tv, ji.row0, ch);
+        kc.mur = mu.x;
+        kc.mui = mu.y;
+    }
+    HarmLane h;
+    h.zA = h.zB = h.zC = h.zD = h.yA = h.yB = h.yC = h.yD = 0.0;
+    if (lane == 0) {
+        h.zA = H[(long long)HV_Z0R * nfits];
+        h.zB = H[(long long)HV_Z0I * nfits];
+        if (OFFS) {
+            h.yA = H[(long long)HV_Y0R * nfits];
+            h.yB = H[(long long)HV_Y0I * nfits];
+        }
+    } else if (lane <= HK) {
+        const double *z = H + (long long)(HV_ZK + 4 * (lane - 1)) * nfits;
+        h.zA = z[0]; h.zB = z[nfits]; h.zC = z[2 * (long long)nfits]; h.zD = z[3 * (long long)nfits];
+        if (OFFS) {
+            const double *y = H + (long long)(HV_YK + 4 * (lane - 1)) * nfits;
+            h.yA = y[0]; h.yB = y[nfits]; h.yC = y[2 * (long long)nfits]; h.yD = y[3 * (long long)nfits];
+        }
+    }
+
+    FitDriverT<true> &drv = s_drv[warp];
+    drv.start(opt, s_ang);
+    double cre = 0, cim = 0, are = 0, aim = 0, f = 0;
+    double *tr = trace ? trace + (long long)fit * (3 * 160) : nullptr;
+    bool failed = false;
+    for (;;) {
+        const double b = drv.b, phi = drv.phi;
+        if (!eval_harmonic_warp<OFFS>(h, kc, ji, lane, b, phi, f, cre, cim, are, aim)) {
+            failed = true;
+            break;
+        }
+        if (tr && lane == 0 && drv.nfev < 160) {
+            tr[3 * drv.nfev] = b;
+            tr[3 * drv.nfev + 1] = phi;
+            tr[3 * drv.nfev + 2] = f;
+        }
+        if (!drv.step(opt, f)) break;
+    }
+    if (lane != 0) return;
+    if (failed) {
+        FitResult r;
+        r.cre = r.cim = r.are = r.aim = r.b = r.phi = r.alpha = r.chi2 = 0.0;
+        r.q = r.cq = r.sq = 0.0;
+        r.uniform = 0; r.nfev = 0; r.status = 0; r.method = 0; r.second = 0;
+        r.fallback = 1; r.pad = 0;
+        results[fit] = r;
+        return;
+    }
+    store_result(results, fit, drv, ji, cre, cim, are, aim, 2);
+}
+
+// ---- one thread per fit ---------------------------------------------------------
 template <bool OFFS>
 __global__ void __launch_bounds__(128)
 k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, int nfits,
                FitOptions opt, FitResult *results, double *trace) {
+    __shared__ NuSinCos s_ang[NU_ANGLES + 1];
+    fill_angle_table(s_ang);
+    __syncthreads();
     const int fit = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = fit < nfits;
     const int fidx = live ? fit : 0;
@@ -166,7 +361,7 @@ k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, i
     }
 
     FitDriver drv;
-    drv.start(opt);
+    drv.start(opt, s_ang);
     double cre = 0, cim = 0, are = 0, aim = 0, f = 0;
     double *tr = (trace && live) ? trace + (long long)fit * (3 * 160) : nullptr;
     bool running = live, failed = false;
@@ -204,13 +399,24 @@ void launch_fit_harmonic(const Launcher &L, const TableDesc *d_tabs, const JobIn
                          const double *d_htab, int nfits, const FitOptions &opt,
                          FitResult *d_results, double *d_trace) {
     if (nfits <= 0) return;
-    const int blocks = (nfits + 127) / 128;
-    if (opt.flags & 2u)
-        k_fit_harmonic<true><<<blocks, 128, 0, L.stream>>>(d_tabs, d_jobs, d_htab, nfits, opt,
-                                                          d_results, d_trace);
-    else
-        k_fit_harmonic<false><<<blocks, 128, 0, L.stream>>>(d_tabs, d_jobs, d_htab, nfits, opt,
-                                                           d_results, d_trace);
+    const bool offs = (opt.flags & 2u) != 0;
+    if (nfits <= FIT_WARP_MAX_FITS) {   // latency matters: one warp per fit
+        const int blocks = (nfits + FITW_WARPS - 1) / FITW_WARPS;
+        if (offs)
+            k_fit_harmonic_warp<true><<<blocks, FITW_WARPS * 32, 0, L.stream>>>(
+                d_tabs, d_jobs, d_htab, nfits, opt, d_results, d_trace);
+        else
+            k_fit_harmonic_warp<false><<<blocks, FITW_WARPS * 32, 0, L.stream>>>(
+                d_tabs, d_jobs, d_htab, nfits, opt, d_results, d_trace);
+    } else {                            // throughput matters: one thread per fit
+        const int blocks = (nfits + 127) / 128;
+        if (offs)
+            k_fit_harmonic<true><<<blocks, 128, 0, L.stream>>>(d_tabs, d_jobs, d_htab, nfits, opt,
+                                                              d_results, d_trace);
+        else
+            k_fit_harmonic<false><<<blocks, 128, 0, L.stream>>>(d_tabs, d_jobs, d_htab, nfits, opt,
+                                                               d_results, d_trace);
+    }
     *L.counter += 1;
 }
 
@@ -226,8 +432,10 @@ k_fit_direct(const TableDesc *tabs, const JobInfo *jobs, int SP, const double *s
              const double *spart2, FitOptions opt, FitResult *results, double *trace) {
     __shared__ double red[7 * 8];
     __shared__ double2 st4[4];
+    __shared__ NuSinCos s_ang[NU_ANGLES + 1];
     const int fit = blockIdx.x;
     if (!SCRATCH && !results[fit].fallback) return;
+    fill_angle_table(s_ang);
     const int job = fit / NDIODE, ch = fit % NDIODE;
     const int group = ch >> 2, fcch = fc_channel(group);
     const JobInfo ji = jobs[job];
@@ -307,7 +515,7 @@ k_fit_direct(const TableDesc *tabs, const JobInfo *jobs, int SP, const double *s
     __syncthreads();  // z / y visible to the whole block
 
     FitDriver drv;
-    drv.start(opt);
+    drv.start(opt, s_ang);
     double cre = 0, cim = 0, are = 0, aim = 0, f = 0;
     double *tr = trace ? trace + (long long)fit * (3 * 160) : nullptr;
     for (;;) {

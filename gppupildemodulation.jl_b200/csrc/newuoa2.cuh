@@ -59,7 +59,29 @@ __host__ __device__ inline void nu_sincos(double x, double *sn, double *cs) {
 
 enum { NU_SUCCESS = 0, NU_ROUNDING_ERRORS = -2, NU_TOO_MANY_EVALUATIONS = -3 };
 
-struct Newuoa2 {
+// The three angle searches (TRSAPP, BIGLAG, BIGDEN) always probe the same 49
+// angles 2 pi i / 50: their sines and cosines are tabulated once with nu_sincos
+// (so the tabulated values are the very bits the oracle computes in its loops).
+constexpr int NU_ANGLES = 49;
+struct NuSinCos {
+    double s, c;
+};
+__host__ __device__ inline void nu_angle_entry(int i, NuSinCos *e) {
+    const double twopi = 6.283185307179586476925;
+    const double temp = twopi / (double)(NU_ANGLES + 1);
+    const double angle = (double)i * temp;
+    nu_sincos(angle, &e->s, &e->c);
+}
+
+// WARP = false: one thread owns the solver (host build, thread-per-fit and
+//               block-replicated device use); the angle searches are serial loops.
+// WARP = true : the 32 lanes of a converged warp run the same solver (the object
+//               may live in shared memory, every lane storing identical values);
+//               the angle searches are split over the lanes, two angles each, and
+//               reduced with the serial loop's own selection rule, so the result
+//               is bit for bit the serial one.
+template <bool WARP>
+struct Newuoa2T {
     static constexpr int N = 2, NPT = 5, NP = 3, NH = 3, NPTM = 2, NDIM = 7;
 
     // ---- interface ----
@@ -78,6 +100,9 @@ struct Newuoa2 {
     double ratio, crvmin, beta, alpha, dstep, fcur;
     int nftest, nfm, nfmm, kopt, idz, itest, nfsav, knew, ipt, jpt;
     int phase;  // 0 = not started, 1 = waiting for an objective value, 2 = done
+    const NuSinCos *ang;  // [0..49]: nu_angle_entry(i), set by the owner before start()
+    // BIGDEN work space (members so that a shared-memory solver keeps them there)
+    double den[10], denex[10], par[10], wvec_[NDIM * 5], prod_[NDIM * 5];
 
 #define XPT(k, j) xpt_[((k)-1) + ((j)-1) * NPT]
 #define BMAT(i, j) bmat_[((i)-1) + ((j)-1) * NDIM]
@@ -117,6 +142,108 @@ struct Newuoa2 {
     }
 
     // ------------------------------------------------------------------
+    // Angle search shared by TRSAPP / BIGLAG / BIGDEN: v_i = val(sin, cos) of the
+    // 49 tabulated angles; Powell's loop keeps the first best value (MODE 0: the
+    // smallest, MODE 1: the largest magnitude) if it beats v0, together with its
+    // two neighbours (v_0 = v_50 = v0) for the parabolic refinement:
+    //     for i: if better(v_i, best) {best = v_i; isave = i; tempa = v_{i-1};}
+    //            else if (i == isave + 1) tempb = v_i;
+    //     if (isave == 0) tempa = v_49;  if (isave == 49) tempb = v0;
+    template <int MODE>
+    __host__ __device__ static bool better(double a, double b) {
+        return MODE == 0 ? (a < b) : (fabs(a) > fabs(b));
+    }
+    template <int MODE, class F>
+    __host__ __device__ void angle_search(F val, double v0, int &isave, double &best, double &tempa,
+                                          double &tempb) const {
+        const int iu = NU_ANGLES;
+#ifdef __CUDA_ARCH__
+        if (WARP) {
+            const unsigned full = 0xffffffffu;
+            const int lane = threadIdx.x & 31;
+            const int i1 = lane + 1, i2 = lane + 33;
+            const bool has2 = i2 <= iu;
+            const NuSinCos a1 = ang[i1], a2 = ang[has2 ? i2 : i1];
+            const double v1 = val(a1.s, a1.c), v2 = val(a2.s, a2.c);
+            double bv = v0;
+            int bi = 0;
+            if (better<MODE>(v1, bv)) { bv = v1; bi = i1; }
+            if (has2 && better<MODE>(v2, bv)) { bv = v2; bi = i2; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(full, bv, o);
+                const int oi = __shfl_xor_sync(full, bi, o);
+                if (better<MODE>(ov, bv) || (!better<MODE>(bv, ov) && oi < bi)) { bv = ov; bi = oi; }
+            }
+            isave = bi;
+            best = bv;
+            // neighbours v_{ja}, v_{jb} of the winner
+            const int ja = bi == 0 ? iu : bi - 1, jb = bi + 1;          // 0..49, 1..50
+            const int sa = ja == 0 ? 1 : ja, sb = jb == iu + 1 ? 1 : jb;  // a valid table slot
+            const double a_lo = __shfl_sync(full, v1, (sa - 1) & 31), a_hi = __shfl_sync(full, v2, (sa - 1) & 31);
+            const double b_lo = __shfl_sync(full, v1, (sb - 1) & 31), b_hi = __shfl_sync(full, v2, (sb - 1) & 31);
+            tempa = ja == 0 ? v0 : (sa <= 32 ? a_lo : a_hi);
+            tempb = jb == iu + 1 ? v0 : (sb <= 32 ? b_lo : b_hi);
+            return;
+        }
+#elif defined(NU_HOST_EMULATE_WARP)
+        // test scaffolding (tests/native/newuoa2_host.cpp): the lane-parallel
+        // selection above, emulated lane by lane on the host
+        if (WARP) {
+            double v1[32], v2[32], bv[32];
+            int bi[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int i1 = lane + 1, i2 = lane + 33;
+                const bool has2 = i2 <= iu;
+                v1[lane] = val(ang[i1].s, ang[i1].c);
+                v2[lane] = val(ang[has2 ? i2 : i1].s, ang[has2 ? i2 : i1].c);
+                bv[lane] = v0;
+                bi[lane] = 0;
+                if (better<MODE>(v1[lane], bv[lane])) { bv[lane] = v1[lane]; bi[lane] = i1; }
+                if (has2 && better<MODE>(v2[lane], bv[lane])) { bv[lane] = v2[lane]; bi[lane] = i2; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                double nv[32];
+                int ni[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    const double ov = bv[lane ^ o];
+                    const int oi = bi[lane ^ o];
+                    nv[lane] = bv[lane];
+                    ni[lane] = bi[lane];
+                    if (better<MODE>(ov, bv[lane]) || (!better<MODE>(bv[lane], ov) && oi < bi[lane])) {
+                        nv[lane] = ov;
+                        ni[lane] = oi;
+                    }
+                }
+                for (int lane = 0; lane < 32; ++lane) { bv[lane] = nv[lane]; bi[lane] = ni[lane]; }
+            }
+            isave = bi[7];
+            best = bv[7];
+            const int ja = isave == 0 ? iu : isave - 1, jb = isave + 1;
+            const int sa = ja == 0 ? 1 : ja, sb = jb == iu + 1 ? 1 : jb;
+            tempa = ja == 0 ? v0 : (sa <= 32 ? v1[(sa - 1) & 31] : v2[(sa - 1) & 31]);
+            tempb = jb == iu + 1 ? v0 : (sb <= 32 ? v1[(sb - 1) & 31] : v2[(sb - 1) & 31]);
+            return;
+        }
+#endif
+        double prev = v0, v = v0;
+        best = v0;
+        isave = 0;
+        for (int i = 1; i <= iu; ++i) {
+            v = val(ang[i].s, ang[i].c);
+            if (better<MODE>(v, best)) {
+                best = v;
+                isave = i;
+                tempa = prev;
+            } else if (i == isave + 1) {
+                tempb = v;
+            }
+            prev = v;
+        }
+        if (isave == 0) tempa = v;
+        if (isave == iu) tempb = v0;
+    }
+
+    // ------------------------------------------------------------------
     __host__ __device__ void trsapp(double *step) {
         const double half = 0.5, zero = 0.0;
         const double twopi = 6.283185307179586476925;
@@ -125,8 +252,8 @@ struct Newuoa2 {
         int iterc = 0;
         const int itermax = N;
         double qred, dd, ds, ss, gg, ggbeg, bstep, dhd, alph, temp, qadd, ggsav;
-        double sg, shs, sgk, angtest, tempa = 0, tempb = 0, dg, dhs, cf, qbeg, qsav;
-        double qmin, qnew = 0, angle, cth, sth, reduc, rat;
+        double sg, shs, sgk, angtest, tempa = 0, tempb = 0, dg, dhs, cf, qbeg;
+        double qmin, angle, cth, sth, reduc, rat;
         int isave;
 
         for (int i = 1; i <= N; ++i) dd_[i] = xopt[i];
@@ -219,26 +346,11 @@ struct Newuoa2 {
             }
             cf = half * (shs - dhd);
             qbeg = sg + cf;
-            qsav = qbeg;
-            qmin = qbeg;
-            isave = 0;
-            const int iu = 49;
+            const int iu = NU_ANGLES;
             temp = twopi / (double)(iu + 1);
-            for (int i = 1; i <= iu; ++i) {
-                angle = (double)i * temp;
-                nu_sincos(angle, &sth, &cth);
-                qnew = (sg + cf * cth) * cth + (dg + dhs * cth) * sth;
-                if (qnew < qmin) {
-                    qmin = qnew;
-                    isave = i;
-                    tempa = qsav;
-                } else if (i == isave + 1) {
-                    tempb = qnew;
-                }
-                qsav = qnew;
-            }
-            if (isave == 0) tempa = qnew;
-            if (isave == iu) tempb = qbeg;
+            angle_search<0>(
+                [=](double sn, double cs) { return (sg + cf * cs) * cs + (dg + dhs * cs) * sn; }, qbeg,
+                isave, qmin, tempa, tempb);
             angle = zero;
             if (tempa != tempb) {
                 tempa -= qmin;
@@ -272,7 +384,7 @@ struct Newuoa2 {
         double delsq = dlt * dlt;
         int iterc = 0, isave;
         double temp, sum, dd, gg, sp, dhd, scale, tau = 0, ss, denom;
-        double cf1, cf2, cf3, cf4, cf5, taubeg, taumax, tauold, angle, cth, sth;
+        double cf1, cf2, cf3, cf4, cf5, taubeg, taumax, angle, cth, sth;
         double tempa = 0, tempb = 0, step;
 
         for (int k = 1; k <= NPT; ++k) hcol[k] = zero;
@@ -356,26 +468,11 @@ struct Newuoa2 {
             cf1 = half * cf1;
             cf4 = half * cf4 - cf1;
             taubeg = cf1 + cf2 + cf4;
-            taumax = taubeg;
-            tauold = taubeg;
-            isave = 0;
-            const int iu = 49;
+            const int iu = NU_ANGLES;
             temp = twopi / (double)(iu + 1);
-            for (int i = 1; i <= iu; ++i) {
-                angle = (double)i * temp;
-                nu_sincos(angle, &sth, &cth);
-                tau = cf1 + (cf2 + cf4 * cth) * cth + (cf3 + cf5 * cth) * sth;
-                if (fabs(tau) > fabs(taumax)) {
-                    taumax = tau;
-                    isave = i;
-                    tempa = tauold;
-                } else if (i == isave + 1) {
-                    tempb = tau;
-                }
-                tauold = tau;
-            }
-            if (isave == 0) tempa = tau;
-            if (isave == iu) tempb = taubeg;
+            angle_search<1>(
+                [=](double sn, double cs) { return cf1 + (cf2 + cf4 * cs) * cs + (cf3 + cf5 * cs) * sn; },
+                taubeg, isave, taumax, tempa, tempb);
             step = zero;
             if (tempa != tempb) {
                 tempa -= taumax;
@@ -399,13 +496,12 @@ struct Newuoa2 {
     __host__ __device__ void bigden() {
         const double half = 0.5, one = 1.0, quart = 0.25, two = 2.0, zero = 0.0;
         const double twopi = 6.283185307179586476925;
-        double den[10], denex[10], par[10], s[N + 1];
-        double wvec_[NDIM * 5], prod_[NDIM * 5];
+        double s[N + 1];
 #define WVEC(k, j) wvec_[((k)-1) + ((j)-1) * NDIM]
 #define PROD(k, j) prod_[((k)-1) + ((j)-1) * NDIM]
         double temp, alph, dd, ds, ss, xosq, dtest, dstemp, sstemp, diff;
         double ssden, densav, xoptd, xopts, tempa = 0, tempb = 0, tempc, sum;
-        double denold, denmax, sumold, angle, step, tau;
+        double denold, denmax, angle, step, tau;
         int ksav, iterc, isave, nw;
 
         for (int k = 1; k <= NPT; ++k) w[N + k] = zero;
@@ -561,31 +657,31 @@ struct Newuoa2 {
 
             sum = denex[1] + denex[2] + denex[4] + denex[6] + denex[8];
             denold = sum;
-            denmax = sum;
-            isave = 0;
-            const int iu = 49;
+            const int iu = NU_ANGLES;
             temp = twopi / (double)(iu + 1);
             par[1] = one;
-            for (int i = 1; i <= iu; ++i) {
-                angle = (double)i * temp;
-                nu_sincos(angle, &par[3], &par[2]);
-                for (int j = 4; j <= 8; j += 2) {
-                    par[j] = par[2] * par[j - 2] - par[3] * par[j - 1];
-                    par[j + 1] = par[2] * par[j - 1] + par[3] * par[j - 2];
-                }
-                sumold = sum;
-                sum = zero;
-                for (int j = 1; j <= 9; ++j) sum += denex[j] * par[j];
-                if (fabs(sum) > fabs(denmax)) {
-                    denmax = sum;
-                    isave = i;
-                    tempa = sumold;
-                } else if (i == isave + 1) {
-                    tempb = sum;
-                }
+            {
+                const double e1 = denex[1], e2 = denex[2], e3 = denex[3], e4 = denex[4], e5 = denex[5],
+                             e6 = denex[6], e7 = denex[7], e8 = denex[8], e9 = denex[9];
+                angle_search<1>(
+                    [=](double sn, double cs) {
+                        const double p4 = cs * cs - sn * sn, p5 = cs * sn + sn * cs;
+                        const double p6 = cs * p4 - sn * p5, p7 = cs * p5 + sn * p4;
+                        const double p8 = cs * p6 - sn * p7, p9 = cs * p7 + sn * p6;
+                        double sm = 0.0;
+                        sm += e1 * 1.0;
+                        sm += e2 * cs;
+                        sm += e3 * sn;
+                        sm += e4 * p4;
+                        sm += e5 * p5;
+                        sm += e6 * p6;
+                        sm += e7 * p7;
+                        sm += e8 * p8;
+                        sm += e9 * p9;
+                        return sm;
+                    },
+                    denold, isave, denmax, tempa, tempb);
             }
-            if (isave == 0) tempa = sum;
-            if (isave == iu) tempb = denold;
             step = zero;
             if (tempa != tempb) {
                 tempa -= denmax;
@@ -1169,5 +1265,7 @@ struct Newuoa2 {
 #undef BMAT
 #undef ZMAT
 };
+
+typedef Newuoa2T<false> Newuoa2;
 
 }  // namespace gppd

@@ -10,16 +10,17 @@ import numpy as np
 import pytest
 
 
-def _run2(L, ora, fun, x0, rhobeg=1.0, rhoend=1e-3, maxfun=60):
+def _run2(L, ora, fun, x0, rhobeg=1.0, rhoend=1e-3, maxfun=60, entry="newuoa2_host"):
     dp = C.POINTER(C.c_double)
-    L.newuoa2_host.argtypes = [ora.OBJFUN, C.c_void_p, dp, C.c_double, C.c_double, C.c_int, dp,
-                               C.POINTER(C.c_int), ora.OBSERVER, C.c_void_p]
+    solver = getattr(L, entry)
+    solver.argtypes = [ora.OBJFUN, C.c_void_p, dp, C.c_double, C.c_double, C.c_int, dp,
+                       C.POINTER(C.c_int), ora.OBSERVER, C.c_void_p]
     x = np.array(x0, float)
     rec = []
     cf = ora.OBJFUN(lambda n, xp, _: float(fun(np.array([xp[0], xp[1]]))))
     co = ora.OBSERVER(lambda nf, n, xp, f, _: rec.append((xp[0], xp[1], f)))
     fo, nf = C.c_double(), C.c_int()
-    st = L.newuoa2_host(cf, None, x.ctypes.data_as(dp), rhobeg, rhoend, maxfun, C.byref(fo),
+    st = solver(cf, None, x.ctypes.data_as(dp), rhobeg, rhoend, maxfun, C.byref(fo),
                         C.byref(nf), co, None)
     return st, x, fo.value, nf.value, rec
 
@@ -45,7 +46,11 @@ def _objectives(rng):
     ]
 
 
-def test_device_solver_bitwise_equals_oracle(ora, newuoa2_host):
+@pytest.mark.parametrize("entry", ["newuoa2_host", "newuoa2_host_warp"])
+def test_device_solver_bitwise_equals_oracle(ora, newuoa2_host, entry):
+    """entry = newuoa2_host: serial angle searches (thread-per-fit / block-replicated
+    kernels); newuoa2_host_warp: the lane-parallel searches of the warp-per-fit
+    kernel, emulated lane by lane (same selection code path, shuffles -> arrays)."""
     rng = np.random.default_rng(5)
     n_runs = 0
     for trial in range(120):
@@ -55,7 +60,8 @@ def test_device_solver_bitwise_equals_oracle(ora, newuoa2_host):
             rhoend = float(rng.choice([1e-3, 1e-6]))
             rec0 = []
             st0, xa, fa, nfa = ora.newuoa(f, x0, rhoend=rhoend, maxfun=maxfun, record=rec0)
-            st1, xb, fb, nfb, rec1 = _run2(newuoa2_host, ora, f, x0, rhoend=rhoend, maxfun=maxfun)
+            st1, xb, fb, nfb, rec1 = _run2(newuoa2_host, ora, f, x0, rhoend=rhoend, maxfun=maxfun,
+                                           entry=entry)
             assert (st0, nfa) == (st1, nfb)
             assert _same_bits(xa, xb) and _same_bits([fa], [fb])
             assert len(rec0) == len(rec1)
