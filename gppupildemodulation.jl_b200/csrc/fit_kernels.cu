@@ -87,7 +87,7 @@ __device__ __forceinline__ void store_result(FitResult *results, int fit, const 
     PhaseQ pq = make_phaseq(drv.phi, ji.thmin, ji.thmax);
     r.q = pq.q; r.cq = pq.cq; r.sq = pq.sq; r.uniform = pq.uniform;
     r.nfev = drv.nfev; r.status = drv.status; r.method = method; r.second = drv.second;
-    r.fallback = 0; r.pad = 0;
+    r.fallback = 0;
     results[fit] = r;
 }
 
@@ -323,7 +323,7 @@ k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *ht
         r.cre = r.cim = r.are = r.aim = r.b = r.phi = r.alpha = r.chi2 = 0.0;
         r.q = r.cq = r.sq = 0.0;
         r.uniform = 0; r.nfev = 0; r.status = 0; r.method = 0; r.second = 0;
-        r.fallback = 1; r.pad = 0;
+        r.fallback = 1;
         results[fit] = r;
         return;
     }
@@ -388,7 +388,7 @@ k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, i
         r.cre = r.cim = r.are = r.aim = r.b = r.phi = r.alpha = r.chi2 = 0.0;
         r.q = r.cq = r.sq = 0.0;
         r.uniform = 0; r.nfev = 0; r.status = 0; r.method = 0; r.second = 0;
-        r.fallback = 1; r.pad = 0;
+        r.fallback = 1;
         results[fit] = r;
         return;
     }

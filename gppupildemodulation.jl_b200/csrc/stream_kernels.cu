@@ -9,6 +9,7 @@
 #include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace gppd {
 
@@ -446,105 +447,226 @@ __device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned fl
                         __dadd_rn(__dmul_rn(d.y, ca), -__dmul_rn(d.x, sa)));
 }
 
-// One thread per (row, group): 4 diodes + the group's FC channel.
-// Table rows are staged through shared memory so that global loads and stores
-// are full 320-byte rows (coalesced), whatever the per-thread access pattern.
-constexpr int DEMOD_ROWS = 32;   // rows per block; 8 threads (groups) per row
+// sin and cos of a moderate argument (|x| < 1e5; psi = b sin(.) is a few radians):
+// two-constant Cody-Waite reduction by pi/2 done with FMAs (exact first step) and
+// the fdlibm kernel polynomials in Horner/FMA form, < 1 ulp.  About a third of the
+// instructions of the general-purpose sincos(), which carries a Payne-Hanek path.
+__device__ __forceinline__ void sincos_moderate(double x, double *sn, double *cs) {
+    if (!(fabs(x) < 1.0e5)) {
+        sincos(x, sn, cs);
+        return;
+    }
+    const double fn = rint(x * 6.36619772367581382433e-01);
+    const int k = (int)fn;
+    double r = fma(-fn, 1.57079632679489655800e+00, x);
+    r = fma(-fn, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double ks = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    pc = fma(z, pc, -0.5);
+    const double kc = fma(z, pc, 1.0);
+    const double s0 = (k & 1) ? kc : ks, c0 = (k & 1) ? ks : kc;
+    *sn = (k & 2) ? -s0 : s0;
+    *cs = ((k + 1) & 2) ? -c0 : c0;
+}
 
-__global__ void __launch_bounds__(256) k_demod(const TableDesc *tabs, const FitResult *results,
-                                               unsigned flags) {
+// Demodulation constants of one fit held in registers by the streaming kernel.
+struct DemodK {
+    double b, alpha, cq, sq, cre, cim;
+};
+
+// One thread per (row, group): 4 diodes + the group's FC channel, DM_ROWS rows per
+// block.  Dense float32 tables (the METROLOGY layout) are moved as whole row tiles
+// by the TMA (cp.async.bulk global -> shared -> global), so the LSU only sees the
+// 128-bit shared-memory accesses of the arithmetic; other layouts use a
+// cooperative word-by-word staging loop.
+constexpr int DM_ROWS = 64;
+constexpr int DM_THREADS = 256;
+constexpr int DM_SMEM_IN = DM_ROWS * 80 * 4;        // raw input rows
+constexpr int DM_SMEM_BASIS = DM_ROWS * 16;
+constexpr int DM_SMEM_OUT = DM_ROWS * 144 * 4;      // output rows (80 or 144 floats)
+constexpr int DM_SMEM = DM_SMEM_IN + DM_SMEM_BASIS + DM_SMEM_OUT + 16;
+
+__global__ void __launch_bounds__(DM_THREADS) k_demod(const TableDesc *tabs, const FitResult *results,
+                                                      unsigned flags) {
     const TableDesc &tb = tabs[blockIdx.y];
     const TableView &tv = tb.tv;
     const OutView &ov = tb.ov;
-    const long long row_base = (long long)blockIdx.x * DEMOD_ROWS;
+    const long long row_base = (long long)blockIdx.x * DM_ROWS;
     if (row_base >= tv.n) return;
-    const int nrow = (int)((tv.n - row_base) < DEMOD_ROWS ? (tv.n - row_base) : DEMOD_ROWS);
+    const int nrow = (int)((tv.n - row_base) < DM_ROWS ? (tv.n - row_base) : DM_ROWS);
     const int rl = threadIdx.x >> 3, group = threadIdx.x & 7;
-    const long long i = row_base + rl;
-    const bool active = rl < nrow;
 
     if (ov.kind == 1) {  // complex128, channel-major: already unit stride along rows
-        if (!active) return;
-        const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
-        double theta = row_theta(tv, i);
-        double2 sc = tb.basis[i];
-        for (int dio = 0; dio < 4; ++dio) {
-            int ch = group * 4 + dio;
-            ov.out[(long long)ch * tv.n + i] =
-                demod_sample(fr[ch], flags, theta, sc, row_sample(tv, i, ch));
+        for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
+            const long long i = row_base + rr;
+            const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
+            double theta = row_theta(tv, i);
+            double2 sc = tb.basis[i];
+            for (int dio = 0; dio < 4; ++dio) {
+                int ch = group * 4 + dio;
+                ov.out[(long long)ch * tv.n + i] =
+                    demod_sample(fr[ch], flags, theta, sc, row_sample(tv, i, ch));
+            }
+            int fcch = fc_channel(group);
+            ov.out[(long long)fcch * tv.n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
         }
-        int fcch = fc_channel(group);
-        ov.out[(long long)fcch * tv.n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
         return;
     }
 
-    __shared__ __align__(16) uint32_t s_in[DEMOD_ROWS * 80];
-    __shared__ __align__(16) uint32_t s_out[DEMOD_ROWS * 80];
-    // coalesced load of nrow input rows (raw 32-bit words, byte order untouched)
-    const bool dense_in = tv.volt_stride == 320;
-    for (int w = threadIdx.x; w < nrow * 80; w += 256) {
-        int r = w / 80, c = w - r * 80;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(
-            reinterpret_cast<const char *>(tv.volt) + (row_base + r) * tv.volt_stride);
-        s_in[w] = dense_in ? __ldg(reinterpret_cast<const uint32_t *>(tv.volt) + row_base * 80 + w)
-                           : __ldg(src + c);
-    }
-    __syncthreads();
-    if (active) {
-        const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
-        double theta = row_theta(tv, i);
-        double2 sc = tb.basis[i];
-        const uint32_t *irow = s_in + rl * 80;
-        uint32_t *orow = s_out + rl * 80;
-        auto ld = [&](int ch) {
-            uint32_t a = irow[2 * ch], b = irow[2 * ch + 1];
-            if (tv.big_endian) { a = bswap32(a); b = bswap32(b); }
-            double re = (double)__uint_as_float(a), im = (double)__uint_as_float(b);
-            if (tv.offsets) {
-                double2 o = __ldg(tv.offsets + ch);
-                re -= o.x;
-                im -= o.y;
-            }
-            return make_double2(re, im);
-        };
-        auto st = [&](int ch, double2 v) {
-            uint32_t a = __float_as_uint(__double2float_rn(v.x));
-            uint32_t b = __float_as_uint(__double2float_rn(v.y));
-            if (ov.big_endian) { a = bswap32(a); b = bswap32(b); }
-            orow[2 * ch] = a;
-            orow[2 * ch + 1] = b;
-        };
-        for (int dio = 0; dio < 4; ++dio) {
-            int ch = group * 4 + dio;
-            st(ch, demod_sample(fr[ch], flags, theta, sc, ld(ch)));
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    uint32_t *s_in = reinterpret_cast<uint32_t *>(dm_smem);
+    double2 *s_basis = reinterpret_cast<double2 *>(dm_smem + DM_SMEM_IN);
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(dm_smem + DM_SMEM_IN + DM_SMEM_BASIS);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(dm_smem + DM_SMEM_IN + DM_SMEM_BASIS + DM_SMEM_OUT);
+
+    const int ow = ov.keepraw ? 144 : 80;   // output words per row
+    const bool bulk_in = tv.volt_stride == 320 && aligned16(tv.volt);
+    const bool bulk_out = ov.volt_stride == 4 * ow && aligned16(ov.volt);
+    if (bulk_in) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (unsigned)nrow * (320u + 16u));
+            bulk_g2s(s_in, reinterpret_cast<const char *>(tv.volt) + row_base * 320, (unsigned)nrow * 320u, bar);
+            bulk_g2s(s_basis, tb.basis + row_base, (unsigned)nrow * 16u, bar);
         }
-        int fcch = fc_channel(group);
-        st(fcch, ld(fcch));  // centred FC channels, :170-171
-    }
-    __syncthreads();
-    // coalesced store
-    if (!ov.keepraw) {
-        const bool dense_out = ov.volt_stride == 320;
-        for (int w = threadIdx.x; w < nrow * 80; w += 256) {
+    } else {
+        for (int w = threadIdx.x; w < nrow * 80; w += DM_THREADS) {
             int r = w / 80, c = w - r * 80;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(
-                reinterpret_cast<char *>(ov.volt) + (row_base + r) * ov.volt_stride);
-            if (dense_out) reinterpret_cast<uint32_t *>(ov.volt)[row_base * 80 + w] = s_out[w];
-            else dst[c] = s_out[w];
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(
+                reinterpret_cast<const char *>(tv.volt) + (row_base + r) * tv.volt_stride);
+            s_in[w] = __ldg(src + c);
         }
-    } else {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
-        for (int w = threadIdx.x; w < nrow * 144; w += 256) {
-            int r = w / 144, c = w - r * 144;
+        for (int r = threadIdx.x; r < nrow; r += DM_THREADS) s_basis[r] = tb.basis[row_base + r];
+    }
+
+    // fit constants of this thread's 4 diodes (re-read only when a tile straddles two jobs)
+    const long long job_first = row_base / tb.wrows, job_last = (row_base + nrow - 1) / tb.wrows;
+    const bool offs = (flags & 2u) != 0, recenter = !(flags & 4u);
+    DemodK kk[4];
+    int uni = 1;
+    long long job_cur = -1;
+    auto load_consts = [&](long long job) {
+        const FitResult *fr = results + ((long long)tb.job0 + job) * NDIODE + group * 4;
+        uni = 1;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const double2 a = *reinterpret_cast<const double2 *>(&fr[d].b);
+            const double2 q = *reinterpret_cast<const double2 *>(&fr[d].cq);
+            kk[d].b = a.x; kk[d].alpha = a.y; kk[d].cq = q.x; kk[d].sq = q.y;
+            kk[d].cre = kk[d].cim = 0.0;
+            if (offs) {
+                const double2 c = *reinterpret_cast<const double2 *>(&fr[d].cre);
+                kk[d].cre = c.x; kk[d].cim = c.y;
+            }
+            uni &= fr[d].uniform;
+        }
+        job_cur = job;
+    };
+    load_consts(job_first);
+    double2 off[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        const int ch = d < 4 ? group * 4 + d : fc_channel(group);
+        off[d] = tv.offsets ? __ldg(tv.offsets + ch) : make_double2(0.0, 0.0);
+    }
+
+    if (bulk_in) mbar_wait(bar, 0);
+    else __syncthreads();
+
+#pragma unroll 1
+    for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
+        const long long i = row_base + rr;
+        if (job_first != job_last) {
+            const long long job = i / tb.wrows;
+            if (job != job_cur) load_consts(job);
+        }
+        const uint4 w0 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group);
+        const uint4 w1 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group + 4);
+        const uint2 wf = *reinterpret_cast<const uint2 *>(s_in + rr * 80 + 64 + 2 * group);
+        uint32_t raw[10] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wf.x, wf.y};
+        uint32_t res[10];
+        const double2 sc = s_basis[rr];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            uint32_t a = raw[2 * d], b = raw[2 * d + 1];
+            if (tv.big_endian) { a = bswap32(a); b = bswap32(b); }
+            double vr = (double)__uint_as_float(a) - off[d].x;
+            double vi = (double)__uint_as_float(b) - off[d].y;
+            double2 o;
+            if (d == 4) {
+                o = make_double2(vr, vi);                       // centred FC channel, :170-171
+            } else if (recenter && uni) {
+                // psi = fl(fl(b sin(theta + q)) + alpha) - alpha), out = (d - c) exp(-j psi)
+                const double sn = fma(sc.x, kk[d].cq, sc.y * kk[d].sq);
+                const double gp = __dadd_rn(__dmul_rn(kk[d].b, sn), kk[d].alpha);
+                const double psi = __dadd_rn(gp, -kk[d].alpha);
+                double sp, cp;
+                sincos_moderate(psi, &sp, &cp);
+                vr -= kk[d].cre;
+                vi -= kk[d].cim;
+                o = make_double2(fma(vr, cp, vi * sp), fma(vi, cp, -(vr * sp)));
+            } else {
+                const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
+                o = demod_sample(fr[group * 4 + d], flags, row_theta(tv, i), sc, make_double2(vr, vi));
+            }
+            a = __float_as_uint(__double2float_rn(o.x));
+            b = __float_as_uint(__double2float_rn(o.y));
+            if (ov.big_endian) { a = bswap32(a); b = bswap32(b); }
+            res[2 * d] = a;
+            res[2 * d + 1] = b;
+        }
+        uint32_t *orow = s_out + rr * ow;
+        if (!ov.keepraw) {
+            *reinterpret_cast<uint4 *>(orow + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
+            *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
+            *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = make_uint2(res[8], res[9]);
+        } else {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
+            *reinterpret_cast<uint4 *>(orow + 8 * group) = w0;
+            *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = w1;
+            *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = wf;
+            *reinterpret_cast<uint4 *>(orow + 80 + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
+            *reinterpret_cast<uint4 *>(orow + 80 + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
+        }
+    }
+
+    if (bulk_out) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(reinterpret_cast<char *>(ov.volt) + row_base * (4ll * ow), s_out, (unsigned)nrow * 4u * ow);
+            bulk_commit();
+            bulk_wait_read();
+        }
+    } else {
+        __syncthreads();
+        for (int w = threadIdx.x; w < nrow * ow; w += DM_THREADS) {
+            int r = w / ow, c = w - r * ow;
             uint32_t *dst = reinterpret_cast<uint32_t *>(
                 reinterpret_cast<char *>(ov.volt) + (row_base + r) * ov.volt_stride);
-            dst[c] = c < 80 ? s_in[r * 80 + c] : s_out[r * 80 + (c - 80)];
+            dst[c] = s_out[w];
         }
     }
 }
 
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
                   const FitResult *d_results, unsigned flags) {
-    k_demod<<<dim3((unsigned)((max_rows + DEMOD_ROWS - 1) / DEMOD_ROWS), ntables), 256, 0,
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+        attr_set = true;
+    }
+    k_demod<<<dim3((unsigned)((max_rows + DM_ROWS - 1) / DM_ROWS), ntables), DM_THREADS, DM_SMEM,
               L.stream>>>(d_tabs, d_results, flags);
     *L.counter += 1;
 }
