@@ -484,80 +484,99 @@ struct DemodK {
     double b, alpha, cq, sq, cre, cim;
 };
 
-// One thread per (row, group): 4 diodes + the group's FC channel, DM_ROWS rows per
-// block.  Dense float32 tables (the METROLOGY layout) are moved as whole row tiles
-// by the TMA (cp.async.bulk global -> shared -> global), so the LSU only sees the
-// 128-bit shared-memory accesses of the arithmetic; other layouts use a
-// cooperative word-by-word staging loop.
+// One thread per (row, group): 4 diodes + the group's FC channel.  A block walks
+// DM_TPB consecutive tiles of DM_ROWS rows of one table.  Dense float32 tables (the
+// METROLOGY layout) are moved as whole row tiles by the TMA: cp.async.bulk
+// global -> shared into a 3-stage ring (two tiles in flight while one is being
+// worked on), results written IN PLACE over the tile and sent back shared -> global
+// by another bulk copy, so the LSU only sees the 128-bit shared-memory accesses of
+// the arithmetic.  Other layouts (strided / unaligned rows, keepraw's 144-float
+// rows) are staged with cooperative word loops through the same buffers.
 constexpr int DM_ROWS = 64;
 constexpr int DM_THREADS = 256;
-constexpr int DM_SMEM_IN = DM_ROWS * 80 * 4;        // raw input rows
-constexpr int DM_SMEM_BASIS = DM_ROWS * 16;
-constexpr int DM_SMEM_OUT = DM_ROWS * 144 * 4;      // output rows (80 or 144 floats)
-constexpr int DM_SMEM = DM_SMEM_IN + DM_SMEM_BASIS + DM_SMEM_OUT + 16;
+constexpr int DM_TPB = 16;                          // tiles per block
+constexpr int DM_STAGES = 3;
+constexpr int DM_STAGE_BYTES = DM_ROWS * (320 + 16); // raw rows + basis
+constexpr int DM_SMEM_OUT = DM_ROWS * 144 * 4;      // keepraw staging
+constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + DM_SMEM_OUT + 64;
 
-__global__ void __launch_bounds__(DM_THREADS) k_demod(const TableDesc *tabs, const FitResult *results,
-                                                      unsigned flags) {
-    const TableDesc &tb = tabs[blockIdx.y];
-    const TableView &tv = tb.tv;
-    const OutView &ov = tb.ov;
-    const long long row_base = (long long)blockIdx.x * DM_ROWS;
-    if (row_base >= tv.n) return;
-    const int nrow = (int)((tv.n - row_base) < DM_ROWS ? (tv.n - row_base) : DM_ROWS);
+__global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, const FitResult *results,
+                                                         unsigned flags) {
+    const TableDesc &tbg = tabs[blockIdx.y];
+    // table description in registers (the asm memory clobbers below would otherwise
+    // force re-reading it from global memory)
+    const long long n = tbg.tv.n, wrows = tbg.wrows;
+    const long long tile_first = (long long)blockIdx.x * DM_TPB;
+    if (tile_first * DM_ROWS >= n) return;
     const int rl = threadIdx.x >> 3, group = threadIdx.x & 7;
 
-    if (ov.kind == 1) {  // complex128, channel-major: already unit stride along rows
-        for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
-            const long long i = row_base + rr;
-            const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
+    if (tbg.ov.kind == 1) {  // complex128, channel-major: already unit stride along rows
+        const TableView &tv = tbg.tv;
+        const OutView &ov = tbg.ov;
+        const long long row_end = (tile_first + DM_TPB) * DM_ROWS < n ? (tile_first + DM_TPB) * DM_ROWS : n;
+        for (long long i = tile_first * DM_ROWS + rl; i < row_end; i += DM_THREADS / 8) {
+            const FitResult *fr = results + ((long long)tbg.job0 + i / wrows) * NDIODE;
             double theta = row_theta(tv, i);
-            double2 sc = tb.basis[i];
+            double2 sc = tbg.basis[i];
             for (int dio = 0; dio < 4; ++dio) {
                 int ch = group * 4 + dio;
-                ov.out[(long long)ch * tv.n + i] =
-                    demod_sample(fr[ch], flags, theta, sc, row_sample(tv, i, ch));
+                ov.out[(long long)ch * n + i] = demod_sample(fr[ch], flags, theta, sc, row_sample(tv, i, ch));
             }
             int fcch = fc_channel(group);
-            ov.out[(long long)fcch * tv.n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
+            ov.out[(long long)fcch * n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
         }
         return;
     }
 
     extern __shared__ __align__(16) unsigned char dm_smem[];
-    uint32_t *s_in = reinterpret_cast<uint32_t *>(dm_smem);
-    double2 *s_basis = reinterpret_cast<double2 *>(dm_smem + DM_SMEM_IN);
-    uint32_t *s_out = reinterpret_cast<uint32_t *>(dm_smem + DM_SMEM_IN + DM_SMEM_BASIS);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(dm_smem + DM_SMEM_IN + DM_SMEM_BASIS + DM_SMEM_OUT);
+    // [3 stages][mbarriers (64 B)][keepraw staging, only allocated with GPPD_KEEPRAW]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dm_smem + DM_STAGES * DM_STAGE_BYTES);
+    uint32_t *s_outbuf = reinterpret_cast<uint32_t *>(dm_smem + DM_STAGES * DM_STAGE_BYTES + 64);
 
-    const int ow = ov.keepraw ? 144 : 80;   // output words per row
-    const bool bulk_in = tv.volt_stride == 320 && aligned16(tv.volt);
-    const bool bulk_out = ov.volt_stride == 4 * ow && aligned16(ov.volt);
+    const char *volt_in = reinterpret_cast<const char *>(tbg.tv.volt);
+    char *volt_out = reinterpret_cast<char *>(tbg.ov.volt);
+    const long long in_stride = tbg.tv.volt_stride, out_stride = tbg.ov.volt_stride;
+    const double2 *basis = tbg.basis;
+    const double2 *offsets = tbg.tv.offsets;
+    const int be_in = tbg.tv.big_endian, be_out = tbg.ov.big_endian, keepraw = tbg.ov.keepraw;
+    const int job0 = tbg.job0, njobs = tbg.njobs;
+    const int ow = keepraw ? 144 : 80;   // output words per row
+    const bool bulk_in = in_stride == 320 && aligned16(volt_in);
+    const bool bulk_out = out_stride == 4 * ow && aligned16(volt_out);
+    const bool offs = (flags & 2u) != 0, recenter = !(flags & 4u);
+
+    const long long ntiles_tab = (n + DM_ROWS - 1) / DM_ROWS;
+    const int T = (int)((ntiles_tab - tile_first) < DM_TPB ? (ntiles_tab - tile_first) : DM_TPB);
+    auto tile_rows = [&](int k) {
+        const long long rb = (tile_first + k) * DM_ROWS;
+        return (int)((n - rb) < DM_ROWS ? (n - rb) : DM_ROWS);
+    };
+    auto issue_load = [&](int k) {  // one thread
+        const int st = k % DM_STAGES;
+        const long long rb = (tile_first + k) * DM_ROWS;
+        const unsigned nr = (unsigned)tile_rows(k);
+        unsigned char *stage = dm_smem + st * DM_STAGE_BYTES;
+        mbar_expect_tx(&bars[st], nr * (320u + 16u));
+        bulk_g2s(stage, volt_in + rb * 320, nr * 320u, &bars[st]);
+        bulk_g2s(stage + DM_ROWS * 320, basis + rb, nr * 16u, &bars[st]);
+    };
     if (bulk_in) {
-        if (threadIdx.x == 0) mbar_init(bar, 1);
+        if (threadIdx.x == 0) {
+            for (int st = 0; st < DM_STAGES; ++st) mbar_init(&bars[st], 1);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (unsigned)nrow * (320u + 16u));
-            bulk_g2s(s_in, reinterpret_cast<const char *>(tv.volt) + row_base * 320, (unsigned)nrow * 320u, bar);
-            bulk_g2s(s_basis, tb.basis + row_base, (unsigned)nrow * 16u, bar);
+            issue_load(0);
+            if (T > 1) issue_load(1);
         }
-    } else {
-        for (int w = threadIdx.x; w < nrow * 80; w += DM_THREADS) {
-            int r = w / 80, c = w - r * 80;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(
-                reinterpret_cast<const char *>(tv.volt) + (row_base + r) * tv.volt_stride);
-            s_in[w] = __ldg(src + c);
-        }
-        for (int r = threadIdx.x; r < nrow; r += DM_THREADS) s_basis[r] = tb.basis[row_base + r];
     }
 
-    // fit constants of this thread's 4 diodes (re-read only when a tile straddles two jobs)
-    const long long job_first = row_base / tb.wrows, job_last = (row_base + nrow - 1) / tb.wrows;
-    const bool offs = (flags & 2u) != 0, recenter = !(flags & 4u);
+    // fit constants of this thread's 4 diodes (re-read only when the job changes)
     DemodK kk[4];
     int uni = 1;
     long long job_cur = -1;
     auto load_consts = [&](long long job) {
-        const FitResult *fr = results + ((long long)tb.job0 + job) * NDIODE + group * 4;
+        const FitResult *fr = results + ((long long)job0 + job) * NDIODE + group * 4;
         uni = 1;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
@@ -573,101 +592,130 @@ __global__ void __launch_bounds__(DM_THREADS) k_demod(const TableDesc *tabs, con
         }
         job_cur = job;
     };
-    load_consts(job_first);
+    if (njobs == 1) load_consts(0);
     double2 off[5];
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
         const int ch = d < 4 ? group * 4 + d : fc_channel(group);
-        off[d] = tv.offsets ? __ldg(tv.offsets + ch) : make_double2(0.0, 0.0);
+        off[d] = offsets ? __ldg(offsets + ch) : make_double2(0.0, 0.0);
     }
-
-    if (bulk_in) mbar_wait(bar, 0);
-    else __syncthreads();
 
 #pragma unroll 1
-    for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
-        const long long i = row_base + rr;
-        if (job_first != job_last) {
-            const long long job = i / tb.wrows;
-            if (job != job_cur) load_consts(job);
-        }
-        const uint4 w0 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group);
-        const uint4 w1 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group + 4);
-        const uint2 wf = *reinterpret_cast<const uint2 *>(s_in + rr * 80 + 64 + 2 * group);
-        uint32_t raw[10] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wf.x, wf.y};
-        uint32_t res[10];
-        const double2 sc = s_basis[rr];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) {
-            uint32_t a = raw[2 * d], b = raw[2 * d + 1];
-            if (tv.big_endian) { a = bswap32(a); b = bswap32(b); }
-            double vr = (double)__uint_as_float(a) - off[d].x;
-            double vi = (double)__uint_as_float(b) - off[d].y;
-            double2 o;
-            if (d == 4) {
-                o = make_double2(vr, vi);                       // centred FC channel, :170-171
-            } else if (recenter && uni) {
-                // psi = fl(fl(b sin(theta + q)) + alpha) - alpha), out = (d - c) exp(-j psi)
-                const double sn = fma(sc.x, kk[d].cq, sc.y * kk[d].sq);
-                const double gp = __dadd_rn(__dmul_rn(kk[d].b, sn), kk[d].alpha);
-                const double psi = __dadd_rn(gp, -kk[d].alpha);
-                double sp, cp;
-                sincos_moderate(psi, &sp, &cp);
-                vr -= kk[d].cre;
-                vi -= kk[d].cim;
-                o = make_double2(fma(vr, cp, vi * sp), fma(vi, cp, -(vr * sp)));
-            } else {
-                const FitResult *fr = results + ((long long)tb.job0 + i / tb.wrows) * NDIODE;
-                o = demod_sample(fr[group * 4 + d], flags, row_theta(tv, i), sc, make_double2(vr, vi));
+    for (int k = 0; k < T; ++k) {
+        const int st = k % DM_STAGES;
+        const long long row_base = (tile_first + k) * DM_ROWS;
+        const int nrow = tile_rows(k);
+        unsigned char *stage = dm_smem + st * DM_STAGE_BYTES;
+        uint32_t *s_in = reinterpret_cast<uint32_t *>(stage);
+        const double2 *s_basis = reinterpret_cast<const double2 *>(stage + DM_ROWS * 320);
+        uint32_t *s_out = keepraw ? s_outbuf : s_in;
+        if (bulk_in) {
+            if (threadIdx.x == 0 && k + 2 < T) {
+                bulk_wait_read();          // tile k-1's store has released stage (k+2) % 3
+                issue_load(k + 2);
             }
-            a = __float_as_uint(__double2float_rn(o.x));
-            b = __float_as_uint(__double2float_rn(o.y));
-            if (ov.big_endian) { a = bswap32(a); b = bswap32(b); }
-            res[2 * d] = a;
-            res[2 * d + 1] = b;
+            mbar_wait(&bars[st], (unsigned)(k / DM_STAGES) & 1u);
+        } else {
+            if (bulk_out) {   // a bulk store of an earlier tile may still be reading this stage
+                if (threadIdx.x == 0) bulk_wait_read();
+                __syncthreads();
+            }
+            for (int w = threadIdx.x; w < nrow * 80; w += DM_THREADS) {
+                int r = w / 80, c = w - r * 80;
+                s_in[w] = __ldg(reinterpret_cast<const uint32_t *>(volt_in + (row_base + r) * in_stride) + c);
+            }
+            double2 *sb = reinterpret_cast<double2 *>(stage + DM_ROWS * 320);
+            for (int r = threadIdx.x; r < nrow; r += DM_THREADS) sb[r] = basis[row_base + r];
+            __syncthreads();
         }
-        uint32_t *orow = s_out + rr * ow;
-        if (!ov.keepraw) {
-            *reinterpret_cast<uint4 *>(orow + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
-            *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
-            *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = make_uint2(res[8], res[9]);
-        } else {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
-            *reinterpret_cast<uint4 *>(orow + 8 * group) = w0;
-            *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = w1;
-            *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = wf;
-            *reinterpret_cast<uint4 *>(orow + 80 + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
-            *reinterpret_cast<uint4 *>(orow + 80 + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
+        if (keepraw && k > 0) {   // the staging buffer is still being read by tile k-1's store
+            if (threadIdx.x == 0) bulk_wait_read();
+            __syncthreads();
         }
-    }
 
-    if (bulk_out) {
-        fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            bulk_s2g(reinterpret_cast<char *>(ov.volt) + row_base * (4ll * ow), s_out, (unsigned)nrow * 4u * ow);
-            bulk_commit();
-            bulk_wait_read();
+#pragma unroll 1
+        for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
+            const long long i = row_base + rr;
+            if (njobs != 1) {
+                const long long job = i / wrows;
+                if (job != job_cur) load_consts(job);
+            }
+            const uint4 w0 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group);
+            const uint4 w1 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group + 4);
+            const uint2 wf = *reinterpret_cast<const uint2 *>(s_in + rr * 80 + 64 + 2 * group);
+            uint32_t raw[10] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wf.x, wf.y};
+            uint32_t res[10];
+            const double2 sc = s_basis[rr];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                uint32_t a = raw[2 * d], b = raw[2 * d + 1];
+                if (be_in) { a = bswap32(a); b = bswap32(b); }
+                double vr = (double)__uint_as_float(a) - off[d].x;
+                double vi = (double)__uint_as_float(b) - off[d].y;
+                double2 o;
+                if (d == 4) {
+                    o = make_double2(vr, vi);                       // centred FC channel, :170-171
+                } else if (recenter && uni) {
+                    // psi = fl(fl(b sin(theta + q)) + alpha) - alpha), out = (d - c) exp(-j psi)
+                    const double sn = fma(sc.x, kk[d].cq, sc.y * kk[d].sq);
+                    const double gp = __dadd_rn(__dmul_rn(kk[d].b, sn), kk[d].alpha);
+                    const double psi = __dadd_rn(gp, -kk[d].alpha);
+                    double sp, cp;
+                    sincos_moderate(psi, &sp, &cp);
+                    vr -= kk[d].cre;
+                    vi -= kk[d].cim;
+                    o = make_double2(fma(vr, cp, vi * sp), fma(vi, cp, -(vr * sp)));
+                } else {
+                    const FitResult *fr = results + ((long long)job0 + i / wrows) * NDIODE;
+                    o = demod_sample(fr[group * 4 + d], flags, row_theta(tbg.tv, i), sc, make_double2(vr, vi));
+                }
+                a = __float_as_uint(__double2float_rn(o.x));
+                b = __float_as_uint(__double2float_rn(o.y));
+                if (be_out) { a = bswap32(a); b = bswap32(b); }
+                res[2 * d] = a;
+                res[2 * d + 1] = b;
+            }
+            uint32_t *orow = s_out + rr * ow;
+            if (!keepraw) {
+                *reinterpret_cast<uint4 *>(orow + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
+                *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
+                *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = make_uint2(res[8], res[9]);
+            } else {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
+                *reinterpret_cast<uint4 *>(orow + 8 * group) = w0;
+                *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = w1;
+                *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = wf;
+                *reinterpret_cast<uint4 *>(orow + 80 + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
+                *reinterpret_cast<uint4 *>(orow + 80 + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
+            }
         }
-    } else {
-        __syncthreads();
-        for (int w = threadIdx.x; w < nrow * ow; w += DM_THREADS) {
-            int r = w / ow, c = w - r * ow;
-            uint32_t *dst = reinterpret_cast<uint32_t *>(
-                reinterpret_cast<char *>(ov.volt) + (row_base + r) * ov.volt_stride);
-            dst[c] = s_out[w];
+
+        if (bulk_out) {
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(volt_out + row_base * (4ll * ow), s_out, (unsigned)nrow * 4u * ow);
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            for (int w = threadIdx.x; w < nrow * ow; w += DM_THREADS) {
+                int r = w / ow, c = w - r * ow;
+                reinterpret_cast<uint32_t *>(volt_out + (row_base + r) * out_stride)[c] = s_out[w];
+            }
+            __syncthreads();   // the tile / staging buffer is reused by a later iteration
         }
     }
+    if (bulk_out && threadIdx.x == 0) bulk_wait_read();
 }
 
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
                   const FitResult *d_results, unsigned flags) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-        attr_set = true;
-    }
-    k_demod<<<dim3((unsigned)((max_rows + DM_ROWS - 1) / DM_ROWS), ntables), DM_THREADS, DM_SMEM,
-              L.stream>>>(d_tabs, d_results, flags);
+    cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+    const long long rows_per_block = (long long)DM_ROWS * DM_TPB;
+    // the 144-float staging buffer is only needed with keepraw (flag bit 8 = GPPD_KEEPRAW)
+    const int smem = (flags & 8u) ? DM_SMEM : DM_SMEM - DM_SMEM_OUT;
+    k_demod<<<dim3((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), ntables), DM_THREADS,
+              smem, L.stream>>>(d_tabs, d_results, flags);
     *L.counter += 1;
 }
 
