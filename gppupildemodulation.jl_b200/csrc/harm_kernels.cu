@@ -17,41 +17,50 @@
 //     Z_k = (A + B) + j (C - D),   Z_{-k} = (A - B) + j (C + D)
 // i.e. 4 FMAs per (row, diode, |k|) for two harmonics.
 //
-// Kernel structure (k_harm_accumulate): one block per (job, group, segment),
-// persistent over the segment's row tiles of TR rows.
-//   * Two PRODUCER warps stream the raw table bytes of the next-but-one tile into
-//     a 3-stage shared-memory ring with cp.async (16-byte copies: the group's 8
-//     VOLT floats, its FC pair, the row's basis, the state byte) -- no register
-//     dependency, so the global-memory latency is off the critical path -- and
-//     turn the previous stage into a compute tile: e^{j theta}, the four diodes' z
-//     (or y) values, and per consumer warp the start phasor e^{j k0 theta}.
-//   * Six CONSUMER warps own KC = 4 harmonics each for the 4 diodes of the group:
-//     64 FP64 accumulators per thread, advanced by complex rotation (3 per row).
-// Compute tiles are double buffered, one __syncthreads per tile.  A segment is a
-// FIXED run of HARM_SEG_TILES tiles of the job (independent of the batch and of
-// the launch shape) and k_harm_reduce adds the segments in index order, so a
-// fit's sums -- hence its whole NEWUOA trajectory -- do not depend on what else
-// is in the batch.
+// Kernel structure (k_harm_accumulate): one block of 12 warps per (job, group,
+// segment), persistent over the segment's row tiles of TR rows, one block per SM.
+//   * Four PRODUCER warps (one per SM sub-partition) stream the raw table bytes of
+//     the next-but-one tile into a 3-stage shared-memory ring with cp.async
+//     (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's basis, the
+//     state byte) -- no register dependency, so the global-memory latency is off
+//     the critical path -- and turn the previous stage into a compute tile:
+//     e^{j theta}, the four diodes' z (or y) values, and the start phasors
+//     e^{j (6h+1) theta}, h = 0..3 (one complex product, then the three-term
+//     recurrence s_{m+1} = 2 cos(6 theta) s_m - s_{m-1}).
+//   * Eight CONSUMER warps (two per sub-partition) each own KC = 6 harmonics of 2
+//     of the 4 diodes: 48 FP64 accumulators per thread; harmonic k+1 comes from
+//     k by one complex rotation, the following ones by the three-term recurrence
+//     (2 FMAs per harmonic): 61 FP64 instructions per row for 48 useful FMAs, and
+//     64 bytes of shared-memory reads (the FP64 pipe and the shared-memory port are
+//     the two resources this kernel balances).
+// Compute tiles are double buffered and handed over with mbarriers (full / empty
+// per buffer), so consumer warps never wait for each other, only for data.
+// A segment is a FIXED run of HARM_SEG_TILES tiles of the job (independent of
+// the batch and of the launch shape) and k_harm_reduce adds the segments in index
+// order, so a fit's sums -- hence its whole NEWUOA trajectory -- do not depend on
+// what else is in the batch.
 #include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace gppd {
 
-constexpr int TR = 192;                       // rows per tile
-constexpr int HARM_SEG_TILES = 32;            // tiles per segment (6144 rows)
-constexpr int KC = 4;                         // harmonics per consumer warp
-constexpr int NCH = HK / KC;                  // consumer warps
-constexpr int NPROD = 2;                      // producer warps
-constexpr int HARM_THREADS = (NCH + NPROD) * 32;
+constexpr int TR = 256;                       // rows per tile
+constexpr int HARM_SEG_TILES = 24;            // tiles per segment (6144 rows)
+constexpr int KC = 6;                         // harmonics per consumer warp
+constexpr int NHR = HK / KC;                  // harmonic ranges
+constexpr int NCONS = NHR * 2;                // consumer warps: range x diode pair
+constexpr int NPROD = 4;                      // producer warps
+constexpr int HARM_THREADS = (NCONS + NPROD) * 32;
 constexpr int RAW_STAGES = 3;
 constexpr int ROWS_PER_PROD = TR / (NPROD * 32);
-static_assert(NCH * KC == HK, "HK must be a multiple of KC");
+static_assert(NHR * KC == HK, "HK must be a multiple of KC");
 static_assert(ROWS_PER_PROD * NPROD * 32 == TR, "TR must be a multiple of the producer threads");
 
 struct HarmTile {
     double2 e1[TR];            // (cos theta, sin theta)
-    double2 start[NCH][TR];    // (cos, sin)((KC*ch + 1) theta)
+    double2 start[NHR][TR];    // (cos, sin)((KC*h + 1) theta)
     double2 v[4][TR];          // stream values of the group's 4 diodes
 };
 
@@ -62,6 +71,8 @@ struct RawStage {              // raw bytes of one tile, as copied by cp.async
     uint32_t state[TR];        // aligned word holding the row's state byte
 };
 
+constexpr int HARM_SMEM = 2 * (int)sizeof(HarmTile) + RAW_STAGES * (int)sizeof(RawStage) + 64;
+
 __host__ __device__ inline int harm_segments(long long nrows) {
     long long ntiles = (nrows + TR - 1) / TR;
     return (int)((ntiles + HARM_SEG_TILES - 1) / HARM_SEG_TILES);
@@ -69,6 +80,9 @@ __host__ __device__ inline int harm_segments(long long nrows) {
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 csqr(double2 a) {
+    return make_double2(fma(a.x, a.x, -(a.y * a.y)), 2.0 * (a.x * a.y));
 }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -83,6 +97,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // unit phasor of the FC sample: (x, y) / |(x, y)|  (= exp(1im*angle(fc)), :388)
@@ -102,6 +119,9 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarmTile *tiles = reinterpret_cast<HarmTile *>(smem_raw);
     RawStage *raws = reinterpret_cast<RawStage *>(smem_raw + 2 * sizeof(HarmTile));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(HarmTile) +
+                                                  RAW_STAGES * sizeof(RawStage));
+    uint64_t *full = bars, *empty = bars + 2;
     __shared__ double2 s_stats[16];
     __shared__ double2 s_off[5];      // centres of the 4 diodes + FC (kind-0 tables)
     __shared__ double s_red[NPROD][32];
@@ -112,17 +132,13 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     const int job = jg >> 3, group = jg & 7;
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
-    const TableView &tv = tb.tv;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool producer = warp >= NCH;
+    const bool producer = warp >= NCONS;
     // segment p of the job: tiles [p*HARM_SEG_TILES, ...)
     const int ntiles = (ji.nrows + TR - 1) / TR;
     const int tile0 = p * HARM_SEG_TILES;
     if (tile0 >= ntiles) return;
     const int nt = (ntiles - tile0) < HARM_SEG_TILES ? (ntiles - tile0) : HARM_SEG_TILES;
-    // cp.async needs 16-byte aligned sources
-    const bool async_ok = tv.kind == 1 ||
-        ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
 
     if (threadIdx.x < 16) {
         s_stats[threadIdx.x] = tb.state
@@ -132,226 +148,272 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     } else if (threadIdx.x < 21) {
         const int k = threadIdx.x - 16;
         const int ch = k < 4 ? group * 4 + k : fc_channel(group);
-        s_off[k] = (tv.kind == 0 && tv.offsets) ? __ldg(tv.offsets + ch) : make_double2(0.0, 0.0);
+        s_off[k] = (tb.tv.kind == 0 && tb.tv.offsets) ? __ldg(tb.tv.offsets + ch) : make_double2(0.0, 0.0);
+    } else if (threadIdx.x == 32) {
+        mbar_init(&full[0], NPROD);
+        mbar_init(&full[1], NPROD);
+        mbar_init(&empty[0], NCONS);
+        mbar_init(&empty[1], NCONS);
     }
     __syncthreads();
 
-    double acc[KC][4][4];
-    double cst[NCONST * 4];
+    double *out = partial + ((long long)jg * P + p) * 4 * HP;
+
+    if (!producer) {
+        // =================== consumers ===================
+        const int h = warp >> 1, pair = warp & 1;
+        double acc[KC][2][4];
 #pragma unroll
-    for (int a = 0; a < KC; ++a)
+        for (int a = 0; a < KC; ++a)
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][d][c] = 0.0;
+
+        for (int it = 0; it < nt; ++it) {
+            const int b = it & 1;
+            const HarmTile &T = tiles[b];
+            mbar_wait(&full[b], (unsigned)(it >> 1) & 1u);
+#pragma unroll 2
+            for (int i = 0; i < TR / 32; ++i) {
+                const int rr = lane + 32 * i;
+                const double2 e1 = T.e1[rr];
+                double2 cs = T.start[h][rr];
+                const double2 v0 = T.v[2 * pair][rr], v1 = T.v[2 * pair + 1][rr];
+                const double tc = e1.x + e1.x;
+                double2 prev = cs;
+#pragma unroll
+                for (int a = 0; a < KC; ++a) {
+                    acc[a][0][0] = fma(cs.x, v0.x, acc[a][0][0]);
+                    acc[a][0][1] = fma(cs.y, v0.y, acc[a][0][1]);
+                    acc[a][0][2] = fma(cs.x, v0.y, acc[a][0][2]);
+                    acc[a][0][3] = fma(cs.y, v0.x, acc[a][0][3]);
+                    acc[a][1][0] = fma(cs.x, v1.x, acc[a][1][0]);
+                    acc[a][1][1] = fma(cs.y, v1.y, acc[a][1][1]);
+                    acc[a][1][2] = fma(cs.x, v1.y, acc[a][1][2]);
+                    acc[a][1][3] = fma(cs.y, v1.x, acc[a][1][3]);
+                    if (a == 0) {
+                        cs = cmul(cs, e1);
+                    } else if (a + 1 < KC) {   // e^{j(k+1)t} = 2 cos t e^{jkt} - e^{j(k-1)t}
+                        const double2 nx = make_double2(fma(tc, cs.x, -prev.x), fma(tc, cs.y, -prev.y));
+                        prev = cs;
+                        cs = nx;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);
+        }
+#pragma unroll
+        for (int a = 0; a < KC; ++a)
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double s = acc[a][d][c];
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) out[(2 * pair + d) * HP + NCONST + (h * KC + a) * 4 + c] = s;
+                }
+    } else {
+        // =================== producers ===================
+        const TableView &tv = tb.tv;
+        // cp.async needs 16-byte aligned sources
+        const bool async_ok = tv.kind == 1 ||
+            ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
+        const int ptid = threadIdx.x - NCONS * 32;
+        double cst[NCONST * 4];
+#pragma unroll
+        for (int c = 0; c < NCONST * 4; ++c) cst[c] = 0.0;
+        double2 mu[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][d][c] = 0.0;
-#pragma unroll
-    for (int c = 0; c < NCONST * 4; ++c) cst[c] = 0.0;
+            mu[d] = (flags & 2u) ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
 
-    double2 mu[4];
+        // ---- step 1: raw bytes of a tile -> ring stage (asynchronous) ----
+        auto issue = [&](int tile, RawStage &S) {
 #pragma unroll
-    for (int d = 0; d < 4; ++d)
-        mu[d] = (flags & 2u) ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
-
-    const int ptid = threadIdx.x - NCH * 32;
-
-    // ---- producer, step 1: raw bytes of a tile -> ring stage (asynchronous) ----
-    auto issue = [&](int tile, RawStage &S) {
-#pragma unroll
-        for (int j = 0; j < ROWS_PER_PROD; ++j) {
-            const int rr = ptid + j * NPROD * 32;
-            const int i = tile * TR + rr;
-            if (i >= ji.nrows) continue;
-            const long long r = ji.row0 + i;
-            cp_async16(&S.basis[rr], tb.basis + r);
-            if (tv.kind == 0) {
-                const char *row = reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride;
-                cp_async16(&S.dio[0][rr], row + 32 * group);
-                cp_async16(&S.dio[1][rr], row + 32 * group + 16);
-                cp_async16(&S.fc[rr], row + 256 + 16 * (group >> 1));
-            } else {
-#pragma unroll
-                for (int d = 0; d < 4; ++d)
-                    cp_async16(&S.dio[d][rr], tv.data + (long long)(group * 4 + d) * tv.n + r);
-                cp_async16(&S.fc[rr], tv.data + (long long)fc_channel(group) * tv.n + r);
-            }
-            if (tb.state) {
-                const int8_t *sp = tb.state + r;
-                const unsigned long long aw = reinterpret_cast<unsigned long long>(sp) & ~3ull;
-                if (aw >= reinterpret_cast<unsigned long long>(tb.state) &&
-                    aw + 4 <= reinterpret_cast<unsigned long long>(tb.state + tv.n)) {
-                    cp_async4(&S.state[rr], reinterpret_cast<const void *>(aw));
-                } else {  // first / last rows: do not read outside the state array
-                    const unsigned sh = 8u * (unsigned)(reinterpret_cast<unsigned long long>(sp) & 3ull);
-                    S.state[rr] = ((unsigned)(unsigned char)*sp) << sh;
-                }
-            }
-        }
-    };
-
-    // ---- producer, step 2: ring stage (or, unaligned tables, global memory) -> compute tile
-    auto produce = [&](int tile, const RawStage &S, HarmTile &T) {
-#pragma unroll
-        for (int j = 0; j < ROWS_PER_PROD; ++j) {
-            const int rr = ptid + j * NPROD * 32;
-            const int i = tile * TR + rr;
-            double2 e1 = make_double2(1.0, 0.0);
-            double2 vv[4];
-#pragma unroll
-            for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
-            if (i < ji.nrows) {
+            for (int j = 0; j < ROWS_PER_PROD; ++j) {
+                const int rr = ptid + j * NPROD * 32;
+                const int i = tile * TR + rr;
+                if (i >= ji.nrows) continue;
                 const long long r = ji.row0 + i;
-                double2 sc, fcs, dd[4];
-                int st = ST_NORMAL;
-                if (async_ok) {
-                    const uint4 bw = S.basis[rr];
-                    sc = make_double2(__hiloint2double(bw.y, bw.x), __hiloint2double(bw.w, bw.z));
-                    if (tv.kind == 0) {
-                        uint4 a = S.dio[0][rr], b = S.dio[1][rr], f = S.fc[rr];
-                        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                        uint32_t fx = (group & 1) ? f.z : f.x, fy = (group & 1) ? f.w : f.y;
-                        if (tv.big_endian) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
-                            fx = bswap32(fx);
-                            fy = bswap32(fy);
-                        }
-#pragma unroll
-                        for (int d = 0; d < 4; ++d)
-                            dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - s_off[d].x,
-                                                 (double)__uint_as_float(w[2 * d + 1]) - s_off[d].y);
-                        fcs = make_double2((double)__uint_as_float(fx) - s_off[4].x,
-                                           (double)__uint_as_float(fy) - s_off[4].y);
-                    } else {
-#pragma unroll
-                        for (int d = 0; d < 4; ++d) {
-                            const uint4 q = S.dio[d][rr];
-                            dd[d] = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
-                        }
-                        const uint4 q = S.fc[rr];
-                        fcs = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
-                    }
-                    if (tb.state) {
-                        const unsigned sh =
-                            8u * (unsigned)(reinterpret_cast<unsigned long long>(tb.state + r) & 3ull);
-                        st = (int)(signed char)((S.state[rr] >> sh) & 0xffu);
-                    }
+                cp_async16(&S.basis[rr], tb.basis + r);
+                if (tv.kind == 0) {
+                    const char *row = reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride;
+                    cp_async16(&S.dio[0][rr], row + 32 * group);
+                    cp_async16(&S.dio[1][rr], row + 32 * group + 16);
+                    cp_async16(&S.fc[rr], row + 256 + 16 * (group >> 1));
                 } else {
-                    sc = tb.basis[r];
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, r, group * 4 + d);
-                    fcs = row_sample(tv, r, fc_channel(group));
-                    if (tb.state) st = tb.state[r];
+                    for (int d = 0; d < 4; ++d)
+                        cp_async16(&S.dio[d][rr], tv.data + (long long)(group * 4 + d) * tv.n + r);
+                    cp_async16(&S.fc[rr], tv.data + (long long)fc_channel(group) * tv.n + r);
                 }
-                e1 = make_double2(sc.y, sc.x);
-                const bool valid = tb.state ? row_valid(st, flags) : true;
-                if (valid) {
-                    const double2 fc = fc_unit(fcs.x, fcs.y);
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) {
-                        const double2 mw = s_stats[d * 4 + (st & 3)];
-                        const double pr = mw.x * fc.x, pi = mw.x * fc.y;   // p = power .* FCphasor
-                        const double wpr = mw.y * pr, wpi = mw.y * pi;
-                        if (KIND == 0) {
-                            const double dr = dd[d].x - mu[d].x, di = dd[d].y - mu[d].y;
-                            vv[d].x = fma(wpr, dr, wpi * di);
-                            vv[d].y = fma(wpr, di, -(wpi * dr));
-                            cst[d * 7 + 0] += mw.y;
-                            cst[d * 7 + 1] = fma(mw.y, fma(dr, dr, di * di), cst[d * 7 + 1]);
-                            cst[d * 7 + 2] = fma(mw.y, fma(pr, pr, pi * pi), cst[d * 7 + 2]);
-                            cst[d * 7 + 3] = fma(mw.y, dr, cst[d * 7 + 3]);
-                            cst[d * 7 + 4] = fma(mw.y, di, cst[d * 7 + 4]);
-                            cst[d * 7 + 5] += vv[d].x;
-                            cst[d * 7 + 6] += vv[d].y;
-                        } else {
-                            vv[d].x = wpr;
-                            vv[d].y = wpi;
-                            cst[d * 2 + 0] += wpr;
-                            cst[d * 2 + 1] += wpi;
-                        }
+                if (tb.state) {
+                    const int8_t *sp = tb.state + r;
+                    const unsigned long long aw = reinterpret_cast<unsigned long long>(sp) & ~3ull;
+                    if (aw >= reinterpret_cast<unsigned long long>(tb.state) &&
+                        aw + 4 <= reinterpret_cast<unsigned long long>(tb.state + tv.n)) {
+                        cp_async4(&S.state[rr], reinterpret_cast<const void *>(aw));
+                    } else {  // first / last rows: do not read outside the state array
+                        const unsigned sh = 8u * (unsigned)(reinterpret_cast<unsigned long long>(sp) & 3ull);
+                        S.state[rr] = ((unsigned)(unsigned char)*sp) << sh;
                     }
                 }
             }
-            T.e1[rr] = e1;
-            const double2 e2 = cmul(e1, e1);
-            const double2 e4 = cmul(e2, e2);
-            double2 pc = e1;
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                T.start[ch][rr] = pc;
-                pc = cmul(pc, e4);
-            }
-#pragma unroll
-            for (int d = 0; d < 4; ++d) T.v[d][rr] = vv[d];
-        }
-    };
+        };
 
-    auto consume = [&](const HarmTile &T) {
-#pragma unroll 2
-        for (int i = 0; i < TR / 32; ++i) {
-            const int rr = lane + 32 * i;
-            const double2 e1 = T.e1[rr];
-            double2 cs = T.start[warp][rr];
-            double2 v[4];
+        // ---- step 2: ring stage (or, unaligned tables, global memory) -> compute tile
+        auto produce = [&](int tile, const RawStage &S, HarmTile &T) {
 #pragma unroll
-            for (int d = 0; d < 4; ++d) v[d] = T.v[d][rr];
+            for (int j = 0; j < ROWS_PER_PROD; ++j) {
+                const int rr = ptid + j * NPROD * 32;
+                const int i = tile * TR + rr;
+                double2 e1 = make_double2(1.0, 0.0);
+                double2 vv[4];
 #pragma unroll
-            for (int a = 0; a < KC; ++a) {
+                for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
+                if (i < ji.nrows) {
+                    const long long r = ji.row0 + i;
+                    double2 sc, fcs, dd[4];
+                    int st = ST_NORMAL;
+                    if (async_ok) {
+                        const uint4 bw = S.basis[rr];
+                        sc = make_double2(__hiloint2double(bw.y, bw.x), __hiloint2double(bw.w, bw.z));
+                        if (tv.kind == 0) {
+                            uint4 a = S.dio[0][rr], b = S.dio[1][rr], f = S.fc[rr];
+                            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                            uint32_t fx = (group & 1) ? f.z : f.x, fy = (group & 1) ? f.w : f.y;
+                            if (tv.big_endian) {
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    acc[a][d][0] = fma(cs.x, v[d].x, acc[a][d][0]);
-                    acc[a][d][1] = fma(cs.y, v[d].y, acc[a][d][1]);
-                    acc[a][d][2] = fma(cs.x, v[d].y, acc[a][d][2]);
-                    acc[a][d][3] = fma(cs.y, v[d].x, acc[a][d][3]);
+                                for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
+                                fx = bswap32(fx);
+                                fy = bswap32(fy);
+                            }
+#pragma unroll
+                            for (int d = 0; d < 4; ++d)
+                                dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - s_off[d].x,
+                                                     (double)__uint_as_float(w[2 * d + 1]) - s_off[d].y);
+                            fcs = make_double2((double)__uint_as_float(fx) - s_off[4].x,
+                                               (double)__uint_as_float(fy) - s_off[4].y);
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) {
+                                const uint4 q = S.dio[d][rr];
+                                dd[d] = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+                            }
+                            const uint4 q = S.fc[rr];
+                            fcs = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+                        }
+                        if (tb.state) {
+                            const unsigned sh =
+                                8u * (unsigned)(reinterpret_cast<unsigned long long>(tb.state + r) & 3ull);
+                            st = (int)(signed char)((S.state[rr] >> sh) & 0xffu);
+                        }
+                    } else {
+                        sc = tb.basis[r];
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, r, group * 4 + d);
+                        fcs = row_sample(tv, r, fc_channel(group));
+                        if (tb.state) st = tb.state[r];
+                    }
+                    e1 = make_double2(sc.y, sc.x);
+                    const bool valid = tb.state ? row_valid(st, flags) : true;
+                    if (valid) {
+                        const double2 fc = fc_unit(fcs.x, fcs.y);
+                        if (tb.state) {
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) {
+                                const double2 mw = s_stats[d * 4 + (st & 3)];
+                                const double pr = mw.x * fc.x, pi = mw.x * fc.y;   // p = power .* FCphasor
+                                const double wpr = mw.y * pr, wpi = mw.y * pi;
+                                if (KIND == 0) {
+                                    const double dr = dd[d].x - mu[d].x, di = dd[d].y - mu[d].y;
+                                    vv[d].x = fma(wpr, dr, wpi * di);
+                                    vv[d].y = fma(wpr, di, -(wpi * dr));
+                                    cst[d * 7 + 0] += mw.y;
+                                    cst[d * 7 + 1] = fma(mw.y, fma(dr, dr, di * di), cst[d * 7 + 1]);
+                                    cst[d * 7 + 2] = fma(mw.y, fma(pr, pr, pi * pi), cst[d * 7 + 2]);
+                                    cst[d * 7 + 3] = fma(mw.y, dr, cst[d * 7 + 3]);
+                                    cst[d * 7 + 4] = fma(mw.y, di, cst[d * 7 + 4]);
+                                    cst[d * 7 + 5] += vv[d].x;
+                                    cst[d * 7 + 6] += vv[d].y;
+                                } else {
+                                    vv[d].x = wpr;
+                                    vv[d].y = wpi;
+                                    cst[d * 2 + 0] += wpr;
+                                    cst[d * 2 + 1] += wpi;
+                                }
+                            }
+                        } else {   // bright: w = 1, p = FCphasor (|p| = 1)
+                            const double pp = fma(fc.x, fc.x, fc.y * fc.y);
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) {
+                                if (KIND == 0) {
+                                    const double dr = dd[d].x - mu[d].x, di = dd[d].y - mu[d].y;
+                                    vv[d].x = fma(fc.x, dr, fc.y * di);
+                                    vv[d].y = fma(fc.x, di, -(fc.y * dr));
+                                    cst[d * 7 + 0] += 1.0;
+                                    cst[d * 7 + 1] += fma(dr, dr, di * di);
+                                    cst[d * 7 + 2] += pp;
+                                    cst[d * 7 + 3] += dr;
+                                    cst[d * 7 + 4] += di;
+                                    cst[d * 7 + 5] += vv[d].x;
+                                    cst[d * 7 + 6] += vv[d].y;
+                                } else {
+                                    vv[d] = fc;
+                                    cst[d * 2 + 0] += fc.x;
+                                    cst[d * 2 + 1] += fc.y;
+                                }
+                            }
+                        }
+                    }
                 }
-                if (a + 1 < KC) cs = cmul(cs, e1);
+                T.e1[rr] = e1;
+                // start phasors e^{j (6h+1) theta}: e6 = ((e1^2) e1)^2, then the
+                // three-term recurrence with 2 cos(6 theta)
+                const double2 e6 = csqr(cmul(csqr(e1), e1));
+                const double tc6 = e6.x + e6.x;
+                double2 s0 = e1, s1 = cmul(e1, e6);
+                T.start[0][rr] = s0;
+                T.start[1][rr] = s1;
+#pragma unroll
+                for (int hh = 2; hh < NHR; ++hh) {
+                    const double2 s2 = make_double2(fma(tc6, s1.x, -s0.x), fma(tc6, s1.y, -s0.y));
+                    T.start[hh][rr] = s2;
+                    s0 = s1;
+                    s1 = s2;
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) T.v[d][rr] = vv[d];
             }
-        }
-    };
+        };
 
-    // Pipeline.  Producers: stage (it+2) is being copied while stage (it+1) is turned
-    // into compute tile (it+1) while the consumers work on compute tile it.  Every
-    // producer thread reads back only the ring bytes it copied itself, so its own
-    // cp.async.wait_group is the only synchronisation the ring needs.
-    if (producer) {
+        // Pipeline: stage (it+2) is being copied while stage (it+1) is turned into
+        // compute tile (it+1) while the consumers work on compute tile it.  Every
+        // producer thread reads back only the ring bytes it copied itself, so its own
+        // cp.async.wait_group is the only synchronisation the ring needs.
         if (async_ok) {
             issue(tile0, raws[0]);
             cp_async_commit();
             if (nt > 1) issue(tile0 + 1, raws[1]);
             cp_async_commit();
-            cp_async_wait<1>();
         }
-        produce(tile0, raws[0], tiles[0]);
-    }
-    __syncthreads();
-    for (int it = 0; it < nt; ++it) {
-        if (producer) {
+        for (int it = 0; it < nt; ++it) {
+            const int b = it & 1;
             if (async_ok) {
                 if (it + 2 < nt) issue(tile0 + it + 2, raws[(it + 2) % RAW_STAGES]);
                 cp_async_commit();
-                cp_async_wait<1>();
+                cp_async_wait<2>();      // tile it's bytes have landed
             }
-            if (it + 1 < nt) produce(tile0 + it + 1, raws[(it + 1) % RAW_STAGES], tiles[(it + 1) & 1]);
-        } else {
-            consume(tiles[it & 1]);
+            if (it >= 2) mbar_wait(&empty[b], (unsigned)((it >> 1) - 1) & 1u);
+            produce(tile0 + it, raws[it % RAW_STAGES], tiles[b]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[b]);
         }
-        __syncthreads();
-    }
-    if (producer && async_ok) cp_async_wait<0>();
+        if (async_ok) cp_async_wait<0>();
 
-    double *out = partial + ((long long)jg * P + p) * 4 * HP;
-    if (!producer) {
-#pragma unroll
-        for (int a = 0; a < KC; ++a)
-#pragma unroll
-            for (int d = 0; d < 4; ++d)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    double s = acc[a][d][c];
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) out[d * HP + NCONST + (warp * KC + a) * 4 + c] = s;
-                }
-    } else {
-        const int pw = warp - NCH;
+        const int pw = warp - NCONS;
 #pragma unroll
         for (int c = 0; c < NCONST * 4; ++c) {
             double s = cst[c];
@@ -394,13 +456,9 @@ int harm_max_segments(long long max_rows_per_job) { return harm_segments(max_row
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab) {
-    static bool attr_set = false;
-    const int smem = 2 * (int)sizeof(HarmTile) + RAW_STAGES * (int)sizeof(RawStage);
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_harm_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(k_harm_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    const int smem = HARM_SMEM;
+    cudaFuncSetAttribute(k_harm_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_harm_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dim3 grid(P, njobs * NGROUP);
     k_harm_accumulate<0><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
                                                                  d_spart1, d_spart2, d_partZ);
