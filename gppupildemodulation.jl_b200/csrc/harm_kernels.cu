@@ -17,9 +17,12 @@
 //     Z_k = (A + B) + j (C - D),   Z_{-k} = (A - B) + j (C + D)
 // i.e. 4 FMAs per (row, diode, |k|) for two harmonics.
 //
-// Kernel structure (k_harm_accumulate): one block of 12 warps per (job, group,
+// Kernel structure (k_harm_accumulate): one block of 16 warps per (job, group,
 // segment), persistent over the segment's row tiles of TR rows, one block per SM.
-//   * Four PRODUCER warps (one per SM sub-partition) stream the raw table bytes of
+// The register file is re-split between the roles with setmaxnreg (consumers 168,
+// producers 88 registers per thread).
+//   * Eight PRODUCER warps (two per SM sub-partition, one row per thread and tile:
+//     their long dependent chains need the extra warps to hide latency) stream the raw table bytes of
 //     the next-but-one tile into a 3-stage shared-memory ring with cp.async
 //     (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's basis, the
 //     state byte) -- no register dependency, so the global-memory latency is off
@@ -33,7 +36,7 @@
 //     (2 FMAs per harmonic): 61 FP64 instructions per row for 48 useful FMAs, and
 //     64 bytes of shared-memory reads (the FP64 pipe and the shared-memory port are
 //     the two resources this kernel balances).
-// Compute tiles are double buffered and handed over with mbarriers (full / empty
+// Compute tiles are triple buffered and handed over with mbarriers (full / empty
 // per buffer), so consumer warps never wait for each other, only for data.
 // A segment is a FIXED run of HARM_SEG_TILES tiles of the job (independent of
 // the batch and of the launch shape) and k_harm_reduce adds the segments in index
@@ -47,13 +50,14 @@
 namespace gppd {
 
 constexpr int TR = 256;                       // rows per tile
-constexpr int HARM_SEG_TILES = 24;            // tiles per segment (6144 rows)
+constexpr int HARM_SEG_TILES = 48;            // tiles per segment (12288 rows)
 constexpr int KC = 6;                         // harmonics per consumer warp
 constexpr int NHR = HK / KC;                  // harmonic ranges
 constexpr int NCONS = NHR * 2;                // consumer warps: range x diode pair
-constexpr int NPROD = 4;                      // producer warps
+constexpr int NPROD = 8;                      // producer warps
 constexpr int HARM_THREADS = (NCONS + NPROD) * 32;
 constexpr int RAW_STAGES = 3;
+constexpr int TILE_BUFS = 3;                   // compute tiles in flight
 constexpr int ROWS_PER_PROD = TR / (NPROD * 32);
 static_assert(NHR * KC == HK, "HK must be a multiple of KC");
 static_assert(ROWS_PER_PROD * NPROD * 32 == TR, "TR must be a multiple of the producer threads");
@@ -71,7 +75,7 @@ struct RawStage {              // raw bytes of one tile, as copied by cp.async
     uint32_t state[TR];        // aligned word holding the row's state byte
 };
 
-constexpr int HARM_SMEM = 2 * (int)sizeof(HarmTile) + RAW_STAGES * (int)sizeof(RawStage) + 64;
+constexpr int HARM_SMEM = TILE_BUFS * (int)sizeof(HarmTile) + RAW_STAGES * (int)sizeof(RawStage) + 64;
 
 __host__ __device__ inline int harm_segments(long long nrows) {
     long long ntiles = (nrows + TR - 1) / TR;
@@ -112,26 +116,41 @@ __device__ __forceinline__ double2 fc_unit(double x, double y) {
     return fc_phasor(make_double2(x, y));
 }
 
-template <int KIND>  // 0: z = w conj(p) (d - mu);  1: y = w p
+__device__ __forceinline__ void reg_alloc_consumer() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
+}
+__device__ __forceinline__ void reg_dealloc_producer() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n");
+}
+
+// The constant (b, phi independent) sums of a fit, per diode:
+//   [0] sum w, [1] sum w |d - mu|^2, [2] sum w |p|^2, [3..4] sum w (d - mu), [5..6] Z_0
+// sum w and sum w |p|^2 (|FCphasor| = 1) follow from the per-state row counts of the
+// segment: sum_s n_s w_s and sum_s n_s w_s m_s^2.
+template <int KIND, bool OFFS>  // KIND 0: z = w conj(p) (d - mu);  1: y = w p
 __global__ void __launch_bounds__(HARM_THREADS, 1)
 k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, int SP,
                   const double *spart1, const double *spart2, double *partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HarmTile *tiles = reinterpret_cast<HarmTile *>(smem_raw);
-    RawStage *raws = reinterpret_cast<RawStage *>(smem_raw + 2 * sizeof(HarmTile));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * sizeof(HarmTile) +
+    RawStage *raws = reinterpret_cast<RawStage *>(smem_raw + TILE_BUFS * sizeof(HarmTile));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + TILE_BUFS * sizeof(HarmTile) +
                                                   RAW_STAGES * sizeof(RawStage));
-    uint64_t *full = bars, *empty = bars + 2;
+    uint64_t *full = bars, *empty = bars + TILE_BUFS;
     __shared__ double2 s_stats[16];
     __shared__ double2 s_off[5];      // centres of the 4 diodes + FC (kind-0 tables)
-    __shared__ double s_red[NPROD][32];
+    __shared__ double s_red[NPROD][24];
+    __shared__ unsigned long long s_cnt[NPROD];
 
     constexpr int NCONST = KIND == 0 ? 7 : 2;
+    constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;   // sums a producer thread carries per diode
     constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
     const int jg = blockIdx.y, p = blockIdx.x;
     const int job = jg >> 3, group = jg & 7;
     const JobInfo ji = jobs[job];
-    const TableDesc &tb = tabs[ji.table];
+    // by value: the table description must sit in registers, not be re-read from
+    // global memory after every asm memory clobber of the pipeline below
+    const TableDesc tb = tabs[ji.table];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp >= NCONS;
     // segment p of the job: tiles [p*HARM_SEG_TILES, ...)
@@ -150,10 +169,10 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
         const int ch = k < 4 ? group * 4 + k : fc_channel(group);
         s_off[k] = (tb.tv.kind == 0 && tb.tv.offsets) ? __ldg(tb.tv.offsets + ch) : make_double2(0.0, 0.0);
     } else if (threadIdx.x == 32) {
-        mbar_init(&full[0], NPROD);
-        mbar_init(&full[1], NPROD);
-        mbar_init(&empty[0], NCONS);
-        mbar_init(&empty[1], NCONS);
+        for (int b = 0; b < TILE_BUFS; ++b) {
+            mbar_init(&full[b], NPROD);
+            mbar_init(&empty[b], NCONS);
+        }
     }
     __syncthreads();
 
@@ -161,6 +180,7 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
 
     if (!producer) {
         // =================== consumers ===================
+        reg_alloc_consumer();
         const int h = warp >> 1, pair = warp & 1;
         double acc[KC][2][4];
 #pragma unroll
@@ -171,9 +191,9 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                 for (int c = 0; c < 4; ++c) acc[a][d][c] = 0.0;
 
         for (int it = 0; it < nt; ++it) {
-            const int b = it & 1;
+            const int b = it % TILE_BUFS;
             const HarmTile &T = tiles[b];
-            mbar_wait(&full[b], (unsigned)(it >> 1) & 1u);
+            mbar_wait(&full[b], (unsigned)(it / TILE_BUFS) & 1u);
 #pragma unroll 2
             for (int i = 0; i < TR / 32; ++i) {
                 const int rr = lane + 32 * i;
@@ -216,18 +236,20 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                 }
     } else {
         // =================== producers ===================
+        reg_dealloc_producer();
         const TableView &tv = tb.tv;
         // cp.async needs 16-byte aligned sources
         const bool async_ok = tv.kind == 1 ||
             ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
         const int ptid = threadIdx.x - NCONS * 32;
-        double cst[NCONST * 4];
+        double cst[NACC * 4];
 #pragma unroll
-        for (int c = 0; c < NCONST * 4; ++c) cst[c] = 0.0;
+        for (int c = 0; c < NACC * 4; ++c) cst[c] = 0.0;
+        unsigned long long cnt = 0;   // valid rows per state, four 16-bit fields
         double2 mu[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-            mu[d] = (flags & 2u) ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
+            mu[d] = OFFS ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
 
         // ---- step 1: raw bytes of a tile -> ring stage (asynchronous) ----
         auto issue = [&](int tile, RawStage &S) {
@@ -321,50 +343,34 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                     const bool valid = tb.state ? row_valid(st, flags) : true;
                     if (valid) {
                         const double2 fc = fc_unit(fcs.x, fcs.y);
-                        if (tb.state) {
+                        cnt += 1ull << (16 * (st & 3));
 #pragma unroll
-                            for (int d = 0; d < 4; ++d) {
+                        for (int d = 0; d < 4; ++d) {
+                            double wpr = fc.x, wpi = fc.y, w = 1.0;   // bright: w = 1, p = FCphasor
+                            if (tb.state) {
                                 const double2 mw = s_stats[d * 4 + (st & 3)];
-                                const double pr = mw.x * fc.x, pi = mw.x * fc.y;   // p = power .* FCphasor
-                                const double wpr = mw.y * pr, wpi = mw.y * pi;
-                                if (KIND == 0) {
-                                    const double dr = dd[d].x - mu[d].x, di = dd[d].y - mu[d].y;
-                                    vv[d].x = fma(wpr, dr, wpi * di);
-                                    vv[d].y = fma(wpr, di, -(wpi * dr));
-                                    cst[d * 7 + 0] += mw.y;
-                                    cst[d * 7 + 1] = fma(mw.y, fma(dr, dr, di * di), cst[d * 7 + 1]);
-                                    cst[d * 7 + 2] = fma(mw.y, fma(pr, pr, pi * pi), cst[d * 7 + 2]);
-                                    cst[d * 7 + 3] = fma(mw.y, dr, cst[d * 7 + 3]);
-                                    cst[d * 7 + 4] = fma(mw.y, di, cst[d * 7 + 4]);
-                                    cst[d * 7 + 5] += vv[d].x;
-                                    cst[d * 7 + 6] += vv[d].y;
-                                } else {
-                                    vv[d].x = wpr;
-                                    vv[d].y = wpi;
-                                    cst[d * 2 + 0] += wpr;
-                                    cst[d * 2 + 1] += wpi;
-                                }
+                                w = mw.y;
+                                const double wm = mw.y * mw.x;        // p = power .* FCphasor
+                                wpr = wm * fc.x;
+                                wpi = wm * fc.y;
                             }
-                        } else {   // bright: w = 1, p = FCphasor (|p| = 1)
-                            const double pp = fma(fc.x, fc.x, fc.y * fc.y);
-#pragma unroll
-                            for (int d = 0; d < 4; ++d) {
-                                if (KIND == 0) {
-                                    const double dr = dd[d].x - mu[d].x, di = dd[d].y - mu[d].y;
-                                    vv[d].x = fma(fc.x, dr, fc.y * di);
-                                    vv[d].y = fma(fc.x, di, -(fc.y * dr));
-                                    cst[d * 7 + 0] += 1.0;
-                                    cst[d * 7 + 1] += fma(dr, dr, di * di);
-                                    cst[d * 7 + 2] += pp;
-                                    cst[d * 7 + 3] += dr;
-                                    cst[d * 7 + 4] += di;
-                                    cst[d * 7 + 5] += vv[d].x;
-                                    cst[d * 7 + 6] += vv[d].y;
-                                } else {
-                                    vv[d] = fc;
-                                    cst[d * 2 + 0] += fc.x;
-                                    cst[d * 2 + 1] += fc.y;
+                            if (KIND == 0) {
+                                double dr = dd[d].x, di = dd[d].y;
+                                if (OFFS) { dr -= mu[d].x; di -= mu[d].y; }
+                                vv[d].x = fma(wpr, dr, wpi * di);
+                                vv[d].y = fma(wpr, di, -(wpi * dr));
+                                cst[d * NACC + 0] = fma(w, fma(dr, dr, di * di), cst[d * NACC + 0]);
+                                cst[d * NACC + 1] += vv[d].x;
+                                cst[d * NACC + 2] += vv[d].y;
+                                if (OFFS) {
+                                    cst[d * NACC + 3] = fma(w, dr, cst[d * NACC + 3]);
+                                    cst[d * NACC + 4] = fma(w, di, cst[d * NACC + 4]);
                                 }
+                            } else {
+                                vv[d].x = wpr;
+                                vv[d].y = wpi;
+                                cst[d * NACC + 0] += wpr;
+                                cst[d * NACC + 1] += wpi;
                             }
                         }
                     }
@@ -400,13 +406,13 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
             cp_async_commit();
         }
         for (int it = 0; it < nt; ++it) {
-            const int b = it & 1;
+            const int b = it % TILE_BUFS;
             if (async_ok) {
                 if (it + 2 < nt) issue(tile0 + it + 2, raws[(it + 2) % RAW_STAGES]);
                 cp_async_commit();
                 cp_async_wait<2>();      // tile it's bytes have landed
             }
-            if (it >= 2) mbar_wait(&empty[b], (unsigned)((it >> 1) - 1) & 1u);
+            if (it >= TILE_BUFS) mbar_wait(&empty[b], (unsigned)(it / TILE_BUFS - 1) & 1u);
             produce(tile0 + it, raws[it % RAW_STAGES], tiles[b]);
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[b]);
@@ -415,18 +421,39 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
 
         const int pw = warp - NCONS;
 #pragma unroll
-        for (int c = 0; c < NCONST * 4; ++c) {
+        for (int c = 0; c < NACC * 4; ++c) {
             double s = cst[c];
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) s_red[pw][c] = s;
         }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) s_cnt[pw] = cnt;
     }
     __syncthreads();
     if (threadIdx.x < NCONST * 4) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NPROD; ++w) s += s_red[w][threadIdx.x];
         const int d = threadIdx.x / NCONST, c = threadIdx.x % NCONST;
+        unsigned long long cn = 0;
+        for (int w = 0; w < NPROD; ++w) cn += s_cnt[w];
+        double s = 0.0;
+        int src = -1;   // index into the carried sums, or -1: from the state counts
+        if (KIND == 0) {
+            if (c == 1) src = 0;
+            else if (c == 5) src = 1;
+            else if (c == 6) src = 2;
+            else if (OFFS && c == 3) src = 3;
+            else if (OFFS && c == 4) src = 4;
+        } else {
+            src = c;
+        }
+        if (src >= 0) {
+            for (int w = 0; w < NPROD; ++w) s += s_red[w][d * NACC + src];
+        } else if (c == 0 || c == 2) {
+            for (int st = 0; st < 4; ++st) {
+                const double n_s = (double)((cn >> (16 * st)) & 0xffffull);
+                const double2 mw = s_stats[d * 4 + st];
+                if (n_s > 0.0) s += c == 0 ? n_s * mw.y : n_s * (mw.y * (mw.x * mw.x));
+            }
+        }
         out[d * HP + c] = s;
     }
 }
@@ -457,16 +484,20 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab) {
     const int smem = HARM_SMEM;
-    cudaFuncSetAttribute(k_harm_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_harm_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_harm_accumulate<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_harm_accumulate<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_harm_accumulate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dim3 grid(P, njobs * NGROUP);
-    k_harm_accumulate<0><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
-                                                                 d_spart1, d_spart2, d_partZ);
-    *L.counter += 1;
     const bool offs = (flags & 2u) != 0;
     if (offs) {
-        k_harm_accumulate<1><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
-                                                                     d_spart1, d_spart2, d_partY);
+        k_harm_accumulate<0, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
+                                                                          d_spart1, d_spart2, d_partZ);
+        k_harm_accumulate<1, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
+                                                                          d_spart1, d_spart2, d_partY);
+        *L.counter += 2;
+    } else {
+        k_harm_accumulate<0, false><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
+                                                                           d_spart1, d_spart2, d_partZ);
         *L.counter += 1;
     }
     const int nfits = njobs * NDIODE;
