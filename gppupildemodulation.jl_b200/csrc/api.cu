@@ -96,7 +96,7 @@ struct Slot {
     // batch scratch
     DevBuf state, basis, z, y, thkeys, nvalid, jobs, results;
     DevBuf spart1, spart2, partZ, partY, htab;
-    DevBuf timers, lb, events, flags, tabs, exps;
+    DevBuf timers, lb, events, flags, tabs, exps, faintjobs;
     PassTimer timer;
 };
 
@@ -180,6 +180,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     bool any_seg = false, any_state = false;
     std::vector<TableDesc> td(T);
     std::vector<ExportDesc> ex(T);
+    std::vector<int> faint_jobs;   // jobs of the tables that have states
     for (int t = 0; t < T; ++t) {
         TableArgs &a = tabs[t];
         const long long n = a.tv.n;
@@ -216,7 +217,10 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
             nevents += (size_t)(a.n1 + a.n2 + 1024);
             if (a.n1 + a.n2 > max_timers) max_timers = (int)(a.n1 + a.n2);
         }
-        if (seg || a.d_state_in) any_state = true;
+        if (seg || a.d_state_in) {
+            any_state = true;
+            for (long long j = 0; j < nj; ++j) faint_jobs.push_back((int)(njobs_ll + j));
+        }
         R += n;
         njobs_ll += nj;
         if (n > max_rows) max_rows = n;
@@ -246,12 +250,13 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     }
     if (!segment_only) {
         if ((rc = s.thkeys.ensure(sizeof(unsigned long long) * 2 * (size_t)njobs))) return rc;
-        if ((rc = s.nvalid.ensure(sizeof(int) * (size_t)njobs))) return rc;
+        if ((rc = s.nvalid.ensure(sizeof(int) * 5 * (size_t)njobs))) return rc;
         if ((rc = s.jobs.ensure(sizeof(JobInfo) * (size_t)njobs))) return rc;
         if ((rc = s.results.ensure(sizeof(FitResult) * (size_t)nfits))) return rc;
         if (any_state) {
             if ((rc = s.spart1.ensure(sizeof(double) * STATS_VALS * (size_t)njg * SP))) return rc;
-            if ((rc = s.spart2.ensure(sizeof(double) * 16 * (size_t)njg * SP))) return rc;
+            if ((rc = s.spart2.ensure(sizeof(double) * 32 * (size_t)njg))) return rc;
+            if ((rc = s.faintjobs.ensure(sizeof(int) * faint_jobs.size()))) return rc;
         }
         if (direct) {
             if ((rc = s.z.ensure(sizeof(double2) * (size_t)R * NDIODE))) return rc;
@@ -311,6 +316,9 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
                            cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(s.exps.p, ex.data(), sizeof(ExportDesc) * (size_t)T,
                            cudaMemcpyHostToDevice, stream));
+        if (any_state && !segment_only)
+            CK(cudaMemcpyAsync(s.faintjobs.p, faint_jobs.data(), sizeof(int) * faint_jobs.size(),
+                               cudaMemcpyHostToDevice, stream));
     }
     const TableDesc *d_tabs = s.tabs.as<TableDesc>();
 
@@ -332,7 +340,8 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     DBG(stream, "basis");
     if (any_state) {
         PassScope ps(h, s, stream, GPPD_PASS_STATS);
-        launch_stats(L, d_tabs, s.jobs.as<JobInfo>(), njobs, fo.flags, SP, s.spart1.as<double>(),
+        launch_stats(L, d_tabs, s.jobs.as<JobInfo>(), njobs, s.faintjobs.as<int>(),
+                     (int)faint_jobs.size(), s.nvalid.as<int>(), fo.flags, SP, s.spart1.as<double>(),
                      s.spart2.as<double>());
     }
     DBG(stream, "stats");
@@ -488,7 +497,7 @@ int gppd_destroy(gppd_handle h) {
                           &s.offsets, &s.params, &s.chi2, &s.info, &s.trace, &s.state_out,
                           &s.state, &s.basis, &s.z, &s.y, &s.thkeys, &s.nvalid, &s.jobs,
                           &s.results, &s.spart1, &s.spart2, &s.partZ, &s.partY, &s.htab,
-                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps};
+                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps, &s.faintjobs};
         for (DevBuf *b : bufs) b->release();
         for (cudaEvent_t e : s.timer.ev) cudaEventDestroy(e);
     }

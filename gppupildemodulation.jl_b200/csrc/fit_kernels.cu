@@ -98,11 +98,7 @@ __device__ __forceinline__ void store_result(FitResult *results, int fit, const 
 // when every |theta| < 4096 (ulp <= 2^-41: the per-row rounding of theta + phi
 // is below 2.3e-13 rad and is neglected).
 __device__ __forceinline__ bool harm_quantum(double phi, const JobInfo &ji, double &q) {
-    PhaseQ pq = make_phaseq(phi, ji.thmin, ji.thmax);
-    if (pq.uniform) {
-        q = pq.q;
-        return true;
-    }
+    if (phase_quantum(phi, ji.thmin, ji.thmax, q)) return true;
     if (fabs(ji.thmin) < 4096.0 && fabs(ji.thmax) < 4096.0 && fabs(phi) < 4096.0) {
         q = phi;
         return true;
@@ -119,7 +115,7 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
     double J[HK + 1];
     bessel_j(b, J);
     double sq, cq;
-    sincos(q, &sq, &cq);
+    sincos_moderate(q, &sq, &cq);
     double sgdr = J[0] * H[(long long)HV_Z0R * nfits], sgdi = J[0] * H[(long long)HV_Z0I * nfits];
     double sgr = 0.0, sgi = 0.0;
     if (OFFS) {
@@ -166,30 +162,6 @@ __device__ __forceinline__ void fill_angle_table(NuSinCos *tab) {
 }
 
 // ---- one warp per fit ---------------------------------------------------------
-// J_lane(b) for lane <= HK: every lane runs bessel_j's recurrence (uniform control
-// flow, no array) and keeps the term of its own order.
-__device__ __forceinline__ double bessel_j_lane(double b, int lane) {
-    if (b == 0.0) return lane == 0 ? 1.0 : 0.0;
-    const int M = 56;
-    const double tb = 2.0 / b;
-    double jp = 0.0, jc = 1.0e-250, sum = 0.0, mine = 0.0;
-#pragma unroll 1
-    for (int k = M; k >= 1; --k) {
-        const double jm = fma((double)k * tb, jc, -jp);  // J_{k-1}
-        jp = jc;
-        jc = jm;
-        if (k - 1 == lane) mine = jc;
-        if (((k - 1) & 1) == 0) sum += (k - 1 == 0) ? jc : 2.0 * jc;
-        if (fabs(jc) > 1.0e200) {
-            jc *= 1.0e-200;
-            jp *= 1.0e-200;
-            sum *= 1.0e-200;
-            if (lane >= k - 1) mine *= 1.0e-200;
-        }
-    }
-    return mine * (1.0 / sum);
-}
-
 struct HarmLane {       // lane k = 1..HK: (A, B, C, D) of harmonic k; lane 0: (Z_0.re, Z_0.im)
     double zA, zB, zC, zD;
     double yA, yB, yC, yD;
@@ -204,15 +176,22 @@ __device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitC
     if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;   // warp-uniform
     const double J = bessel_j_lane(b, lane);
     double sq, cq;
-    sincos(q, &sq, &cq);
-    // (ck, sk) = (cos lane q, sin lane q), by the rotation recurrence of the serial evaluator
-    double ck = 1.0, sk = 0.0, rc = 1.0, rs = 0.0;
-#pragma unroll 1
-    for (int k = 1; k <= HK; ++k) {
-        const double cn = fma(rc, cq, -(rs * sq)), sn = fma(rs, cq, rc * sq);
-        rc = cn;
-        rs = sn;
-        if (k == lane) { ck = rc; sk = rs; }
+    sincos_moderate(q, &sq, &cq);
+    // (ck, sk) = (cos lane q, sin lane q): e^{jq} squared four times, then the product
+    // of the powers selected by the bits of the lane number
+    double ck = 1.0, sk = 0.0, pr = cq, pi = sq;
+#pragma unroll
+    for (int bit = 0; bit < 5; ++bit) {
+        if ((lane >> bit) & 1) {
+            const double nr = fma(ck, pr, -(sk * pi)), ni = fma(ck, pi, sk * pr);
+            ck = nr;
+            sk = ni;
+        }
+        if (bit < 4) {
+            const double nr = fma(pr, pr, -(pi * pi)), ni = 2.0 * (pr * pi);
+            pr = nr;
+            pi = ni;
+        }
     }
     double tr = 0.0, ti = 0.0, ur = 0.0, ui = 0.0;
     if (lane == 0) {
@@ -448,8 +427,7 @@ k_fit_direct(const TableDesc *tabs, const JobInfo *jobs, int SP, const double *s
 
     // per-state (mean |d|, 1/var |d|), reference compute_mean_var_power
     if (threadIdx.x < 4)
-        st4[threadIdx.x] = state ? stats_mean_weight(spart1, spart2, job * NGROUP + group, SP,
-                                                     stats_segments(ji.nrows), ch & 3, threadIdx.x)
+        st4[threadIdx.x] = state ? stats_mean_weight(spart2, job * NGROUP + group, ch & 3, threadIdx.x)
                                  : make_double2(1.0, 1.0);
     __syncthreads();
 

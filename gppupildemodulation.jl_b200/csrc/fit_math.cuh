@@ -46,69 +46,114 @@ __device__ __forceinline__ double solve_linear(const FitConsts &k, bool offs, do
 }
 
 // J_0(b) .. J_HK(b) by Miller's backward recurrence J_{k-1} = (2k/b) J_k - J_{k+1}
-// from k = 56, normalised with J_0 + 2 sum J_{2k} = 1 (|b| <= HARM_BMAX keeps the
-// start order far in the decaying region).  Valid for either sign of b.
+// from k = BESSEL_M = 40 (far in the decaying region for |b| <= HARM_BMAX: the
+// result is within 2.3e-16 absolute of the true values, as with any higher start),
+// normalised with J_0 + 2 sum J_{2k} = 1.  Valid for either sign of b.  The
+// recurrence grows like (2k/b)^k, so |b| < 1e-4 uses the first terms of the power
+// series instead (the rest is below 1e-19).
+constexpr int BESSEL_M = 40;
+constexpr double BESSEL_TINY = 1.0e-4;
+
+// value for order k of the tiny-|b| series, x = b/2
+__device__ __forceinline__ double bessel_tiny(double b, int k) {
+    const double x = 0.5 * b, x2 = x * x;
+    if (k == 0) return 1.0 - x2;
+    if (k == 1) return x * (1.0 - 0.5 * x2);
+    if (k == 2) return 0.5 * x2;
+    if (k == 3) return x2 * x * (1.0 / 6.0);
+    return 0.0;
+}
+
+// Two recurrence steps (k even -> orders k-1 and k-2), shared by both evaluators.
+#define GPPD_BESSEL_STEP2(k, kd, tb, jp, jc, seven, ON_ODD, ON_EVEN)   \
+    {                                                                  \
+        const double j1 = fma((kd) * (tb), jc, -(jp)); /* J_{k-1} */   \
+        const double j0 = fma(((kd) - 1.0) * (tb), j1, -(jc)); /* J_{k-2} */ \
+        ON_ODD(k - 1, j1);                                             \
+        ON_EVEN(k - 2, j0);                                            \
+        jp = j1;                                                       \
+        jc = j0;                                                       \
+        if (k - 2 > 0) seven += j0;                                    \
+        kd -= 2.0;                                                     \
+    }
+
 __device__ __forceinline__ void bessel_j(double b, double *J) {
-    if (b == 0.0) {
-        J[0] = 1.0;
+    if (fabs(b) < BESSEL_TINY) {
 #pragma unroll 1
-        for (int k = 1; k <= HK; ++k) J[k] = 0.0;
+        for (int k = 0; k <= HK; ++k) J[k] = bessel_tiny(b, k);
         return;
     }
-    const int M = 56;
     const double tb = 2.0 / b;
-    double jp = 0.0, jc = 1.0e-250, sum = 0.0;
+    double jp = 0.0, jc = 1.0e-280, seven = 0.0, kd = (double)BESSEL_M;
+#define GPPD_STORE(kk, v) if ((kk) <= HK) J[kk] = (v)
 #pragma unroll 1
-    for (int k = M; k >= 1; --k) {
-        double jm = fma((double)k * tb, jc, -jp);  // J_{k-1}
-        jp = jc;
-        jc = jm;
-        if (k - 1 <= HK) J[k - 1] = jc;
-        if (((k - 1) & 1) == 0) sum += (k - 1 == 0) ? jc : 2.0 * jc;
-        if (fabs(jc) > 1.0e200) {  // rescale (tiny |b|: the recurrence grows like (2k/b)^k)
-            jc *= 1.0e-200;
-            jp *= 1.0e-200;
-            sum *= 1.0e-200;
-#pragma unroll 1
-            for (int i = k - 1; i <= HK; ++i) J[i] *= 1.0e-200;
-        }
-    }
-    double inv = 1.0 / sum;
+    for (int k = BESSEL_M; k >= 2; k -= 2) GPPD_BESSEL_STEP2(k, kd, tb, jp, jc, seven, GPPD_STORE, GPPD_STORE)
+#undef GPPD_STORE
+    const double inv = 1.0 / (jc + 2.0 * seven);   // jc = J_0
 #pragma unroll 1
     for (int k = 0; k <= HK; ++k) J[k] *= inv;
 }
 
-// Per-state statistics of one (job, group) from the two partial-sum passes:
-//   part1[(jg*P + p)*STATS_VALS + dio*4 + st] = sum |d|,  [.. + 16 + st] = count
-//   part2[(jg*P + p)*16 + dio*4 + st]         = sum (|d| - mean)^2
-// mean = sum/n, weight = 1/var = (n-1)/M2 (reference src/Faint.jl:93-98).  P is the
-// stride (max segments per job in the batch), nseg the job's own segment count;
-// segments are added in index order so every kernel gets bit-identical values.
-constexpr int STATS_SEG_ROWS = 4096;
+// J_lane(b) for lane <= HK: every lane of a warp runs the same recurrence (uniform
+// control flow, no array) and keeps the term of its own order.
+__device__ __forceinline__ double bessel_j_lane(double b, int lane) {
+    if (fabs(b) < BESSEL_TINY) return bessel_tiny(b, lane);
+    const double tb = 2.0 / b;
+    double jp = 0.0, jc = 1.0e-280, seven = 0.0, kd = (double)BESSEL_M, mine = 0.0;
+#define GPPD_KEEP(kk, v) if ((kk) == lane) mine = (v)
+#pragma unroll 4
+    for (int k = BESSEL_M; k >= 2; k -= 2) GPPD_BESSEL_STEP2(k, kd, tb, jp, jc, seven, GPPD_KEEP, GPPD_KEEP)
+#undef GPPD_KEEP
+    return mine * (1.0 / (jc + 2.0 * seven));
+}
+
+// sin and cos of a moderate argument (|x| < 1e5), < 1 ulp: two-constant Cody-Waite
+// reduction by pi/2 with FMAs (exact first step) and the fdlibm kernel polynomials in
+// Horner/FMA form.  About a third of the instructions of the general-purpose
+// sincos(), which carries a Payne-Hanek path.  Every operation is an explicit fma or
+// a single multiply, so the result does not depend on the -fmad setting.
+__device__ __forceinline__ void sincos_moderate(double x, double *sn, double *cs) {
+    if (!(fabs(x) < 1.0e5)) {
+        sincos(x, sn, cs);
+        return;
+    }
+    const double fn = rint(x * 6.36619772367581382433e-01);
+    const int k = (int)fn;
+    double r = fma(-fn, 1.57079632679489655800e+00, x);
+    r = fma(-fn, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double ks = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    pc = fma(z, pc, -0.5);
+    const double kc = fma(z, pc, 1.0);
+    const double s0 = (k & 1) ? kc : ks, c0 = (k & 1) ? ks : kc;
+    *sn = (k & 2) ? -s0 : s0;
+    *cs = ((k + 1) & 2) ? -c0 : c0;
+}
+
+// Per-state statistics of one (job, group) (reference compute_mean_var_power,
+// src/Faint.jl:89-100): the statistics pass leaves, per (job, group), a table of 16
+// (mean |d|, weight = 1 / var |d|) pairs indexed [diode * 4 + state].
+//   part[(jg*P + p)*STATS_VALS + ...]: per FIXED segment of STATS_SEG_ROWS rows,
+//       [0..3] row count per state, [4..19] sum (|d| - pivot), [20..35] sum (|d| - pivot)^2
+//       per (diode, state); the pivot is |d| at the job's first row of the state
+//   table[jg*16 + diode*4 + state] = (mean, weight), segments added in index order,
+// so the values are deterministic and independent of the batch the job is in.
+constexpr int STATS_SEG_ROWS = 2048;
 __host__ __device__ inline int stats_segments(long long nrows) {
     return (int)((nrows + STATS_SEG_ROWS - 1) / STATS_SEG_ROWS);
 }
-__device__ __forceinline__ double stats_mean(const double *part1, int jg, int P, int nseg, int dio,
-                                             int st) {
-    double s = 0.0, n = 0.0;
-    for (int p = 0; p < nseg; ++p) {
-        const double *q = part1 + ((long long)jg * P + p) * STATS_VALS;
-        s += q[dio * 4 + st];
-        n += q[16 + st];
-    }
-    return s / n;
-}
-__device__ __forceinline__ double2 stats_mean_weight(const double *part1, const double *part2,
-                                                     int jg, int P, int nseg, int dio, int st) {
-    double s = 0.0, n = 0.0, m2 = 0.0;
-    for (int p = 0; p < nseg; ++p) {
-        const double *q = part1 + ((long long)jg * P + p) * STATS_VALS;
-        s += q[dio * 4 + st];
-        n += q[16 + st];
-        m2 += part2[((long long)jg * P + p) * 16 + dio * 4 + st];
-    }
-    double var = m2 / (n - 1.0);   // n == 1 -> 0/0 = NaN as in Julia
-    return make_double2(s / n, 1.0 / var);
+__device__ __forceinline__ double2 stats_mean_weight(const double *table, int jg, int dio, int st) {
+    return reinterpret_cast<const double2 *>(table)[jg * 16 + dio * 4 + st];
 }
 
 }  // namespace gppd

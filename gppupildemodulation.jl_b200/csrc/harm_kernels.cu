@@ -161,8 +161,7 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
 
     if (threadIdx.x < 16) {
         s_stats[threadIdx.x] = tb.state
-            ? stats_mean_weight(spart1, spart2, jg, SP, stats_segments(ji.nrows), threadIdx.x >> 2,
-                                threadIdx.x & 3)
+            ? stats_mean_weight(spart2, jg, threadIdx.x >> 2, threadIdx.x & 3)
             : make_double2(1.0, 1.0);
     } else if (threadIdx.x < 21) {
         const int k = threadIdx.x - 16;

@@ -19,18 +19,22 @@ struct ExportDesc {
 void launch_segmentation(const Launcher &L, const TableDesc *d_tabs, int ntables,
                          long long max_rows, int max_timers);
 
-// per-row basis + per-job theta range / valid count
+// per-row basis + per-job theta range / valid count / first row of each state
+// (d_nvalid: 5 ints per job)
 void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
                   int max_jobs_per_table, int njobs, unsigned flags,
                   unsigned long long *d_thkeys, int *d_nvalid, JobInfo *d_jobs);
 
-// per-state sums (reference compute_mean_var_power, src/Faint.jl:89-100), two passes
+// per-state (mean |d|, 1 / var |d|) table (reference compute_mean_var_power,
+// src/Faint.jl:89-100): d_part = per-segment partials, d_table = [njobs*8][16] double2
+// d_faint_jobs: the nfaint jobs (batch job indices) whose table has states
 void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
-                  unsigned flags, int P, double *d_part1, double *d_part2);
+                  const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
+                  double *d_part, double *d_table);
 
 // Jacobi-Anger harmonic sums of every fit + reduction into the harmonic table
 int harm_max_segments(long long max_rows_per_job);   // fixed 12288-row segments
-int stats_max_segments(long long max_rows_per_job);  // fixed 4096-row segments
+int stats_max_segments(long long max_rows_per_job);  // fixed 2048-row segments
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab);

@@ -230,12 +230,16 @@ void launch_segmentation(const Launcher &L, const TableDesc *d_tabs, int ntables
 // ~3e10 rad argument, done ONCE per row instead of once per objective call,
 // plus the per-job theta range and valid-row count.
 // ===========================================================================
+// per-job counters: [0] valid rows, [1 + s] first row (within the job) of state s
+constexpr int JOBCNT = 5;
+
 __global__ void k_init_thkeys(unsigned long long *thkeys, int *nvalid, int njobs) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= njobs) return;
     thkeys[2 * j] = ~0ull;
     thkeys[2 * j + 1] = 0ull;
-    nvalid[j] = 0;
+    nvalid[JOBCNT * j] = 0;
+    for (int s = 0; s < 4; ++s) nvalid[JOBCNT * j + 1 + s] = 0x7fffffff;
 }
 
 __global__ void k_basis(const TableDesc *tabs, unsigned flags, unsigned long long *thkeys,
@@ -249,7 +253,15 @@ __global__ void k_basis(const TableDesc *tabs, unsigned flags, unsigned long lon
     tb.basis[i] = make_double2(s, c);
     long long job = tb.job0 + i / tb.wrows;
     unsigned long long key = f64_key(th);
-    int valid = tb.state ? (row_valid(tb.state[i], flags) ? 1 : 0) : 1;
+    int st = ST_NORMAL, valid = 1;
+    if (tb.state) {
+        st = tb.state[i];
+        valid = row_valid(st, flags) ? 1 : 0;
+        // first row of every run of a state: candidates for the job's first row of it
+        const long long il = i - (i / tb.wrows) * tb.wrows;
+        if (valid && st >= 0 && st <= 3 && (il == 0 || tb.state[i - 1] != st))
+            atomicMin(nvalid + JOBCNT * job + 1 + st, (int)il);
+    }
     // warp-aggregate when a full warp sits in one job
     unsigned mask = __activemask();
     if (mask == 0xffffffffu) {
@@ -267,14 +279,14 @@ __global__ void k_basis(const TableDesc *tabs, unsigned flags, unsigned long lon
             if ((threadIdx.x & 31) == 0) {
                 atomicMin(thkeys + 2 * job, kmin);
                 atomicMax(thkeys + 2 * job + 1, kmax);
-                if (cnt) atomicAdd(nvalid + job, cnt);
+                if (cnt) atomicAdd(nvalid + JOBCNT * job, cnt);
             }
             return;
         }
     }
     atomicMin(thkeys + 2 * job, key);
     atomicMax(thkeys + 2 * job + 1, key);
-    if (valid) atomicAdd(nvalid + job, 1);
+    if (valid) atomicAdd(nvalid + JOBCNT * job, 1);
 }
 
 __global__ void k_jobinfo(const TableDesc *tabs, const unsigned long long *thkeys,
@@ -290,7 +302,7 @@ __global__ void k_jobinfo(const TableDesc *tabs, const unsigned long long *thkey
     ji.row0 = (long long)jl * tb.wrows;
     long long rem = tb.tv.n - ji.row0;
     ji.nrows = (int)(rem < tb.wrows ? rem : tb.wrows);
-    ji.nvalid = nvalid[j];
+    ji.nvalid = nvalid[JOBCNT * j];
     ji.table = t;
     ji.pad = 0;
     jobs[j] = ji;
@@ -308,106 +320,172 @@ void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
 }
 
 // ===========================================================================
-// Per-state statistics of |d| (FAINT), as two partial-sum passes over row
-// tiles: pass 1 sums |d| and counts per state, pass 2 sums (|d| - mean)^2 with
-// the pass-1 mean (the reference's mean / var(...; mean) pair).  One block per
-// (job, group, part); parts are combined in index order by the consumers
-// (stats_mean / stats_mean_weight).  A part is a FIXED segment of
-// STATS_SEG_ROWS rows of the job, so results are deterministic and independent of
-// the batch the job is in.
+// Per-state statistics of |d| (FAINT; reference compute_mean_var_power,
+// src/Faint.jl:89-100: mean(|d|) and 1 / var(|d|; mean) per state over the valid
+// rows).  ONE streaming pass: per (diode, state) the sums of (x - p) and (x - p)^2,
+// x = |d|, around a pivot p = |d| at the job's first row of that state (found by the
+// basis pass), so that  mean = p + S1/n,  sum (x - mean)^2 = S2 - S1^2/n  without the
+// cancellation of raw moments.  One block per (job, group, FIXED segment of
+// STATS_SEG_ROWS rows); k_stats_final adds the segments of a job in index order.
 // ===========================================================================
-constexpr int STATS_THREADS = 128;
+constexpr int STATS_THREADS = 256;
+constexpr int STATS_RPT = STATS_SEG_ROWS / STATS_THREADS;   // rows per thread
+constexpr int STATS_BATCH = 4;                              // rows loaded ahead of their use
 
-template <int NV>
-__device__ __forceinline__ void block_sum_n(double (&v)[NV], double *red, int nwarps) {
+__global__ void __launch_bounds__(STATS_THREADS, 2)
+k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, const int *jobcnt,
+            unsigned flags, int P, double *part) {
+    __shared__ double s_piv[16];
+    __shared__ double s_red[STATS_VALS][STATS_THREADS / 32];
+    const int p = blockIdx.x;
+    const int job = faint_jobs[blockIdx.y >> 3], group = blockIdx.y & 7;
+    const int jg = job * NGROUP + group;
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    if (!tb.state) return;
+    const long long seg0 = (long long)p * STATS_SEG_ROWS;
+    if (seg0 >= ji.nrows) return;
+    const int nseg = (int)((ji.nrows - seg0) < STATS_SEG_ROWS ? (ji.nrows - seg0) : STATS_SEG_ROWS);
+    const TableView &tv = tb.tv;
+    const bool vec = tv.kind == 0 && !tv.big_endian && (tv.volt_stride & 15) == 0 &&
+                     (reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0;
+    if (threadIdx.x < 16) {   // pivots
+        const int dio = threadIdx.x >> 2, st = threadIdx.x & 3;
+        const int first = jobcnt[JOBCNT * job + 1 + st];
+        double pv = 0.0;
+        if (first != 0x7fffffff) {
+            const double2 d = row_sample(tv, ji.row0 + first, group * 4 + dio);
+            pv = sqrt(fma(d.x, d.x, d.y * d.y));
+        }
+        s_piv[threadIdx.x] = pv;
+    }
+    double2 off[4];
 #pragma unroll
-    for (int k = 0; k < NV; ++k)
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    int w = threadIdx.x >> 5;
+    for (int d = 0; d < 4; ++d)
+        off[d] = (tv.kind == 0 && tv.offsets) ? __ldg(tv.offsets + group * 4 + d) : make_double2(0.0, 0.0);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
+
+    double cnt[4], s1[16], s2[16];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) red[k * 8 + w] = v[k];
+    for (int k = 0; k < 16; ++k) s1[k] = s2[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt[k] = 0.0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < STATS_RPT; j0 += STATS_BATCH) {
+        // the loads of a batch of rows are issued before their first use
+        float4 ra[STATS_BATCH], rb[STATS_BATCH];
+        int rs[STATS_BATCH];
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < STATS_BATCH; ++j) {
+                const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
+                rs[j] = -2;
+                if (i < nseg) {
+                    const long long r = ji.row0 + seg0 + i;
+                    const float4 *q = reinterpret_cast<const float4 *>(
+                        reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride + 32 * group);
+                    ra[j] = __ldg(q);
+                    rb[j] = __ldg(q + 1);
+                    rs[j] = tb.state[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < STATS_BATCH; ++j) {
+            const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
+            if (i >= nseg) continue;
+            const long long r = ji.row0 + seg0 + i;
+            int st = vec ? rs[j] : (int)tb.state[r];
+            if (!row_valid(st, flags) || st < 0 || st > 3) continue;
+            double2 dd[4];
+            if (vec) {
+                dd[0] = make_double2((double)ra[j].x - off[0].x, (double)ra[j].y - off[0].y);
+                dd[1] = make_double2((double)ra[j].z - off[1].x, (double)ra[j].w - off[1].y);
+                dd[2] = make_double2((double)rb[j].x - off[2].x, (double)rb[j].y - off[2].y);
+                dd[3] = make_double2((double)rb[j].z - off[3].x, (double)rb[j].w - off[3].y);
+            } else {
+#pragma unroll
+                for (int dio = 0; dio < 4; ++dio) dd[dio] = row_sample(tv, r, group * 4 + dio);
+            }
+#pragma unroll
+            for (int dio = 0; dio < 4; ++dio) {
+                const double e =
+                    sqrt(fma(dd[dio].x, dd[dio].x, dd[dio].y * dd[dio].y)) - s_piv[dio * 4 + st];
+                const double e2 = e * e;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (st == s) {
+                        s1[dio * 4 + s] += e;
+                        s2[dio * 4 + s] += e2;
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (st == s) cnt[s] += 1.0;
+        }
+    }
+    // block sums in a fixed order: [0..3] counts, [4..19] S1, [20..35] S2
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < STATS_VALS; ++k) {
+        double v = k < 4 ? cnt[k] : (k < 20 ? s1[k - 4] : s2[k - 20]);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[k][w] = v;
     }
     __syncthreads();
+    if (threadIdx.x < STATS_VALS) {
+        double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double s = 0.0;
-        for (int j = 0; j < nwarps; ++j) s += red[k * 8 + j];
-        v[k] = s;
+        for (int j = 0; j < STATS_THREADS / 32; ++j) v += s_red[threadIdx.x][j];
+        part[((long long)jg * P + p) * STATS_VALS + threadIdx.x] = v;
     }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(STATS_THREADS)
-k_stats(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, double *part1,
-        double *part2) {
-    __shared__ double red[20 * 8];
-    __shared__ double mean_s[16];
-    const int jg = blockIdx.y, p = blockIdx.x;
-    const int job = jg >> 3, group = jg & 7;
+// add the segments of every (job, group): one thread per (jg, diode, state)
+__global__ void k_stats_final(const TableDesc *tabs, const JobInfo *jobs, const int *jobcnt, int njg,
+                              int P, const double *part, double *table) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= njg * 16) return;
+    const int jg = idx >> 4, ds = idx & 15, st = ds & 3, group = jg & 7;
+    const int job = jg >> 3;
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
     if (!tb.state) return;
     const int nseg = stats_segments(ji.nrows);
-    if (PASS == 2) {
-        if (threadIdx.x < 16)
-            mean_s[threadIdx.x] = stats_mean(part1, jg, P, nseg, threadIdx.x >> 2, threadIdx.x & 3);
-        __syncthreads();
+    double n = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < nseg; ++p) {
+        const double *q = part + ((long long)jg * P + p) * STATS_VALS;
+        n += q[st];
+        s1 += q[4 + ds];
+        s2 += q[20 + ds];
     }
-    double acc[20];
-#pragma unroll
-    for (int k = 0; k < 20; ++k) acc[k] = 0.0;
-    // rows of segment p of the job
-    const long long seg_end = (long long)(p + 1) * STATS_SEG_ROWS < ji.nrows
-                                  ? (long long)(p + 1) * STATS_SEG_ROWS : ji.nrows;
-    if ((long long)p * STATS_SEG_ROWS >= ji.nrows) return;
-    for (long long i = (long long)p * STATS_SEG_ROWS + threadIdx.x; i < seg_end;
-         i += STATS_THREADS) {
-        long long r = ji.row0 + i;
-        int st = tb.state[r];
-        if (!row_valid(st, flags) || st < 0 || st > 3) continue;
-#pragma unroll
-        for (int dio = 0; dio < 4; ++dio) {
-            double2 d = row_sample(tb.tv, r, group * 4 + dio);
-            double a = hypot(d.x, d.y);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                if (st == s) {
-                    if (PASS == 1) {
-                        acc[dio * 4 + s] += a;
-                    } else {
-                        double e = a - mean_s[dio * 4 + s];
-                        acc[dio * 4 + s] = fma(e, e, acc[dio * 4 + s]);
-                    }
-                }
-            }
-        }
-        if (PASS == 1) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (st == s) acc[16 + s] += 1.0;
-        }
+    double pv = 0.0;
+    const int first = jobcnt[JOBCNT * job + 1 + st];
+    if (first != 0x7fffffff) {
+        const double2 d = row_sample(tb.tv, ji.row0 + first, group * 4 + (ds >> 2));
+        pv = sqrt(fma(d.x, d.x, d.y * d.y));
     }
-    block_sum_n<20>(acc, red, STATS_THREADS / 32);
-    if (threadIdx.x < (PASS == 1 ? 20 : 16)) {
-        double *dst = PASS == 1 ? part1 + ((long long)jg * P + p) * STATS_VALS
-                                : part2 + ((long long)jg * P + p) * 16;
-        double v = 0.0;  // select chain instead of a dynamic register-array index
-#pragma unroll
-        for (int k = 0; k < 20; ++k)
-            if (threadIdx.x == k) v = acc[k];
-        dst[threadIdx.x] = v;
-    }
+    // mean of an empty state: 0/0 = NaN like Julia's mean of an empty vector;
+    // weight = 1 / var = (n - 1) / sum (x - mean)^2   (n == 1 -> 0/0 = NaN as in Julia)
+    double2 r;
+    r.x = pv + s1 / n;
+    r.y = (n - 1.0) / (s2 - s1 * (s1 / n));
+    reinterpret_cast<double2 *>(table)[idx] = r;
 }
 
 int stats_max_segments(long long max_rows_per_job) { return stats_segments(max_rows_per_job); }
 
 void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
-                  unsigned flags, int P, double *d_part1, double *d_part2) {
-    dim3 grid(P, njobs * NGROUP);
-    k_stats<1><<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, flags, P, d_part1, d_part2);
-    k_stats<2><<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, flags, P, d_part1, d_part2);
+                  const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
+                  double *d_part, double *d_table) {
+    if (nfaint <= 0) return;
+    dim3 grid(P, nfaint * NGROUP);
+    k_stats_seg<<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt, flags, P,
+                                                     d_part);
+    const int njg = njobs * NGROUP;
+    k_stats_final<<<(njg * 16 + 127) / 128, 128, 0, L.stream>>>(d_tabs, d_jobs, d_jobcnt, njg, P, d_part,
+                                                               d_table);
     *L.counter += 2;
 }
 
@@ -445,38 +523,6 @@ __device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned fl
     sincos(ang, &sa, &ca);
     return make_double2(__dadd_rn(__dmul_rn(d.x, ca), __dmul_rn(d.y, sa)),
                         __dadd_rn(__dmul_rn(d.y, ca), -__dmul_rn(d.x, sa)));
-}
-
-// sin and cos of a moderate argument (|x| < 1e5; psi = b sin(.) is a few radians):
-// two-constant Cody-Waite reduction by pi/2 done with FMAs (exact first step) and
-// the fdlibm kernel polynomials in Horner/FMA form, < 1 ulp.  About a third of the
-// instructions of the general-purpose sincos(), which carries a Payne-Hanek path.
-__device__ __forceinline__ void sincos_moderate(double x, double *sn, double *cs) {
-    if (!(fabs(x) < 1.0e5)) {
-        sincos(x, sn, cs);
-        return;
-    }
-    const double fn = rint(x * 6.36619772367581382433e-01);
-    const int k = (int)fn;
-    double r = fma(-fn, 1.57079632679489655800e+00, x);
-    r = fma(-fn, 6.12323399573676603587e-17, r);
-    const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    const double ks = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    pc = fma(z, pc, -0.5);
-    const double kc = fma(z, pc, 1.0);
-    const double s0 = (k & 1) ? kc : ks, c0 = (k & 1) ? ks : kc;
-    *sn = (k & 2) ? -s0 : s0;
-    *cs = ((k + 1) & 2) ? -c0 : c0;
 }
 
 // Demodulation constants of one fit held in registers by the streaming kernel.
