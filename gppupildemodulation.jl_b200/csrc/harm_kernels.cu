@@ -17,31 +17,38 @@
 //     Z_k = (A + B) + j (C - D),   Z_{-k} = (A - B) + j (C + D)
 // i.e. 4 FMAs per (row, diode, |k|) for two harmonics.
 //
+// Per group (4 diodes) and row tile the sums are the product
+//     C[48 x 8] += E^T[48 x rows] V[rows x 8],
+//     E[row][2(k-1) + {0,1}] = (cos, sin)(k theta_row), k = 1..24,
+//     V[row][2d + {0,1}]     = (x, y) of diode d's stream value,
+// whose entries are exactly the four sums: (cos,x) = A, (sin,y) = B, (cos,y) = C,
+// (sin,x) = D.  The FP64 units take this contraction as warp-level
+// mma.sync.m8n8k4.f64 (DMMA: one instruction = 256 FMAs on the same FP64 units as
+// DFMA, measured 37.1 against 33.9 TFLOP/s), which removes the instruction-issue and
+// register pressure that kept the plain-FMA form near half of the pipe's peak.  E is
+// never stored: the lane that owns element (m, row) of an A fragment generates the six
+// harmonics k0, k0 + 4, ..., k0 + 20 it needs with the three-term recurrence
+//     trig((k + 4) t) = 2 cos(4 t) trig(k t) - trig((k - 4) t)      (one FMA each)
+// from the row's (cos, sin)(t .. 4t), which the producers tabulate.
+//
 // Kernel structure (k_harm_accumulate): one block of 16 warps per (job, group,
 // segment), persistent over the segment's row tiles of TR rows, one block per SM.
-// The register file is re-split between the roles with setmaxnreg (consumers 168,
-// producers 88 registers per thread).
 //   * Eight PRODUCER warps (two per SM sub-partition, one row per thread and tile:
-//     their long dependent chains need the extra warps to hide latency) stream the raw table bytes of
-//     the next-but-one tile into a 3-stage shared-memory ring with cp.async
-//     (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's basis, the
-//     state byte) -- no register dependency, so the global-memory latency is off
-//     the critical path -- and turn the previous stage into a compute tile:
-//     e^{j theta}, the four diodes' z (or y) values, and the start phasors
-//     e^{j (6h+1) theta}, h = 0..3 (one complex product, then the three-term
-//     recurrence s_{m+1} = 2 cos(6 theta) s_m - s_{m-1}).
-//   * Eight CONSUMER warps (two per sub-partition) each own KC = 6 harmonics of 2
-//     of the 4 diodes: 48 FP64 accumulators per thread; harmonic k+1 comes from
-//     k by one complex rotation, the following ones by the three-term recurrence
-//     (2 FMAs per harmonic): 61 FP64 instructions per row for 48 useful FMAs, and
-//     64 bytes of shared-memory reads (the FP64 pipe and the shared-memory port are
-//     the two resources this kernel balances).
+//     their long dependent chains need the warps to hide latency) stream the raw
+//     table bytes of the next-but-one tile into a 3-stage shared-memory ring with
+//     cp.async (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's
+//     basis, the state byte) -- no register dependency, so the global-memory latency
+//     is off the critical path -- and turn the previous stage into a compute tile:
+//     (cos, sin)(k theta), k = 1..4, and the four diodes' z (or y) values.
+//   * Eight CONSUMER warps (two per sub-partition) each take 32 rows of the tile:
+//     8 k-steps of 4 rows, per k-step 5 recurrence FMAs and 6 DMMAs into the 12
+//     accumulator registers that hold the warp's 48 x 8 partial C.
 // Compute tiles are triple buffered and handed over with mbarriers (full / empty
 // per buffer), so consumer warps never wait for each other, only for data.
 // A segment is a FIXED run of HARM_SEG_TILES tiles of the job (independent of
-// the batch and of the launch shape) and k_harm_reduce adds the segments in index
-// order, so a fit's sums -- hence its whole NEWUOA trajectory -- do not depend on
-// what else is in the batch.
+// the batch and of the launch shape), the consumer warps' partial C are added in warp
+// order, and k_harm_reduce adds the segments in index order, so a fit's sums -- hence
+// its whole NEWUOA trajectory -- do not depend on what else is in the batch.
 #include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
@@ -51,21 +58,24 @@ namespace gppd {
 
 constexpr int TR = 256;                       // rows per tile
 constexpr int HARM_SEG_TILES = 48;            // tiles per segment (12288 rows)
-constexpr int KC = 6;                         // harmonics per consumer warp
-constexpr int NHR = HK / KC;                  // harmonic ranges
-constexpr int NCONS = NHR * 2;                // consumer warps: range x diode pair
+constexpr int NCONS = 8;                      // consumer warps, 32 rows of a tile each
 constexpr int NPROD = 8;                      // producer warps
 constexpr int HARM_THREADS = (NCONS + NPROD) * 32;
 constexpr int RAW_STAGES = 3;
 constexpr int TILE_BUFS = 3;                   // compute tiles in flight
 constexpr int ROWS_PER_PROD = TR / (NPROD * 32);
-static_assert(NHR * KC == HK, "HK must be a multiple of KC");
+constexpr int MTILES = 2 * HK / 8;            // 8-row tiles of the 48 (harmonic, cos|sin) rows of C
+static_assert(2 * HK == 8 * MTILES && MTILES == 6, "lane k0 + 4j must cover k = 1..HK");
 static_assert(ROWS_PER_PROD * NPROD * 32 == TR, "TR must be a multiple of the producer threads");
+static_assert(NCONS * 32 == TR, "each consumer warp takes 32 rows of a tile");
 
+// Component-major with a 4-double pad: the producers' stores (32 consecutive rows of
+// one component) and the consumers' fragment loads (8 components x 4 consecutive rows)
+// are both bank-conflict free.
+constexpr int TRP = TR + 4;
 struct HarmTile {
-    double2 e1[TR];            // (cos theta, sin theta)
-    double2 start[NHR][TR];    // (cos, sin)((KC*h + 1) theta)
-    double2 v[4][TR];          // stream values of the group's 4 diodes
+    double e[8][TRP];          // (cos t, sin t, cos 2t, sin 2t, cos 3t, sin 3t, cos 4t, sin 4t)
+    double v[8][TRP];          // stream values of the group's 4 diodes: (x0, y0, ..., x3, y3)
 };
 
 struct RawStage {              // raw bytes of one tile, as copied by cp.async
@@ -116,11 +126,12 @@ __device__ __forceinline__ double2 fc_unit(double x, double y) {
     return fc_phasor(make_double2(x, y));
 }
 
-__device__ __forceinline__ void reg_alloc_consumer() {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
-}
-__device__ __forceinline__ void reg_dealloc_producer() {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n");
+// C[8x8] += A[8x4] B[4x8] on the FP64 units: lane t holds A[t/4][t%4], B[t%4][t/4]
+// and C[t/4][2(t%4)], C[t/4][2(t%4) + 1]
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
 // The constant (b, phi independent) sums of a fit, per diode:
@@ -141,6 +152,8 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     __shared__ double2 s_off[5];      // centres of the 4 diodes + FC (kind-0 tables)
     __shared__ double s_red[NPROD][24];
     __shared__ unsigned long long s_cnt[NPROD];
+    double *s_cpart = reinterpret_cast<double *>(smem_raw);   // [NCONS][48][8], reuses tile 0 at the end
+    static_assert(NCONS * 48 * 8 * 8 <= (int)sizeof(HarmTile), "partial C must fit in a tile buffer");
 
     constexpr int NCONST = KIND == 0 ? 7 : 2;
     constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;   // sums a producer thread carries per diode
@@ -179,63 +192,56 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
 
     if (!producer) {
         // =================== consumers ===================
-        reg_alloc_consumer();
-        const int h = warp >> 1, pair = warp & 1;
-        double acc[KC][2][4];
+        // lane (m8, r) owns A[m8][r] = trig(k theta_row) of harmonic k = k0 + 4j in
+        // m-tile j (k0 = m8/2 + 1, trig = cos for even m8, sin for odd) and B[r][m8] =
+        // V[row][m8], row = (k-step base) + r
+        const int m8 = lane >> 2, r4 = lane & 3;
+        const int k0 = (m8 >> 1) + 1, trig = m8 & 1;
+        // trig((k0 - 4) t) = +cos((4 - k0) t) or -sin((4 - k0) t); k0 = 4: cos 0 = 1, sin 0 = 0
+        const int pidx = k0 < 4 ? 2 * (3 - k0) + trig : 0;
+        const double psgn = k0 < 4 ? (trig ? -1.0 : 1.0) : 0.0;
+        const double padd = (k0 == 4 && !trig) ? 1.0 : 0.0;
+        double c[MTILES][2];
 #pragma unroll
-        for (int a = 0; a < KC; ++a)
-#pragma unroll
-            for (int d = 0; d < 2; ++d)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[a][d][c] = 0.0;
+        for (int j = 0; j < MTILES; ++j) c[j][0] = c[j][1] = 0.0;
 
         for (int it = 0; it < nt; ++it) {
             const int b = it % TILE_BUFS;
             const HarmTile &T = tiles[b];
             mbar_wait(&full[b], (unsigned)(it / TILE_BUFS) & 1u);
-#pragma unroll 2
-            for (int i = 0; i < TR / 32; ++i) {
-                const int rr = lane + 32 * i;
-                const double2 e1 = T.e1[rr];
-                double2 cs = T.start[h][rr];
-                const double2 v0 = T.v[2 * pair][rr], v1 = T.v[2 * pair + 1][rr];
-                const double tc = e1.x + e1.x;
-                double2 prev = cs;
+#pragma unroll 4
+            for (int ks = 0; ks < 8; ++ks) {
+                const int row = warp * 32 + ks * 4 + r4;
+                const double a0 = T.e[m8][row];
+                const double c4 = T.e[6][row];
+                const double pv = T.e[pidx][row];
+                const double bv = T.v[m8][row];
+                const double tc = c4 + c4;
+                double am = fma(psgn, pv, padd);        // harmonic k0 - 4
+                double ak = a0;                         // harmonic k0
 #pragma unroll
-                for (int a = 0; a < KC; ++a) {
-                    acc[a][0][0] = fma(cs.x, v0.x, acc[a][0][0]);
-                    acc[a][0][1] = fma(cs.y, v0.y, acc[a][0][1]);
-                    acc[a][0][2] = fma(cs.x, v0.y, acc[a][0][2]);
-                    acc[a][0][3] = fma(cs.y, v0.x, acc[a][0][3]);
-                    acc[a][1][0] = fma(cs.x, v1.x, acc[a][1][0]);
-                    acc[a][1][1] = fma(cs.y, v1.y, acc[a][1][1]);
-                    acc[a][1][2] = fma(cs.x, v1.y, acc[a][1][2]);
-                    acc[a][1][3] = fma(cs.y, v1.x, acc[a][1][3]);
-                    if (a == 0) {
-                        cs = cmul(cs, e1);
-                    } else if (a + 1 < KC) {   // e^{j(k+1)t} = 2 cos t e^{jkt} - e^{j(k-1)t}
-                        const double2 nx = make_double2(fma(tc, cs.x, -prev.x), fma(tc, cs.y, -prev.y));
-                        prev = cs;
-                        cs = nx;
+                for (int j = 0; j < MTILES; ++j) {
+                    dmma_m8n8k4(c[j][0], c[j][1], ak, bv);
+                    if (j + 1 < MTILES) {
+                        const double an = fma(tc, ak, -am);
+                        am = ak;
+                        ak = an;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[b]);
         }
+        // park the warp's partial C; added over the warps in order after the barrier below
+        __syncthreads();   // every tile has been consumed: tile buffer 0 is free
 #pragma unroll
-        for (int a = 0; a < KC; ++a)
-#pragma unroll
-            for (int d = 0; d < 2; ++d)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    double s = acc[a][d][c];
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) out[(2 * pair + d) * HP + NCONST + (h * KC + a) * 4 + c] = s;
-                }
+        for (int j = 0; j < MTILES; ++j) {
+            double *dst = s_cpart + ((warp * 48 + 8 * j + m8) * 8 + 2 * r4);
+            dst[0] = c[j][0];
+            dst[1] = c[j][1];
+        }
     } else {
         // =================== producers ===================
-        reg_dealloc_producer();
         const TableView &tv = tb.tv;
         // cp.async needs 16-byte aligned sources
         const bool async_ok = tv.kind == 1 ||
@@ -374,23 +380,17 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                         }
                     }
                 }
-                T.e1[rr] = e1;
-                // start phasors e^{j (6h+1) theta}: e6 = ((e1^2) e1)^2, then the
-                // three-term recurrence with 2 cos(6 theta)
-                const double2 e6 = csqr(cmul(csqr(e1), e1));
-                const double tc6 = e6.x + e6.x;
-                double2 s0 = e1, s1 = cmul(e1, e6);
-                T.start[0][rr] = s0;
-                T.start[1][rr] = s1;
+                // (cos, sin)(k theta), k = 1..4
+                const double2 e2 = csqr(e1), e3 = cmul(e2, e1), e4 = csqr(e2);
+                T.e[0][rr] = e1.x; T.e[1][rr] = e1.y;
+                T.e[2][rr] = e2.x; T.e[3][rr] = e2.y;
+                T.e[4][rr] = e3.x; T.e[5][rr] = e3.y;
+                T.e[6][rr] = e4.x; T.e[7][rr] = e4.y;
 #pragma unroll
-                for (int hh = 2; hh < NHR; ++hh) {
-                    const double2 s2 = make_double2(fma(tc6, s1.x, -s0.x), fma(tc6, s1.y, -s0.y));
-                    T.start[hh][rr] = s2;
-                    s0 = s1;
-                    s1 = s2;
+                for (int d = 0; d < 4; ++d) {
+                    T.v[2 * d][rr] = vv[d].x;
+                    T.v[2 * d + 1][rr] = vv[d].y;
                 }
-#pragma unroll
-                for (int d = 0; d < 4; ++d) T.v[d][rr] = vv[d];
             }
         };
 
@@ -417,6 +417,7 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
             if (lane == 0) mbar_arrive(&full[b]);
         }
         if (async_ok) cp_async_wait<0>();
+        __syncthreads();   // pairs with the consumers' barrier before they park their partial C
 
         const int pw = warp - NCONS;
 #pragma unroll
@@ -429,6 +430,17 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
         if (lane == 0) s_cnt[pw] = cnt;
     }
     __syncthreads();
+    // C[m][n], m = 2(k-1) + {cos, sin}, n = 2d + {x, y}  ->  (A, B, C, D) of harmonic k, diode d
+    if (threadIdx.x < 48 * 8) {
+        const int m = threadIdx.x >> 3, n = threadIdx.x & 7;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NCONS; ++w) s += s_cpart[(w * 48 + m) * 8 + n];
+        const int k = m >> 1, sn = m & 1, d = n >> 1, im = n & 1;
+        // (cos, x) -> A = 0, (sin, y) -> B = 1, (cos, y) -> C = 2, (sin, x) -> D = 3
+        const int slot = sn ? (im ? 1 : 3) : (im ? 2 : 0);
+        out[d * HP + NCONST + k * 4 + slot] = s;
+    }
     if (threadIdx.x < NCONST * 4) {
         const int d = threadIdx.x / NCONST, c = threadIdx.x % NCONST;
         unsigned long long cn = 0;
