@@ -49,6 +49,8 @@
 // the batch and of the launch shape), the consumer warps' partial C are added in warp
 // order, and k_harm_reduce adds the segments in index order, so a fit's sums -- hence
 // its whole NEWUOA trajectory -- do not depend on what else is in the batch.
+#include <type_traits>
+
 #include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
@@ -207,8 +209,17 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
 
         for (int it = 0; it < nt; ++it) {
             const int b = it % TILE_BUFS;
-            const HarmTile &T = tiles[b];
+            HarmTile &T = tiles[b];
             mbar_wait(&full[b], (unsigned)(it / TILE_BUFS) & 1u);
+            {   // (cos, sin)(k theta), k = 2..4, of the warp's 32 rows, one row per lane
+                const int row = warp * 32 + lane;
+                const double2 e1 = make_double2(T.e[0][row], T.e[1][row]);
+                const double2 e2 = csqr(e1), e3 = cmul(e2, e1), e4 = csqr(e2);
+                T.e[2][row] = e2.x; T.e[3][row] = e2.y;
+                T.e[4][row] = e3.x; T.e[5][row] = e3.y;
+                T.e[6][row] = e4.x; T.e[7][row] = e4.y;
+            }
+            __syncwarp();
 #pragma unroll 4
             for (int ks = 0; ks < 8; ++ks) {
                 const int row = warp * 32 + ks * 4 + r4;
@@ -291,7 +302,8 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
         };
 
         // ---- step 2: ring stage (or, unaligned tables, global memory) -> compute tile
-        auto produce = [&](int tile, const RawStage &S, HarmTile &T) {
+        auto produce = [&](auto faint_tag, int tile, const RawStage &S, HarmTile &T) {
+            constexpr bool FAINT = decltype(faint_tag)::value;   // the table has states
 #pragma unroll
             for (int j = 0; j < ROWS_PER_PROD; ++j) {
                 const int rr = ptid + j * NPROD * 32;
@@ -332,7 +344,7 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                             const uint4 q = S.fc[rr];
                             fcs = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
                         }
-                        if (tb.state) {
+                        if (FAINT) {
                             const unsigned sh =
                                 8u * (unsigned)(reinterpret_cast<unsigned long long>(tb.state + r) & 3ull);
                             st = (int)(signed char)((S.state[rr] >> sh) & 0xffu);
@@ -342,17 +354,17 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
 #pragma unroll
                         for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, r, group * 4 + d);
                         fcs = row_sample(tv, r, fc_channel(group));
-                        if (tb.state) st = tb.state[r];
+                        if (FAINT) st = tb.state[r];
                     }
                     e1 = make_double2(sc.y, sc.x);
-                    const bool valid = tb.state ? row_valid(st, flags) : true;
+                    const bool valid = FAINT ? row_valid(st, flags) : true;
                     if (valid) {
                         const double2 fc = fc_unit(fcs.x, fcs.y);
                         cnt += 1ull << (16 * (st & 3));
 #pragma unroll
                         for (int d = 0; d < 4; ++d) {
                             double wpr = fc.x, wpi = fc.y, w = 1.0;   // bright: w = 1, p = FCphasor
-                            if (tb.state) {
+                            if (FAINT) {
                                 const double2 mw = s_stats[d * 4 + (st & 3)];
                                 w = mw.y;
                                 const double wm = mw.y * mw.x;        // p = power .* FCphasor
@@ -380,12 +392,9 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                         }
                     }
                 }
-                // (cos, sin)(k theta), k = 1..4
-                const double2 e2 = csqr(e1), e3 = cmul(e2, e1), e4 = csqr(e2);
-                T.e[0][rr] = e1.x; T.e[1][rr] = e1.y;
-                T.e[2][rr] = e2.x; T.e[3][rr] = e2.y;
-                T.e[4][rr] = e3.x; T.e[5][rr] = e3.y;
-                T.e[6][rr] = e4.x; T.e[7][rr] = e4.y;
+                // (cos, sin)(theta); the consumer warp that owns the row adds k = 2..4
+                T.e[0][rr] = e1.x;
+                T.e[1][rr] = e1.y;
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     T.v[2 * d][rr] = vv[d].x;
@@ -412,7 +421,8 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
                 cp_async_wait<2>();      // tile it's bytes have landed
             }
             if (it >= TILE_BUFS) mbar_wait(&empty[b], (unsigned)(it / TILE_BUFS - 1) & 1u);
-            produce(tile0 + it, raws[it % RAW_STAGES], tiles[b]);
+            if (tb.state) produce(std::true_type{}, tile0 + it, raws[it % RAW_STAGES], tiles[b]);
+            else produce(std::false_type{}, tile0 + it, raws[it % RAW_STAGES], tiles[b]);
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[b]);
         }
