@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--rows", type=int, default=100_000)
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--cpu-files", type=int, default=12, help="files in the CPU-baseline sample")
+    ap.add_argument("--window-rows", type=int, default=0,
+                    help="fit windows of this many rows instead of whole tables (reference --window); "
+                         "an exploration switch, the headline workload is whole-file")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -208,9 +211,13 @@ def main():
     faint = night_plan(F)
     time_us, volt, mjds, fss = generate_night(torch, gp, dev, F, N, rank)
     out = torch.empty_like(volt)
-    params = torch.empty((F, 32, 6), dtype=torch.float64, device=dev)
-    chi2 = torch.empty((F, 32), dtype=torch.float64, device=dev)
-    info = torch.zeros((F, 32, 4), dtype=torch.int32, device=dev)
+    W = args.window_rows if 0 < args.window_rows < N else 0
+    NW = (N + W - 1) // W if W else 1          # windows (jobs) per table
+    if W:
+        args.no_e2e = True
+    params = torch.empty((F, NW * 32, 6), dtype=torch.float64, device=dev)
+    chi2 = torch.empty((F, NW * 32), dtype=torch.float64, device=dev)
+    info = torch.zeros((F, NW * 32, 4), dtype=torch.int32, device=dev)
     offsets = torch.tensor(gp.synthetic.stefan_centres().view(np.float64), device=dev)
     opt = gp.api._options()
     torch.cuda.synchronize()
@@ -226,6 +233,7 @@ def main():
     vp = lambda ts: (C.c_void_p * F)(*[t.data_ptr() for t in ts])
     dpp = lambda arrs: (_lib._dp * F)(*[C.cast(None, _lib._dp) if a is None else a.ctypes.data_as(_lib._dp) for a in arrs])
     b_n = i64([N] * F)
+    b_w = i64([W] * F) if W else None
     b_mjd = (C.c_double * F)(*mjds)
     b_time, b_volt, b_out = vp([time_us[k] for k in range(F)]), vp([volt[k] for k in range(F)]), vp([out[k] for k in range(F)])
     b_par, b_chi, b_info = vp([params[k] for k in range(F)]), vp([chi2[k] for k in range(F)]), vp([info[k] for k in range(F)])
@@ -238,7 +246,7 @@ def main():
 
     def step_resident():
         _lib.check(L.gppd_process_tables_f32_dev(
-            h.raw, 0, C.c_void_p(bench_stream.cuda_stream), F, b_n, None, b_time, b_mjd, b_volt, p(offsets),
+            h.raw, 0, C.c_void_p(bench_stream.cuda_stream), F, b_n, b_w, b_time, b_mjd, b_volt, p(offsets),
             b_t1, b_n1, b_t2, b_n2, C.byref(opt), b_out, b_par, b_chi, b_info, None))
 
     def barrier():
@@ -341,15 +349,15 @@ def main():
     alg_bytes_per_launch = ALG_BYTES_PER_ROW * N * F      # one launch covers the whole night
     achieved = alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9
     fp64_peak = h.fp64_peak_tflops()
-    # algorithmic FP64 work of the fit: measured objective calls x ~35 FMA-class
-    # operations per row and call, 2 flop each
-    # algorithmic FP64 work of the harmonic pass: per (row, diode): 24 harmonics x
-    # 4 FMA (two harmonics each) + 3/4 complex rotation per harmonic group
-    harm_flops_per_launch = F * N * 32 * (24 * 4 + 18) * 2.0
+    # algorithmic FP64 work of the harmonic pass: the contraction C[48 x 8] += E^T V,
+    # i.e. per (row, diode) 24 harmonics x 4 FMA; the recurrences
+    # that generate E and the producers' arithmetic are overhead, not counted
+    harm_flops_per_launch = F * N * 32 * (24 * 4) * 2.0
     harm_ms, harm_n = passes["harmonics"]
     fp64 = {"kernel": "harmonics",
             "achieved_tflops": harm_flops_per_launch / (harm_ms / max(harm_n, 1) * 1e-3) / 1e12 if harm_n else None,
-            "peak_tflops": fp64_peak, "peak_source": "DFMA micro-benchmark in this run",
+            "peak_tflops": fp64_peak,
+            "peak_source": "FP64 micro-benchmark in this run (better of DFMA and mma.sync.m8n8k4.f64)",
             "objective_calls_per_fit": nfev_mean}
     fp64["frac"] = fp64["achieved_tflops"] / fp64_peak if (fp64_peak and fp64["achieved_tflops"]) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak,
@@ -359,8 +367,9 @@ def main():
                 "avg_launch_ms": avg_ms, "launches_timed": dom_n,
                 "pass_ms_per_step": {k: v[0] / args.steps for k, v in passes.items() if v[1]},
                 "fp64": fp64,
-                "note": "one launch of each pass covers the whole night; the harmonic pass is "
-                        "FP64-pipe bound (see fp64), the demod pass HBM/sincos bound"}
+                "note": "one launch of each pass covers the whole night; the dominant (harmonic) pass "
+                        "is bound by the FP64 units, not by HBM (see fp64: its 192 flop per "
+                        "diode-sample against 20 B); the demod pass is the HBM-bound one"}
 
     # ---- CPU baseline on a bounded sample -------------------------------
     cpu = None
@@ -383,6 +392,7 @@ def main():
         "config": {"workload": "night of %d METROLOGY tables x %d rows per GPU (70%% bright / 30%% FAINT), "
                                "whole-file fits, --center stefan (BASELINE.json configs[2])" % (F, N),
                    "tables_per_gpu": F, "rows_per_table": N, "diodes": DIODES, "e2e_slots": S,
+                   "window_rows": W or None,
                    "cache": "inputs (%.1f GB per step) larger than L2" % (F * N * 324 / 1e9),
                    "sharding": "files -> ranks, no data-path collective"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -96,7 +96,7 @@ struct Slot {
     // batch scratch
     DevBuf state, basis, z, y, thkeys, nvalid, jobs, results;
     DevBuf spart1, spart2, partZ, partY, htab;
-    DevBuf timers, lb, events, flags, tabs, exps, faintjobs;
+    DevBuf timers, lb, events, flags, tabs, exps, faintjobs, fbq;
     PassTimer timer;
 };
 
@@ -267,6 +267,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
             if (offs)
                 if ((rc = s.partY.ensure(sizeof(double) * HP_Y * 4 * (size_t)njg * P))) return rc;
             if ((rc = s.htab.ensure(sizeof(double) * HV_COUNT * (size_t)nfits))) return rc;
+            if ((rc = s.fbq.ensure(sizeof(int) * ((size_t)nfits + 1)))) return rc;
         }
     }
 
@@ -348,7 +349,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     if (direct) {
         PassScope ps(h, s, stream, GPPD_PASS_FIT);
         launch_fit_direct(L, d_tabs, s.jobs.as<JobInfo>(), nfits, SP, s.spart1.as<double>(),
-                          s.spart2.as<double>(), fo, true, s.results.as<FitResult>(), d_trace);
+                          s.spart2.as<double>(), fo, true, s.results.as<FitResult>(), d_trace, nullptr);
     } else {
         {
             PassScope ps(h, s, stream, GPPD_PASS_HARMONICS);
@@ -359,14 +360,16 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         DBG(stream, "harmonics");
         {
             PassScope ps(h, s, stream, GPPD_PASS_FIT);
+            CK(cudaMemsetAsync(s.fbq.p, 0, sizeof(int), stream));
             launch_fit_harmonic(L, d_tabs, s.jobs.as<JobInfo>(), s.htab.as<double>(), nfits, fo,
-                                s.results.as<FitResult>(), d_trace);
+                                s.results.as<FitResult>(), d_trace, s.fbq.as<int>());
         }
         DBG(stream, "fit_harmonic");
         {
             PassScope ps(h, s, stream, GPPD_PASS_FALLBACK);
             launch_fit_direct(L, d_tabs, s.jobs.as<JobInfo>(), nfits, SP, s.spart1.as<double>(),
-                              s.spart2.as<double>(), fo, false, s.results.as<FitResult>(), d_trace);
+                              s.spart2.as<double>(), fo, false, s.results.as<FitResult>(), d_trace,
+                              s.fbq.as<int>());
         }
     }
     DBG(stream, "fit_direct");
@@ -497,7 +500,7 @@ int gppd_destroy(gppd_handle h) {
                           &s.offsets, &s.params, &s.chi2, &s.info, &s.trace, &s.state_out,
                           &s.state, &s.basis, &s.z, &s.y, &s.thkeys, &s.nvalid, &s.jobs,
                           &s.results, &s.spart1, &s.spart2, &s.partZ, &s.partY, &s.htab,
-                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps, &s.faintjobs};
+                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps, &s.faintjobs, &s.fbq};
         for (DevBuf *b : bufs) b->release();
         for (cudaEvent_t e : s.timer.ev) cudaEventDestroy(e);
     }
@@ -531,7 +534,7 @@ int gppd_measure_fp64_peak(gppd_handle h, double *tflops) {
     Slot &s = h->slots[0];
     if ((rc = s.flags.ensure(64))) return rc;
     *tflops = measure_dfma_tflops(s.stream, s.flags.as<double>());
-    h->launches += 4;
+    h->launches += 6;
     CK(cudaGetLastError());
     return GPPD_OK;
 }

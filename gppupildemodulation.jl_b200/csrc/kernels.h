@@ -42,13 +42,15 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
 // the fit, harmonic evaluator (one thread per fit)
 void launch_fit_harmonic(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,
                          const double *d_htab, int nfits, const FitOptions &opt,
-                         FitResult *d_results, double *d_trace);
+                         FitResult *d_results, double *d_trace, int *d_fbq);
 
-// the fit, direct evaluator (one block per fit); scratch = false: only fits whose
-// result is flagged `fallback` run, recomputing z / y from the table
+// the fit, direct evaluator (one block per fit); scratch = false: only the fits the
+// harmonic evaluator queued in d_fbq ([0] = count, [1..] = fit numbers) run,
+// recomputing z / y from the table
 void launch_fit_direct(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,
                        int nfits, int SP, const double *d_spart1, const double *d_spart2,
-                       const FitOptions &opt, bool scratch, FitResult *d_results, double *d_trace);
+                       const FitOptions &opt, bool scratch, FitResult *d_results, double *d_trace,
+                       const int *d_fbq);
 
 // demodulation + repack (reference src/Modulation.jl:417-425)
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,

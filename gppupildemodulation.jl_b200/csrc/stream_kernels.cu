@@ -795,8 +795,10 @@ void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int
 }
 
 // ===========================================================================
-// FP64 pipe micro-benchmark: 16 independent DFMA chains per thread.  Gives the
-// measured denominator of the fit's FP64 roofline (MEASURED_PEAKS.json has none).
+// FP64 unit micro-benchmarks: 16 independent DFMA chains per thread, and 8
+// independent mma.sync.m8n8k4.f64 accumulators per warp (the form the harmonic pass
+// uses; both run on the same FP64 units).  The larger of the two is the measured
+// denominator of the fit's FP64 roofline (MEASURED_PEAKS.json has none).
 // ===========================================================================
 __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
     double x[16];
@@ -812,6 +814,23 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
     if (s == 12345.678) out[0] = s;  // keep the chains alive
 }
 
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters, double a, double b) {
+    double c[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c[k] = (double)(threadIdx.x + k) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[2 * k]), "+d"(c[2 * k + 1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += c[k];
+    if (s == 12345.678) out[0] = s;
+}
+
 double measure_dfma_tflops(cudaStream_t stream, double *d_scratch) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -821,16 +840,20 @@ double measure_dfma_tflops(cudaStream_t stream, double *d_scratch) {
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     double best = 0.0;
-    for (int rep = 0; rep < 4; ++rep) {
+    for (int rep = 0; rep < 6; ++rep) {
+        const bool mma = rep >= 3;
         cudaEventRecord(a, stream);
-        k_dfma_peak<<<blocks, 256, 0, stream>>>(d_scratch, iters, 0.999999, 1e-9);
+        if (mma) k_dmma_peak<<<blocks, 256, 0, stream>>>(d_scratch, iters / 4, 0.999999, 1e-9);
+        else k_dfma_peak<<<blocks, 256, 0, stream>>>(d_scratch, iters, 0.999999, 1e-9);
         cudaEventRecord(b, stream);
         cudaEventSynchronize(b);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
-        double flops = 2.0 * 16.0 * iters * 256.0 * blocks;
-        double tf = flops / (ms * 1e-3) / 1e12;
-        if (rep > 0 && tf > best) best = tf;
+        // one warp-level m8n8k4 = 256 FMAs; one DFMA per thread = 1 FMA
+        const double fmas = mma ? 256.0 * 8.0 * (iters / 4) * 8.0 * blocks   // 8 warps per block
+                                : 16.0 * iters * 256.0 * blocks;
+        const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
+        if (rep != 0 && rep != 3 && tf > best) best = tf;
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);

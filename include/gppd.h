@@ -214,8 +214,9 @@ int64_t gppd_launch_count(gppd_handle h);
 #define GPPD_PASS_FALLBACK 7  /* direct re-fit of the fits the harmonic evaluator gave up on */
 #define GPPD_NPASS 8
 int gppd_enable_timing(gppd_handle h, int on);
-/* measured FP64 FMA throughput of the device in TFLOP/s (a DFMA micro-benchmark):
- * the denominator of the fit's FP64 roofline */
+/* measured FP64 FMA throughput of the device in TFLOP/s (the better of a DFMA and an
+ * mma.sync.m8n8k4.f64 micro-benchmark; both use the same FP64 units): the denominator
+ * of the harmonic pass's FP64 roofline */
 int gppd_measure_fp64_peak(gppd_handle h, double *tflops);
 int gppd_pass_times(gppd_handle h, double *ms, int64_t *counts, int reset);
 

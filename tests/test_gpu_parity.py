@@ -449,3 +449,52 @@ def test_full_size_properties(gp, ora, method):
     ref32 = np.empty((100_000, 80), np.float32)
     ref32[:, 0::2], ref32[:, 1::2] = out.real, out.imag
     assert np.array_equal(vout, ref32)
+
+
+@pytest.mark.parametrize("n,window", [(5, None), (63, None), (257, None), (1237, 0.35), (2051, 1.0),
+                                      (2500, None)])
+@pytest.mark.parametrize("keepraw", [False, True])
+def test_ragged_sizes_table(gp, ora, n, window, keepraw):
+    """Row counts / windows that are not multiples of any tile size (4-row MMA
+    k-steps, 32-row warps, 64-row demod tiles, 256-row harmonic tiles, 2048-row
+    statistics segments): objective-level agreement with the oracle for every window."""
+    tab = make_case(gp.synthetic, n, k=31, faint=False)
+    off = gp.synthetic.stefan_centres()
+    tg, hg, to, ho = _table_compare(gp, ora, tab, off, window, keepraw, False)
+    vg, vo = tg["VOLT"], to["VOLT"]
+    assert vg.shape == vo.shape == (n, 144 if keepraw else 80)
+    if keepraw:
+        assert np.array_equal(vg[:, :80], tab["volt"])
+    else:
+        assert np.array_equal(vg[:, 64:], vo[:, 64:])
+    # |out| is invariant under the demodulation whatever trajectory the solver took
+    base = 80 if keepraw else 0
+    ag = np.hypot(vg[:, base:base + 64:2].astype(np.float64), vg[:, base + 1:base + 64:2])
+    ao = np.hypot(vo[:, base:base + 64:2].astype(np.float64), vo[:, base + 1:base + 64:2])
+    assert np.allclose(ag, ao, rtol=3e-7, atol=1e-9)
+    if window is None:
+        # (tables much shorter than a modulation period leave (b, phi) undetermined: the
+        # objective is flat and trajectories fork, so parameters are not compared there)
+        assert set(hg) == set(ho)
+        if n >= 2000:
+            nb = sum(abs(hg[k] - ho[k]) <= REL_FIT * abs(ho[k]) for k in ho if "SIN AMPLITUDE" in k)
+            assert nb >= 16
+    else:
+        assert tg["B"].shape == to["B"].shape == (n, 32)
+        wrows, nwin = gp.table_windows(tab["time_us"], tab["mjd"], window)
+        chg = np.nonzero(np.any(np.diff(tg["B"], axis=0) != 0, axis=1))[0] + 1
+        assert set(chg) <= set(range(wrows, n, wrows))
+
+
+def test_fallback_queue_large_b(gp, ora):
+    """A start vector with |b| > 5 is outside the harmonic evaluator's range: those
+    fits go through the fallback queue to the direct evaluator (info[:, 2] == 1) and
+    agree with a direct-only run bit for bit."""
+    tab = make_case(gp.synthetic, 3000, k=5)
+    off = gp.synthetic.stefan_centres()
+    t, z = gp.synthetic.to_complex(tab, off)
+    r_auto = gp.demodulateall(t, z, init=[7.0, 0.3], raw=True, return_info=True, method="auto")
+    r_dir = gp.demodulateall(t, z, init=[7.0, 0.3], raw=True, return_info=True, method="direct")
+    assert np.all(r_auto[3][:, 2] == 1)          # every fit fell back
+    assert r_auto[1].tobytes() == r_dir[1].tobytes() and r_auto[2].tobytes() == r_dir[2].tobytes()
+    assert np.array_equal(r_auto[0], r_dir[0])
