@@ -43,12 +43,12 @@ METRIC = "diode-samples demodulated/sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gppd", choices=["gppd", "reference"])
     ap.add_argument("--files", type=int, default=100)
     ap.add_argument("--rows", type=int, default=100_000)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=5)
     ap.add_argument("--cpu-files", type=int, default=12, help="files in the CPU-baseline sample")
     ap.add_argument("--window-rows", type=int, default=0,
                     help="fit windows of this many rows instead of whole tables (reference --window); "
@@ -60,50 +60,81 @@ def parse():
 
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed regions, polled through NVML
+    every ~2 ms (nvidia-smi's loop mode is too coarse for a region of tens of ms)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.th, self.stop_flag = index, [], None, False
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                ut = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.rows.append((sm, rs, ut))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        nv = self.nv
         try:
-            self.proc.wait(timeout=2)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            mx = None
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": reasons, "samples": len(sm),
+                "how": "NVML polled every ~2 ms during the resident and end-to-end timed regions"}
+
+
+def pin_to_gpu_numa_node(index):
+    """Run this rank on the CPUs next to its GPU, so that the pinned staging buffers
+    of the end-to-end path are allocated on the GPU's own NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:
+        return False
+
+
+class quiet_stdout:
+    """NCCL prints its version banner on stdout; keep stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 # --------------------------------------------------------------------------
@@ -203,8 +234,12 @@ def main():
         raise SystemExit("bench.py needs a B200: libgppd has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_pinned = pin_to_gpu_numa_node(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()          # creates the communicator (and prints NCCL's banner) now
+            torch.cuda.synchronize()
     h = gp.Handle(local)
     L = _lib.lib()
     F, N, S = args.files, args.rows, max(1, min(args.streams, h.num_slots - 1))
@@ -270,7 +305,6 @@ def main():
         step_resident()
     e1.record(bench_stream)
     barrier()
-    clk = clocks.stop()
     elapsed_ms = e0.elapsed_time(e1)
     passes = h.pass_times(reset=True)
     h.enable_timing(False)
@@ -330,6 +364,7 @@ def main():
                "timing": "host wall clock around the K steps, device-synchronised, max over ranks",
                "matches_resident_path": same}
 
+    clk = clocks.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -394,7 +429,8 @@ def main():
                    "tables_per_gpu": F, "rows_per_table": N, "diodes": DIODES, "e2e_slots": S,
                    "window_rows": W or None,
                    "cache": "inputs (%.1f GB per step) larger than L2" % (F * N * 324 / 1e9),
-                   "sharding": "files -> ranks, no data-path collective"},
+                   "sharding": "files -> ranks, no data-path collective",
+                   "rank_pinned_to_gpu_numa_node": numa_pinned},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -77,7 +77,7 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr int NSLOTS = 4;
+constexpr int NSLOTS = 8;
 constexpr int NPASS = GPPD_NPASS;
 constexpr int MAX_TIMER = 1 << 16;
 

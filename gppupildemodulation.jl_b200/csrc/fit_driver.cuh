@@ -42,9 +42,7 @@ struct FitDriverT {
         if (o.has_xinit) {  // init = [b, phi], reference :362-364
             x1 = o.xinit[0];
             x2 = o.xinit[1];
-            phase = NEWUOA1;
-            nu.start(x1, x2, rhobeg, rhoend, maxfun);
-            advance_solver(0.0, LKL_X);
+            begin_solver(NEWUOA1, x1, x2);
         } else {
             phase = SCAN;
             b = 0.1;  // binit, reference :403
@@ -52,25 +50,21 @@ struct FitDriverT {
         }
     }
 
-    // run the solver until it needs an objective value or finishes
-    __device__ void advance_solver(double f, int next_phase) {
-        if (nu.step(f)) {
-            b = nu.x[1];
-            phi = nu.x[2];
-        } else {
-            status = nu.status;
-            x1 = nu.x[1];
-            x2 = nu.x[2];
-            phase = next_phase;
-            b = x1;
-            phi = x2;
-        }
+    // NEWUOA's first objective call is at its start point: hand that point out
+    // directly; the solver itself is set up when the value comes back (so that the
+    // solver code has a single call site, see step()).
+    __device__ void begin_solver(int solver_phase, double b0, double phi0) {
+        phase = solver_phase;
+        nu.start(b0, phi0, rhobeg, rhoend, maxfun);
+        b = b0;
+        phi = phi0;
     }
 
     // f = chi2 at the (b, phi) handed out by the previous call.
     // Returns true while another evaluation (at this->b, this->phi) is needed.
     __device__ bool step(const FitOptions &o, double f) {
         ++nfev;
+        int next_phase = DONE;
         switch (phase) {
         case SCAN:
             // argmin over the scan; Julia's argmin returns the first NaN
@@ -90,13 +84,14 @@ struct FitDriverT {
             }
             x1 = 0.1;
             x2 = o.phi8[kbest];
-            phase = NEWUOA1;
-            nu.start(x1, x2, rhobeg, rhoend, maxfun);
-            advance_solver(0.0, LKL_X);
+            begin_solver(NEWUOA1, x1, x2);
             return true;
         case NEWUOA1:
-            advance_solver(f, LKL_X);
-            return true;
+            next_phase = LKL_X;
+            break;
+        case NEWUOA2:
+            next_phase = FINAL;
+            break;
         case LKL_X:
             lklval = f;
             phipi = x2 + (x2 < 0 ? PI_F64 : -PI_F64);
@@ -107,17 +102,12 @@ struct FitDriverT {
         case LKL_FLIP:
             if (lklval > f) {  // "bad minima", strict >
                 second = 1;
-                phase = NEWUOA2;
-                nu.start(x1, phipi, rhobeg, rhoend, maxfun);
-                advance_solver(0.0, FINAL);
+                begin_solver(NEWUOA2, x1, phipi);
                 return true;
             }
             phase = FINAL;
             b = x1;
             phi = x2;
-            return true;
-        case NEWUOA2:
-            advance_solver(f, FINAL);
             return true;
         case FINAL:
             chi2 = f;
@@ -126,6 +116,25 @@ struct FitDriverT {
         default:
             return false;
         }
+        // ---- the one call site of the solver (phase NEWUOA1 / NEWUOA2) ----
+        // A solver that has not run yet first sets itself up and asks for its start
+        // point, which is the point f was just evaluated at: feed f straight back.
+        bool more = true;
+        const int calls = nu.phase == 0 ? 2 : 1;
+#pragma unroll 1
+        for (int c = 0; c < calls; ++c) more = nu.step(f);
+        if (more) {
+            b = nu.x[1];
+            phi = nu.x[2];
+        } else {
+            status = nu.status;
+            x1 = nu.x[1];
+            x2 = nu.x[2];
+            phase = next_phase;
+            b = x1;
+            phi = x2;
+        }
+        return true;
     }
 };
 

@@ -59,6 +59,15 @@ __host__ __device__ inline void nu_sincos(double x, double *sn, double *cs) {
 
 enum { NU_SUCCESS = 0, NU_ROUNDING_ERRORS = -2, NU_TOO_MANY_EVALUATIONS = -3 };
 
+// Loops over the NPT = 5 points / NDIM = 7 rows are kept rolled on the device: fully
+// unrolled, the solver is ~140 KB of code and the fit kernels stall on instruction
+// fetch (the arithmetic and its order are the same either way).
+#ifdef __CUDA_ARCH__
+#define NU_ROLLED _Pragma("unroll 1")
+#else
+#define NU_ROLLED
+#endif
+
 // The three angle searches (TRSAPP, BIGLAG, BIGDEN) always probe the same 49
 // angles 2 pi i / 50: their sines and cosines are tabulated once with nu_sincos
 // (so the tabulated values are the very bits the oracle computes in its loops).
@@ -126,7 +135,7 @@ struct Newuoa2T {
     // HD = (second derivative matrix of the model) * D
     __host__ __device__ void hess_mul(const double *dd_, double *hd) const {
         for (int i = 1; i <= N; ++i) hd[i] = 0.0;
-        for (int k = 1; k <= NPT; ++k) {
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) {
             double temp = 0.0;
             for (int j = 1; j <= N; ++j) temp += XPT(k, j) * dd_[j];
             temp *= pq[k];
@@ -387,11 +396,11 @@ struct Newuoa2T {
         double cf1, cf2, cf3, cf4, cf5, taubeg, taumax, angle, cth, sth;
         double tempa = 0, tempb = 0, step;
 
-        for (int k = 1; k <= NPT; ++k) hcol[k] = zero;
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) hcol[k] = zero;
         for (int j = 1; j <= NPTM; ++j) {
             temp = ZMAT(knew, j);
             if (j < idz) temp = -temp;
-            for (int k = 1; k <= NPT; ++k) hcol[k] += temp * ZMAT(k, j);
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) hcol[k] += temp * ZMAT(k, j);
         }
         alpha = hcol[knew];
         dd = zero;
@@ -401,7 +410,7 @@ struct Newuoa2T {
             gd[i] = zero;
             dd += d[i] * d[i];
         }
-        for (int k = 1; k <= NPT; ++k) {
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) {
             temp = zero;
             sum = zero;
             for (int j = 1; j <= N; ++j) {
@@ -451,7 +460,7 @@ struct Newuoa2T {
                 s[i] = (dd * s[i] - sp * d[i]) / denom;
                 ww[i] = zero;
             }
-            for (int k = 1; k <= NPT; ++k) {
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                 sum = zero;
                 for (int j = 1; j <= N; ++j) sum += XPT(k, j) * s[j];
                 sum = hcol[k] * sum;
@@ -504,11 +513,11 @@ struct Newuoa2T {
         double denold, denmax, angle, step, tau;
         int ksav, iterc, isave, nw;
 
-        for (int k = 1; k <= NPT; ++k) w[N + k] = zero;
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) w[N + k] = zero;
         for (int j = 1; j <= NPTM; ++j) {
             temp = ZMAT(knew, j);
             if (j < idz) temp = -temp;
-            for (int k = 1; k <= NPT; ++k) w[N + k] += temp * ZMAT(k, j);
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) w[N + k] += temp * ZMAT(k, j);
         }
         alph = w[N + knew];
         dd = ds = ss = xosq = zero;
@@ -522,7 +531,7 @@ struct Newuoa2T {
         if (ds * ds > 0.99 * dd * ss) {
             ksav = knew;
             dtest = ds * ds / ss;
-            for (int k = 1; k <= NPT; ++k) {
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                 if (k != kopt) {
                     dstemp = zero;
                     sstemp = zero;
@@ -562,7 +571,7 @@ struct Newuoa2T {
             den[4] = tempa - tempb;
             den[5] = xoptd * xopts;
             for (int i = 6; i <= 9; ++i) den[i] = zero;
-            for (int k = 1; k <= NPT; ++k) {
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                 tempa = tempb = tempc = zero;
                 for (int i = 1; i <= N; ++i) {
                     tempa += XPT(k, i) * d[i];
@@ -583,18 +592,18 @@ struct Newuoa2T {
                 WVEC(ip, 4) = zero;
                 WVEC(ip, 5) = zero;
             }
-            for (int jc = 1; jc <= 5; ++jc) {
+            NU_ROLLED for (int jc = 1; jc <= 5; ++jc) {
                 nw = NPT;
                 if (jc == 2 || jc == 3) nw = NDIM;
-                for (int k = 1; k <= NPT; ++k) PROD(k, jc) = zero;
+                NU_ROLLED for (int k = 1; k <= NPT; ++k) PROD(k, jc) = zero;
                 for (int j = 1; j <= NPTM; ++j) {
                     sum = zero;
-                    for (int k = 1; k <= NPT; ++k) sum += ZMAT(k, j) * WVEC(k, jc);
+                    NU_ROLLED for (int k = 1; k <= NPT; ++k) sum += ZMAT(k, j) * WVEC(k, jc);
                     if (j < idz) sum = -sum;
-                    for (int k = 1; k <= NPT; ++k) PROD(k, jc) += sum * ZMAT(k, j);
+                    NU_ROLLED for (int k = 1; k <= NPT; ++k) PROD(k, jc) += sum * ZMAT(k, j);
                 }
                 if (nw == NDIM) {
-                    for (int k = 1; k <= NPT; ++k) {
+                    NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                         sum = zero;
                         for (int j = 1; j <= N; ++j) sum += BMAT(k, j) * WVEC(NPT + j, jc);
                         PROD(k, jc) += sum;
@@ -602,11 +611,11 @@ struct Newuoa2T {
                 }
                 for (int j = 1; j <= N; ++j) {
                     sum = zero;
-                    for (int i = 1; i <= nw; ++i) sum += BMAT(i, j) * WVEC(i, jc);
+                    NU_ROLLED for (int i = 1; i <= nw; ++i) sum += BMAT(i, j) * WVEC(i, jc);
                     PROD(NPT + j, jc) = sum;
                 }
             }
-            for (int k = 1; k <= NDIM; ++k) {
+            NU_ROLLED for (int k = 1; k <= NDIM; ++k) {
                 sum = zero;
                 for (int i = 1; i <= 5; ++i) {
                     par[i] = half * PROD(k, i) * WVEC(k, i);
@@ -700,7 +709,7 @@ struct Newuoa2T {
                 beta += den[j] * par[j];
                 denmax += denex[j] * par[j];
             }
-            for (int k = 1; k <= NDIM; ++k) {
+            NU_ROLLED for (int k = 1; k <= NDIM; ++k) {
                 vlag[k] = zero;
                 for (int j = 1; j <= 5; ++j) vlag[k] += PROD(k, j) * par[j];
             }
@@ -723,7 +732,7 @@ struct Newuoa2T {
                 temp = tempa * xopt[i] + tempb * d[i] - vlag[NPT + i];
                 s[i] = tau * BMAT(knew, i) + alph * temp;
             }
-            for (int k = 1; k <= NPT; ++k) {
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                 sum = zero;
                 for (int j = 1; j <= N; ++j) sum += XPT(k, j) * w[j];
                 temp = (tau * w[N + k] - alph * vlag[k]) * sum;
@@ -739,7 +748,7 @@ struct Newuoa2T {
             if (ssden >= 1.0e-8 * dd * ss) continue;
             break;
         }
-        for (int k = 1; k <= NDIM; ++k) {
+        NU_ROLLED for (int k = 1; k <= NDIM; ++k) {
             w[k] = zero;
             for (int j = 1; j <= 5; ++j) w[k] += WVEC(k, j) * par[j];
         }
@@ -760,7 +769,7 @@ struct Newuoa2T {
                 temp = sqrt(ZMAT(knew, jl) * ZMAT(knew, jl) + ZMAT(knew, j) * ZMAT(knew, j));
                 tempa = ZMAT(knew, jl) / temp;
                 tempb = ZMAT(knew, j) / temp;
-                for (int i = 1; i <= NPT; ++i) {
+                NU_ROLLED for (int i = 1; i <= NPT; ++i) {
                     temp = tempa * ZMAT(i, jl) + tempb * ZMAT(i, j);
                     ZMAT(i, j) = tempa * ZMAT(i, j) - tempb * ZMAT(i, jl);
                     ZMAT(i, jl) = temp;
@@ -771,7 +780,7 @@ struct Newuoa2T {
         tempa = ZMAT(knew, 1);
         if (idz >= 2) tempa = -tempa;
         if (jl > 1) tempb = ZMAT(knew, jl);
-        for (int i = 1; i <= NPT; ++i) {
+        NU_ROLLED for (int i = 1; i <= NPT; ++i) {
             w[i] = tempa * ZMAT(i, 1);
             if (jl > 1) w[i] += tempb * ZMAT(i, jl);
         }
@@ -785,7 +794,7 @@ struct Newuoa2T {
             temp = sqrt(fabs(denom));
             tempb = tempa / temp;
             tempa = tau / temp;
-            for (int i = 1; i <= NPT; ++i) ZMAT(i, 1) = tempa * ZMAT(i, 1) - tempb * vlag[i];
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) ZMAT(i, 1) = tempa * ZMAT(i, 1) - tempb * vlag[i];
             // Powell's published tests use TEMP (>= 0) here, kept as published
             if (idz == 1 && temp < zero) idz = 2;
             if (idz >= 2 && temp >= zero) iflag = 1;
@@ -799,7 +808,7 @@ struct Newuoa2T {
             temp = ZMAT(knew, ja);
             scala = one / sqrt(fabs(beta) * temp * temp + tausq);
             scalb = scala * sqrt(fabs(denom));
-            for (int i = 1; i <= NPT; ++i) {
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) {
                 ZMAT(i, ja) = scala * (tau * ZMAT(i, ja) - temp * vlag[i]);
                 ZMAT(i, jb) = scalb * (ZMAT(i, jb) - tempa * w[i] - tempb * vlag[i]);
             }
@@ -810,7 +819,7 @@ struct Newuoa2T {
         }
         if (iflag == 1) {
             idz = idz - 1;
-            for (int i = 1; i <= NPT; ++i) {
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) {
                 temp = ZMAT(i, 1);
                 ZMAT(i, 1) = ZMAT(i, idz);
                 ZMAT(i, idz) = temp;
@@ -821,7 +830,7 @@ struct Newuoa2T {
             w[jp] = BMAT(knew, j);
             tempa = (alph * vlag[jp] - tau * w[jp]) / denom;
             tempb = (-beta * w[jp] - tau * vlag[jp]) / denom;
-            for (int i = 1; i <= jp; ++i) {
+            NU_ROLLED for (int i = 1; i <= jp; ++i) {
                 BMAT(i, j) = BMAT(i, j) + tempa * vlag[i] + tempb * w[i];
                 if (i > NPT) BMAT(jp, i - NPT) = BMAT(i, j);
             }
@@ -850,7 +859,7 @@ struct Newuoa2T {
         for (int i = 0; i < NDIM * N; ++i) bmat_[i] = zero;
         for (int i = 0; i < NPT * NPTM; ++i) zmat_[i] = zero;
         for (ih = 1; ih <= NH; ++ih) hq[ih] = zero;
-        for (int k = 1; k <= NPT; ++k) pq[k] = zero;
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) pq[k] = zero;
         for (int k = 0; k <= NPT; ++k) fval[k] = zero;
         for (int k = 0; k <= N; ++k) gq[k] = zero;
         rhosq = rhobeg * rhobeg;
@@ -968,7 +977,7 @@ struct Newuoa2T {
     L120:
         if (dsq <= 1.0e-3 * xoptsq) {
             tempq = 0.25 * xoptsq;
-            for (int k = 1; k <= NPT; ++k) {
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                 sum = zero;
                 for (int i = 1; i <= N; ++i) sum += XPT(k, i) * xopt[i];
                 temp = pq[k] * sum;
@@ -984,18 +993,18 @@ struct Newuoa2T {
                         BMAT(ip, j) = BMAT(ip, j) + vlag[i] * w[j] + w[i] * vlag[j];
                 }
             }
-            for (int k = 1; k <= NPTM; ++k) {
+            NU_ROLLED for (int k = 1; k <= NPTM; ++k) {
                 sumz = zero;
-                for (int i = 1; i <= NPT; ++i) {
+                NU_ROLLED for (int i = 1; i <= NPT; ++i) {
                     sumz += ZMAT(i, k);
                     w[i] = w[NPT + i] * ZMAT(i, k);
                 }
                 for (int j = 1; j <= N; ++j) {
                     sum = tempq * sumz * xopt[j];
-                    for (int i = 1; i <= NPT; ++i) sum += w[i] * XPT(i, j);
+                    NU_ROLLED for (int i = 1; i <= NPT; ++i) sum += w[i] * XPT(i, j);
                     vlag[j] = sum;
                     if (k < idz) sum = -sum;
-                    for (int i = 1; i <= NPT; ++i) BMAT(i, j) = BMAT(i, j) + sum * ZMAT(i, k);
+                    NU_ROLLED for (int i = 1; i <= NPT; ++i) BMAT(i, j) = BMAT(i, j) + sum * ZMAT(i, k);
                 }
                 for (int i = 1; i <= N; ++i) {
                     ip = i + NPT;
@@ -1007,7 +1016,7 @@ struct Newuoa2T {
             ih = 0;
             for (int j = 1; j <= N; ++j) {
                 w[j] = zero;
-                for (int k = 1; k <= NPT; ++k) {
+                NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                     w[j] += pq[k] * XPT(k, j);
                     XPT(k, j) -= half * xopt[j];
                 }
@@ -1027,7 +1036,7 @@ struct Newuoa2T {
         }
         if (knew > 0) biglag(dstep);
 
-        for (int k = 1; k <= NPT; ++k) {
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) {
             suma = zero;
             sumb = zero;
             sum = zero;
@@ -1040,22 +1049,22 @@ struct Newuoa2T {
             vlag[k] = sum;
         }
         beta = zero;
-        for (int k = 1; k <= NPTM; ++k) {
+        NU_ROLLED for (int k = 1; k <= NPTM; ++k) {
             sum = zero;
-            for (int i = 1; i <= NPT; ++i) sum += ZMAT(i, k) * w[i];
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) sum += ZMAT(i, k) * w[i];
             if (k < idz) {
                 beta += sum * sum;
                 sum = -sum;
             } else {
                 beta -= sum * sum;
             }
-            for (int i = 1; i <= NPT; ++i) vlag[i] += sum * ZMAT(i, k);
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) vlag[i] += sum * ZMAT(i, k);
         }
         bsum = zero;
         dx = zero;
         for (int j = 1; j <= N; ++j) {
             sum = zero;
-            for (int i = 1; i <= NPT; ++i) sum += w[i] * BMAT(i, j);
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) sum += w[i] * BMAT(i, j);
             bsum += sum * d[j];
             int jp = NPT + j;
             for (int k = 1; k <= N; ++k) sum += BMAT(jp, k) * d[k];
@@ -1098,7 +1107,7 @@ struct Newuoa2T {
                 vquad += temp * hq[ih];
             }
         }
-        for (int k = 1; k <= NPT; ++k) vquad += pq[k] * w[k];
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) vquad += pq[k] * w[k];
         diff = fcur - fopt - vquad;
         diffc = diffb;
         diffb = diffa;
@@ -1136,7 +1145,7 @@ struct Newuoa2T {
             ktemp = kopt;
             detrat = one;
         }
-        for (int k = 1; k <= NPT; ++k) {
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) {
             hdiag = zero;
             for (int j = 1; j <= NPTM; ++j) {
                 temp = one;
@@ -1174,7 +1183,7 @@ struct Newuoa2T {
         for (int j = 1; j <= NPTM; ++j) {
             temp = diff * ZMAT(knew, j);
             if (j < idz) temp = -temp;
-            for (int k = 1; k <= NPT; ++k) pq[k] += temp * ZMAT(k, j);
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) pq[k] += temp * ZMAT(k, j);
         }
         gqsq = zero;
         for (int i = 1; i <= N; ++i) {
@@ -1186,11 +1195,11 @@ struct Newuoa2T {
             if (fabs(ratio) > 1.0e-2) {
                 itest = 0;
             } else {
-                for (int k = 1; k <= NPT; ++k) vlag[k] = fval[k] - fval[kopt];
+                NU_ROLLED for (int k = 1; k <= NPT; ++k) vlag[k] = fval[k] - fval[kopt];
                 gisq = zero;
                 for (int i = 1; i <= N; ++i) {
                     sum = zero;
-                    for (int k = 1; k <= NPT; ++k) sum += BMAT(k, i) * vlag[k];
+                    NU_ROLLED for (int k = 1; k <= NPT; ++k) sum += BMAT(k, i) * vlag[k];
                     gisq += sum * sum;
                     w[i] = sum;
                 }
@@ -1201,10 +1210,10 @@ struct Newuoa2T {
                     for (ih = 1; ih <= NH; ++ih) hq[ih] = zero;
                     for (int j = 1; j <= NPTM; ++j) {
                         w[j] = zero;
-                        for (int k = 1; k <= NPT; ++k) w[j] += vlag[k] * ZMAT(k, j);
+                        NU_ROLLED for (int k = 1; k <= NPT; ++k) w[j] += vlag[k] * ZMAT(k, j);
                         if (j < idz) w[j] = -w[j];
                     }
-                    for (int k = 1; k <= NPT; ++k) {
+                    NU_ROLLED for (int k = 1; k <= NPT; ++k) {
                         pq[k] = zero;
                         for (int j = 1; j <= NPTM; ++j) pq[k] += ZMAT(k, j) * w[j];
                     }
@@ -1218,7 +1227,7 @@ struct Newuoa2T {
         knew = 0;
     L460:
         distsq = 4.0 * delta * delta;
-        for (int k = 1; k <= NPT; ++k) {
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) {
             sum = zero;
             for (int j = 1; j <= N; ++j) {
                 double t = XPT(k, j) - xopt[j];
