@@ -395,8 +395,15 @@ def main():
             "peak_source": "FP64 micro-benchmark in this run (better of DFMA and mma.sync.m8n8k4.f64)",
             "objective_calls_per_fit": nfev_mean}
     fp64["frac"] = fp64["achieved_tflops"] / fp64_peak if (fp64_peak and fp64["achieved_tflops"]) else None
+    traffic = None   # DRAM bytes per launch of the dominant pass, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tj["workload"] == {"tables": F, "rows": N} and not W:
+            traffic = tj["bytes_per_launch"].get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_ms, "launches_timed": dom_n,
