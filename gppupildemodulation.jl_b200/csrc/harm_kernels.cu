@@ -58,10 +58,10 @@
 
 namespace gppd {
 
-constexpr int TR = 256;                       // rows per tile
-constexpr int HARM_SEG_TILES = 48;            // tiles per segment (12288 rows)
-constexpr int NCONS = 8;                      // consumer warps, 32 rows of a tile each
-constexpr int NPROD = 8;                      // producer warps
+constexpr int TR = 128;                       // rows per tile
+constexpr int HARM_SEG_TILES = 96;            // tiles per segment (12288 rows)
+constexpr int NCONS = 4;                      // consumer warps, 32 rows of a tile each
+constexpr int NPROD = 4;                      // producer warps
 constexpr int HARM_THREADS = (NCONS + NPROD) * 32;
 constexpr int RAW_STAGES = 3;
 constexpr int TILE_BUFS = 3;                   // compute tiles in flight
@@ -141,7 +141,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 // sum w and sum w |p|^2 (|FCphasor| = 1) follow from the per-state row counts of the
 // segment: sum_s n_s w_s and sum_s n_s w_s m_s^2.
 template <int KIND, bool OFFS>  // KIND 0: z = w conj(p) (d - mu);  1: y = w p
-__global__ void __launch_bounds__(HARM_THREADS, 1)
+__global__ void __launch_bounds__(HARM_THREADS, 2)
 k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, int SP,
                   const double *spart1, const double *spart2, double *partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -441,8 +441,8 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     }
     __syncthreads();
     // C[m][n], m = 2(k-1) + {cos, sin}, n = 2d + {x, y}  ->  (A, B, C, D) of harmonic k, diode d
-    if (threadIdx.x < 48 * 8) {
-        const int m = threadIdx.x >> 3, n = threadIdx.x & 7;
+    for (int idx = threadIdx.x; idx < 48 * 8; idx += HARM_THREADS) {
+        const int m = idx >> 3, n = idx & 7;
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < NCONS; ++w) s += s_cpart[(w * 48 + m) * 8 + n];
