@@ -31,18 +31,21 @@
 //     trig((k + 4) t) = 2 cos(4 t) trig(k t) - trig((k - 4) t)      (one FMA each)
 // from the row's (cos, sin)(t .. 4t), which the producers tabulate.
 //
-// Kernel structure (k_harm_accumulate): one block of 16 warps per (job, group,
-// segment), persistent over the segment's row tiles of TR rows, one block per SM.
-//   * Eight PRODUCER warps (two per SM sub-partition, one row per thread and tile:
-//     their long dependent chains need the warps to hide latency) stream the raw
-//     table bytes of the next-but-one tile into a 3-stage shared-memory ring with
-//     cp.async (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's
-//     basis, the state byte) -- no register dependency, so the global-memory latency
-//     is off the critical path -- and turn the previous stage into a compute tile:
-//     (cos, sin)(k theta), k = 1..4, and the four diodes' z (or y) values.
-//   * Eight CONSUMER warps (two per sub-partition) each take 32 rows of the tile:
-//     8 k-steps of 4 rows, per k-step 5 recurrence FMAs and 6 DMMAs into the 12
-//     accumulator registers that hold the warp's 48 x 8 partial C.
+// Kernel structure (k_harm_accumulate): one block of 8 warps per (job, group,
+// segment), persistent over the segment's row tiles of TR = 128 rows; TWO blocks are
+// resident per SM, so that one block's pipeline fill and final reduction overlap the
+// other's steady state (measured: one 16-warp block per SM 3.5 ms, two 8-warp blocks
+// 3.1 ms, four 4-warp blocks 3.3 ms).
+//   * Four PRODUCER warps (one row per thread and tile) stream the raw table bytes
+//     of the next-but-one tile into a 3-stage shared-memory ring with cp.async
+//     (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's basis, the
+//     state byte) -- no register dependency, so the global-memory latency is off the
+//     critical path -- and turn the previous stage into a compute tile:
+//     (cos, sin)(theta) and the four diodes' z (or y) values.
+//   * Four CONSUMER warps each take 32 rows of the tile: they first extend their
+//     rows' (cos, sin) to k = 2..4, then run 8 k-steps of 4 rows, per k-step 5
+//     recurrence FMAs and 6 DMMAs into the 12 accumulator registers that hold the
+//     warp's 48 x 8 partial C.
 // Compute tiles are triple buffered and handed over with mbarriers (full / empty
 // per buffer), so consumer warps never wait for each other, only for data.
 // A segment is a FIXED run of HARM_SEG_TILES tiles of the job (independent of
