@@ -74,6 +74,10 @@ def lib():
            C.c_double, C.POINTER(Options), _fp, _dp, _dp, _i32p, _i8p]
     L.gppd_process_table_f32.argtypes = [H] + tab
     L.gppd_submit_table_f32.argtypes = [H, C.c_int] + tab
+    L.gppd_submit_fits_rows.argtypes = [
+        H, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, _dp,
+        _dp, C.c_int64, _dp, C.c_int64, C.c_double, C.POINTER(Options), C.c_void_p, _dp, _dp,
+        _i32p, _i8p]
     L.gppd_wait.argtypes = [H, C.c_int]
     L.gppd_num_slots.argtypes = [H]
     L.gppd_process_table_f32_dev.argtypes = [
@@ -92,6 +96,7 @@ def lib():
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
+                 "gppd_submit_fits_rows",
                  "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",
                  "gppd_process_tables_f32_dev", "gppd_enable_timing",
                  "gppd_pass_times", "gppd_measure_fp64_peak"):

@@ -255,6 +255,51 @@ def _rem2pi_nearest(x):
     return float(np.remainder(x + np.pi, 2 * np.pi) - np.pi)
 
 
+def demodulation_keys(params, fitoffsets: bool) -> dict:
+    """The whole-file header keywords of src/GPPupilDemodulation.jl:174-189 from the
+    (32, 6) parameter array (c.re, c.im, a.re, a.im, b, phi)."""
+    hdr = {}
+    for s in (Side.FT, Side.SC):
+        for j in range(1, 5):
+            for d in (Diode.D1, Diode.D2, Diode.D3, Diode.D4):
+                p = params[idx(s, j, d) - 1]
+                b, phi = p[4], p[5]
+                if b < 0:
+                    b, phi = -b, _rem2pi_nearest(phi + np.pi)
+                a = complex(p[2], p[3])
+                suffix = f"{s.name} T{j} {d.name}"
+                if fitoffsets:
+                    hdr[f"DEMODULATION CENTER X0 {suffix}"] = float(p[0])
+                    hdr[f"DEMODULATION CENTER Y0 {suffix}"] = float(p[1])
+                hdr[f"DEMODULATION AMPLITUDE ABS {suffix}"] = abs(a)
+                hdr[f"DEMODULATION AMPLITUDE ARG {suffix}"] = float(np.angle(a))
+                hdr[f"DEMODULATION SIN AMPLITUDE {suffix}"] = float(b)
+                hdr[f"DEMODULATION SIN PHASE {suffix}"] = float(phi)
+    return hdr
+
+
+def window_columns(params, n: int, wrows: int, nwin: int, fitoffsets: bool) -> dict:
+    """The per-row parameter tables of window mode (src/GPPupilDemodulation.jl:209-247):
+    each window's values broadcast over its rows, Float32 (n, 32)."""
+    P = np.asarray(params).reshape(nwin, 32, 6)
+    b, phi = P[:, :, 4].copy(), P[:, :, 5].copy()
+    neg = b < 0
+    phi[neg] = np.remainder(phi[neg] + np.pi + np.pi, 2 * np.pi) - np.pi
+    b[neg] = -b[neg]
+    a = P[:, :, 2] + 1j * P[:, :, 3]
+    rows = np.minimum(np.arange(n) // wrows, nwin - 1)
+
+    def col(x):
+        return x[rows].astype(np.float32)
+
+    out = {}
+    if fitoffsets:
+        out["X0"], out["Y0"] = col(P[:, :, 0]), col(P[:, :, 1])
+    out["ABSA"], out["ARGA"] = col(np.abs(a)), col(np.angle(a))
+    out["B"], out["PHI"] = col(b), col(phi)
+    return out
+
+
 def processmetrology(table, mjd, window=None, faintparam: FaintStates | None = None,
                      keepraw=False, verb=False, onlyhigh=False, offsets=True, handle=None,
                      method="auto"):
@@ -276,39 +321,11 @@ def processmetrology(table, mjd, window=None, faintparam: FaintStates | None = N
         table["TIME"], table["VOLT"], mjd, offsets=off, faintparam=faintparam, window=window,
         keepraw=keepraw, onlyhigh=onlyhigh, handle=handle, method=method)
     n = vout.shape[0]
-    names = [(s, j, d) for s in (Side.FT, Side.SC) for j in range(1, 5) for d in Diode if d != Diode.FC]
     if window is None:
-        for s, j, d in names:   # :174-189
-            p = params[idx(s, j, d) - 1]
-            b, phi = p[4], p[5]
-            if b < 0:
-                b, phi = -b, _rem2pi_nearest(phi + np.pi)
-            a = complex(p[2], p[3])
-            suffix = f"{s.name} T{j} {d.name}"
-            if fitoffsets:
-                hdr[f"DEMODULATION CENTER X0 {suffix}"] = float(p[0])
-                hdr[f"DEMODULATION CENTER Y0 {suffix}"] = float(p[1])
-            hdr[f"DEMODULATION AMPLITUDE ABS {suffix}"] = abs(a)
-            hdr[f"DEMODULATION AMPLITUDE ARG {suffix}"] = float(np.angle(a))
-            hdr[f"DEMODULATION SIN AMPLITUDE {suffix}"] = float(b)
-            hdr[f"DEMODULATION SIN PHASE {suffix}"] = float(phi)
+        hdr.update(demodulation_keys(params, fitoffsets))
     else:
         wrows, nwin = table_windows(table["TIME"], mjd, window)
-        P = params.reshape(nwin, 32, 6)
-        b, phi = P[:, :, 4].copy(), P[:, :, 5].copy()
-        neg = b < 0
-        phi[neg] = np.remainder(phi[neg] + np.pi + np.pi, 2 * np.pi) - np.pi
-        b[neg] = -b[neg]
-        a = P[:, :, 2] + 1j * P[:, :, 3]
-        rows = np.minimum(np.arange(n) // wrows, nwin - 1)
-
-        def col(x):  # broadcast the window's value over its rows, :209-224
-            return x[rows].astype(np.float32)
-
-        if fitoffsets:
-            out["X0"], out["Y0"] = col(P[:, :, 0]), col(P[:, :, 1])
-        out["ABSA"], out["ARGA"] = col(np.abs(a)), col(np.angle(a))
-        out["B"], out["PHI"] = col(b), col(phi)
+        out.update(window_columns(params, n, wrows, nwin, fitoffsets))
         if state is not None:
             out["STATE"] = state.astype(np.int8)   # :248
     hdr["PROCSOFT"] = "GPPupilDemodulation.jl"     # :252

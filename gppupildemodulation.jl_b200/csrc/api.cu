@@ -91,7 +91,7 @@ struct PassTimer {
 struct Slot {
     cudaStream_t stream = nullptr;
     // staging of caller data (host-buffer entry points)
-    DevBuf time, volt, volt_out, t, data, out, state_in, offsets;
+    DevBuf time, volt, volt_out, t, data, out, state_in, offsets, rows, rows_out;
     DevBuf params, chi2, info, trace, state_out;
     // batch scratch
     DevBuf state, basis, z, y, thkeys, nvalid, jobs, results;
@@ -509,7 +509,7 @@ int gppd_destroy(gppd_handle h) {
         }
         if (s.fork) cudaEventDestroy(s.fork);
         if (s.join) cudaEventDestroy(s.join);
-        DevBuf *bufs[] = {&s.time, &s.volt, &s.volt_out, &s.t, &s.data, &s.out, &s.state_in,
+        DevBuf *bufs[] = {&s.rows, &s.rows_out, &s.time, &s.volt, &s.volt_out, &s.t, &s.data, &s.out, &s.state_in,
                           &s.offsets, &s.params, &s.chi2, &s.info, &s.trace, &s.state_out,
                           &s.state, &s.basis, &s.z, &s.y, &s.thkeys, &s.nvalid, &s.jobs,
                           &s.results, &s.spart1, &s.spart2, &s.partZ, &s.partY, &s.htab,
@@ -778,6 +778,85 @@ int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n, const int32_t *tim
     a.d_state_out = s.state_out.as<int8_t>();
     if ((rc = run_batch(h, s, st, tabs, &o, nullptr, false))) return rc;
     CK(cudaMemcpyAsync(volt_out, s.volt_out.p, obytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(params, s.params.p, sizeof(double) * 6 * nfits, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(chi2, s.chi2.p, sizeof(double) * nfits, cudaMemcpyDeviceToHost, st));
+    if (info)
+        CK(cudaMemcpyAsync(info, s.info.p, sizeof(int) * GPPD_INFO_STRIDE * nfits,
+                           cudaMemcpyDeviceToHost, st));
+    if (state_out && faint)
+        CK(cudaMemcpyAsync(state_out, s.state_out.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    return GPPD_OK;
+}
+
+int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, int64_t row_bytes,
+                          int64_t time_off, int64_t volt_off, double mjd, const double *offsets,
+                          const double *timer1, int64_t n1, const double *timer2, int64_t n2,
+                          double window_s, const gppd_options *opt, void *rows_out, double *params,
+                          double *chi2, int32_t *info, int8_t *state_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS || !rows || !rows_out || !params || !chi2 || n < 2 ||
+        time_off < 0 || volt_off < 0 || time_off + 4 > row_bytes || volt_off + 320 > row_bytes ||
+        (time_off + 4 > volt_off && time_off < volt_off + 320)) {
+        g_last_error = "submit_fits_rows: bad slot, null buffer, n < 2 or fields outside the record";
+        return GPPD_ERR_ARG;
+    }
+    gppd_options o;
+    memset(&o, 0, sizeof o);
+    if (opt) o = *opt;
+    if (!offsets) o.flags |= GPPD_FITOFFSETS;
+    else o.flags &= ~GPPD_FITOFFSETS;
+    o.flags &= ~GPPD_BIG_ENDIAN;    // the unpack pass delivers little-endian arrays
+    const int out_floats = (o.flags & GPPD_KEEPRAW) ? 144 : 80;
+    const int64_t row_bytes_out = row_bytes + 4 * (out_floats - 80);
+    // TIME of the first two records (host side), for the --window arithmetic (:192)
+    int32_t t01[2];
+    for (int k = 0; k < 2; ++k) {
+        const unsigned char *p = reinterpret_cast<const unsigned char *>(rows) + k * row_bytes + time_off;
+        t01[k] = (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]);
+    }
+    int64_t wrows = n, nwin = 1;
+    if ((rc = gppd_table_windows(2, t01, mjd, window_s, &wrows, &nwin))) return rc;
+    if (!(window_s > 0.0)) wrows = n;
+    nwin = gppd_num_windows(n, wrows);
+    size_t nfits = (size_t)nwin * NDIODE;
+    Slot &s = h->slots[slot];
+    cudaStream_t st = s.stream;
+    CK(cudaStreamSynchronize(st));  // slot reuse: previous table of this slot must be done
+    if ((rc = s.rows.ensure((size_t)n * (size_t)row_bytes))) return rc;
+    if ((rc = s.rows_out.ensure((size_t)n * (size_t)row_bytes_out))) return rc;
+    if ((rc = s.time.ensure(sizeof(int32_t) * (size_t)n))) return rc;
+    if ((rc = s.volt.ensure(sizeof(float) * 80 * (size_t)n))) return rc;
+    if ((rc = s.volt_out.ensure(sizeof(float) * out_floats * (size_t)n))) return rc;
+    if ((rc = s.params.ensure(sizeof(double) * 6 * nfits))) return rc;
+    if ((rc = s.chi2.ensure(sizeof(double) * nfits))) return rc;
+    if ((rc = s.info.ensure(sizeof(int) * GPPD_INFO_STRIDE * nfits))) return rc;
+    if ((rc = s.state_out.ensure((size_t)n))) return rc;
+    if ((rc = s.offsets.ensure(sizeof(double) * 80))) return rc;
+    CK(cudaMemcpyAsync(s.rows.p, rows, (size_t)n * (size_t)row_bytes, cudaMemcpyHostToDevice, st));
+    if (offsets)
+        CK(cudaMemcpyAsync(s.offsets.p, offsets, sizeof(double) * 80, cudaMemcpyHostToDevice, st));
+    Launcher L{st, &h->launches};
+    launch_unpack_rows(L, s.rows.p, n, row_bytes, time_off, volt_off, s.time.as<int32_t>(), s.volt.as<float>());
+    std::vector<TableArgs> tabs(1);
+    TableArgs &a = tabs[0];
+    table_views(n, mjd, s.time.as<int32_t>(), s.volt.as<float>(),
+                offsets ? s.offsets.as<double>() : nullptr, s.volt_out.as<float>(), o.flags, a);
+    a.wrows = wrows;
+    const bool faint = timer1 && timer2 && n1 > 0 && n2 > 0;
+    a.timer1 = timer1;
+    a.timer2 = timer2;
+    a.n1 = faint ? n1 : 0;
+    a.n2 = faint ? n2 : 0;
+    a.d_params = s.params.as<double>();
+    a.d_chi2 = s.chi2.as<double>();
+    a.d_info = s.info.as<int>();
+    a.d_state_out = s.state_out.as<int8_t>();
+    if ((rc = run_batch(h, s, st, tabs, &o, nullptr, false))) return rc;
+    launch_pack_rows(L, s.rows.p, n, row_bytes, volt_off, s.volt_out.as<float>(), out_floats, s.rows_out.p,
+                     row_bytes_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rows_out, s.rows_out.p, (size_t)n * (size_t)row_bytes_out, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(params, s.params.p, sizeof(double) * 6 * nfits, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(chi2, s.chi2.p, sizeof(double) * nfits, cudaMemcpyDeviceToHost, st));
     if (info)

@@ -60,6 +60,13 @@ void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
 void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int max_fits,
                    const FitResult *d_results);
 
+// raw FITS binary-table records <-> dense little-endian TIME / VOLT arrays
+void launch_unpack_rows(const Launcher &L, const void *d_rows, long long n, long long row_bytes,
+                        long long time_off, long long volt_off, int32_t *d_time, float *d_volt);
+void launch_pack_rows(const Launcher &L, const void *d_rows, long long n, long long row_bytes,
+                      long long volt_off, const float *d_volt_out, int out_floats, void *d_rows_out,
+                      long long row_bytes_out);
+
 // measured FP64 FMA throughput of the device (TFLOP/s), for the fit's roofline
 double measure_dfma_tflops(cudaStream_t stream, double *d_scratch);
 

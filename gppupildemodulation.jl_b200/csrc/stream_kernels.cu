@@ -795,6 +795,69 @@ void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int
 }
 
 // ===========================================================================
+// Raw FITS binary-table rows (what FitsUtils.jl's Dict(hdu) / FITScopy! move,
+// reference src/FitsUtils.jl:31-37,95-156): records of row_bytes bytes, big-endian,
+// TIME (int32) at byte time_off and VOLT (80 float32) at byte volt_off, at any
+// alignment.  k_unpack_rows turns them into the dense little-endian TIME / VOLT
+// arrays the passes above stream through; k_pack_rows writes the output records:
+// the input record with its VOLT field replaced by the 80 (keepraw: 144) output
+// floats, every other byte copied.
+// ===========================================================================
+__device__ __forceinline__ uint32_t load_be32(const unsigned char *p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+
+__global__ void k_unpack_rows(const unsigned char *rows, long long n, long long row_bytes,
+                              long long time_off, long long volt_off, int32_t *time_us, float *volt) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // (row, word 0..80)
+    if (idx >= n * 81) return;
+    const long long r = idx / 81;
+    const int w = (int)(idx - r * 81);
+    const unsigned char *rec = rows + r * row_bytes;
+    if (w == 80) time_us[r] = (int32_t)load_be32(rec + time_off);
+    else reinterpret_cast<uint32_t *>(volt)[r * 80 + w] = load_be32(rec + volt_off + 4 * w);
+}
+
+__global__ void k_pack_rows(const unsigned char *rows, long long n, long long row_bytes,
+                            long long volt_off, const float *volt_out, int out_floats,
+                            unsigned char *rows_out, long long row_bytes_out) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // output byte
+    if (idx >= n * row_bytes_out) return;
+    const long long r = idx / row_bytes_out;
+    const long long b = idx - r * row_bytes_out;
+    const long long vend = volt_off + 4ll * out_floats;
+    unsigned char v;
+    if (b < volt_off) {
+        v = rows[r * row_bytes + b];
+    } else if (b < vend) {
+        const long long k = b - volt_off;
+        const uint32_t word = reinterpret_cast<const uint32_t *>(volt_out)[r * out_floats + (k >> 2)];
+        v = (unsigned char)(word >> (8 * (3 - (int)(k & 3))));   // big-endian byte k & 3
+    } else {
+        v = rows[r * row_bytes + (b - vend) + volt_off + 320];
+    }
+    rows_out[idx] = v;
+}
+
+void launch_unpack_rows(const Launcher &L, const void *d_rows, long long n, long long row_bytes,
+                        long long time_off, long long volt_off, int32_t *d_time, float *d_volt) {
+    const long long tot = n * 81;
+    k_unpack_rows<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
+        reinterpret_cast<const unsigned char *>(d_rows), n, row_bytes, time_off, volt_off, d_time, d_volt);
+    *L.counter += 1;
+}
+
+void launch_pack_rows(const Launcher &L, const void *d_rows, long long n, long long row_bytes,
+                      long long volt_off, const float *d_volt_out, int out_floats, void *d_rows_out,
+                      long long row_bytes_out) {
+    const long long tot = n * row_bytes_out;
+    k_pack_rows<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
+        reinterpret_cast<const unsigned char *>(d_rows), n, row_bytes, volt_off, d_volt_out, out_floats,
+        reinterpret_cast<unsigned char *>(d_rows_out), row_bytes_out);
+    *L.counter += 1;
+}
+
+// ===========================================================================
 // FP64 unit micro-benchmarks: 16 independent DFMA chains per thread, and 8
 // independent mma.sync.m8n8k4.f64 accumulators per warp (the form the harmonic pass
 // uses; both run on the same FP64 units).  The larger of the two is the measured

@@ -118,3 +118,39 @@ def to_complex(table, offsets=None):
     if offsets is not None:
         z = z - np.asarray(offsets).reshape(1, 40)
     return t, z
+
+
+def make_fits(path, table, header=None, modulate=True, met_mode=None):
+    """Write ``table`` (make_table) as a GRAVITY-shaped FITS file: primary header with
+    the keywords ``main`` looks at (src/GPPupilDemodulation.jl:362-389), a dummy image
+    extension and a dummy table before, and the ``METROLOGY`` BINTABLE with columns
+    TIME (1J), VOLT (80E), POWER_LASER (1E), LAMBDA_LASER (1E) -- 332-byte records,
+    big-endian, as in tex/GPPupilDemodulation.tex:40-52."""
+    from . import fits
+    n = table["time_us"].size
+    keys = [("MJD-OBS", float(table["mjd"])), ("ESO INS PMC1 MODULATE", bool(modulate))]
+    hdr = dict(header or {})
+    mode = met_mode or hdr.get("ESO INS MET MODE", "ON")
+    keys.append(("ESO INS MET MODE", mode))
+    for k, v in hdr.items():
+        if k not in ("MJD-OBS", "ESO INS PMC1 MODULATE", "ESO INS MET MODE"):
+            keys.append((k, v))
+    rng = np.random.default_rng(int(n) + 17)
+    cols = [("TIME", "1J", "usec", table["time_us"].astype(">i4")),
+            ("VOLT", "80E", "V", table["volt"].astype(">f4")),
+            ("POWER_LASER", "1E", "mW", rng.normal(1.0, 0.01, n).astype(">f4")),
+            ("LAMBDA_LASER", "1E", "nm", np.full(n, 1908.0, dtype=">f4"))]
+    img = fits.HDU([fits.format_card("XTENSION", "IMAGE"), fits.format_card("BITPIX", 16),
+                    fits.format_card("NAXIS", 2), fits.format_card("NAXIS1", 7),
+                    fits.format_card("NAXIS2", 5), fits.format_card("PCOUNT", 0),
+                    fits.format_card("GCOUNT", 1), fits.format_card("EXTNAME", "IMAGING_DATA_ACQ")],
+                   rng.integers(0, 255, 70, dtype=np.uint8).tobytes(), {})
+    for c in img.cards:
+        k, v = fits.parse_card(c)
+        if k:
+            img.header.setdefault(k, v)
+    other = fits.make_bintable("OPDC", [("TIME", "1J", "usec", np.arange(11, dtype=">i4")),
+                                        ("STATE", "1J", None, rng.integers(0, 9, 11).astype(">i4"))])
+    hdus = [fits.make_primary(keys), img, other, fits.make_bintable("METROLOGY", cols)]
+    fits.write_fits(path, hdus)
+    return path

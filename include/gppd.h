@@ -165,6 +165,25 @@ int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n,
 int gppd_wait(gppd_handle h, int slot);
 
 /*
+ * Raw FITS binary-table records (what FitsUtils.jl's Dict(hdu) reads and FITScopy!
+ * writes, reference src/FitsUtils.jl:31-37,95-156): `rows` holds the n records of the
+ * METROLOGY BINTABLE as stored in the file (big-endian, row_bytes = NAXIS1 bytes each),
+ * TIME (int32, "1J") at byte time_off and VOLT (80 float32, "80E") at byte volt_off of
+ * a record, at any alignment.  Byte-swapping, de-interleaving and re-packing are done
+ * on the device.  rows_out receives the records of the output table: the input record
+ * with its VOLT field replaced by the demodulated 80 floats (144 with GPPD_KEEPRAW, the
+ * record then grows by 256 bytes: row_bytes_out = row_bytes + 256), every other byte
+ * copied.  Asynchronous on pipeline slot `slot` like gppd_submit_table_f32; the
+ * other arguments are as for gppd_process_table_f32.
+ */
+int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows,
+                          int64_t row_bytes, int64_t time_off, int64_t volt_off, double mjd,
+                          const double *offsets, const double *timer1, int64_t n1,
+                          const double *timer2, int64_t n2, double window_s,
+                          const gppd_options *opt, void *rows_out, double *params,
+                          double *chi2, int32_t *info, int8_t *state_out);
+
+/*
  * Device-resident variant (all pointers are device pointers on the handle's
  * GPU; `stream` is a cudaStream_t passed as void*, NULL = the slot's own
  * stream).  No host<->device copies, no synchronisation: the caller orders
