@@ -116,4 +116,47 @@ function demodulateall(timestamp::AbstractVector, data::AbstractMatrix{Complex{T
     return (Matrix{Complex{T}}(output), param, T.(chi2))
 end
 
+"""
+    processrows!(rows_out, rows, row_bytes, time_off, volt_off, mjd; offsets, faintparam,
+                 window, keepraw, onlyhigh) -> (params, chi2, state)
+
+Table-level fast path on the raw bytes of the METROLOGY BINTABLE (big-endian records of
+`row_bytes` bytes, TIME at byte `time_off`, VOLT at byte `volt_off`), replacing the array
+work of `processmetrology` (src/GPPupilDemodulation.jl:139-171,192-253) and the column
+decoding of `Dict(hdu)` (src/FitsUtils.jl:31-37).  `rows_out` receives the output records
+(`row_bytes + 256` bytes each with `keepraw`).  `offsets === nothing` fits the centres.
+"""
+function processrows!(rows_out::Vector{UInt8}, rows::Vector{UInt8}, row_bytes::Integer,
+                      time_off::Integer, volt_off::Integer, mjd::Real;
+                      offsets::Union{Nothing,Vector{ComplexF64}} = nothing,
+                      faintparam::Union{Nothing,FaintStates} = nothing,
+                      window::Real = 0.0, keepraw::Bool = false, onlyhigh::Bool = false, slot::Integer = 0)
+    n = length(rows) ÷ row_bytes
+    flags = (onlyhigh ? GPPD_ONLYHIGH : UInt32(0)) | (keepraw ? GPPD_KEEPRAW : UInt32(0))
+    opt = Options(flags, 0, 0, 0, (0.0, 0.0), 0.0, 0.0)
+    nwrows = Ref{Int64}(0); nwin = Ref{Int64}(1)
+    if window > 0
+        t01 = Int32[ntoh(reinterpret(Int32, rows[k*row_bytes+time_off+1:k*row_bytes+time_off+4])[1]) for k in 0:1]
+        gppd_assert_ok(ccall((:gppd_table_windows, libgppd), Cint,
+            (Int64, Ptr{Int32}, Float64, Float64, Ref{Int64}, Ref{Int64}), 2, t01, mjd, window, nwrows, nwin))
+        nwin[] = cld(n, nwrows[])
+    end
+    params = Matrix{Float64}(undef, 6, 32 * nwin[])
+    chi2 = Vector{Float64}(undef, 32 * nwin[])
+    state = Vector{Int8}(undef, n)
+    t1 = isnothing(faintparam) ? Float64[] : Vector{Float64}(faintparam.timer1)
+    t2 = isnothing(faintparam) ? Float64[] : Vector{Float64}(faintparam.timer2)
+    GC.@preserve rows rows_out offsets t1 t2 begin
+        gppd_assert_ok(ccall((:gppd_submit_fits_rows, libgppd), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Ptr{UInt8}, Int64, Int64, Int64, Float64, Ptr{ComplexF64},
+             Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ref{Options}, Ptr{UInt8},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int8}),
+            gethandle(), slot, n, rows, row_bytes, time_off, volt_off, mjd,
+            isnothing(offsets) ? C_NULL : pointer(offsets), t1, length(t1), t2, length(t2),
+            window, opt, rows_out, params, chi2, C_NULL, state))
+        gppd_assert_ok(ccall((:gppd_wait, libgppd), Cint, (Ptr{Cvoid}, Cint), gethandle(), slot))
+    end
+    return (params, chi2, isnothing(faintparam) ? nothing : state)
+end
+
 end # module
