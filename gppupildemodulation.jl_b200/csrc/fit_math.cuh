@@ -111,33 +111,56 @@ __device__ __forceinline__ double bessel_j_lane(double b, int lane) {
 // reduction by pi/2 with FMAs (exact first step) and the fdlibm kernel polynomials in
 // Horner/FMA form.  About a third of the instructions of the general-purpose
 // sincos(), which carries a Payne-Hanek path.  Every operation is an explicit fma or
-// a single multiply, so the result does not depend on the -fmad setting.
+// a single multiply, so the result does not depend on the -fmad setting.  The
+// coefficients live in constant memory: as literals every one of them costs two
+// extra (uniform-register move) instructions per use.
+__constant__ double c_sincos[16] = {
+    6.36619772367581382433e-01,   // 0: 2/pi
+    1.57079632679489655800e+00,   // 1: pi/2, high part
+    6.12323399573676603587e-17,   // 2: pi/2, low part
+    1.58969099521155010221e-10,   // 3: S6
+    -2.50507602534068634195e-08,  // 4: S5
+    2.75573137070700676789e-06,   // 5: S4
+    -1.98412698298579493134e-04,  // 6: S3
+    8.33333333332248946124e-03,   // 7: S2
+    -1.66666666666666324348e-01,  // 8: S1
+    -1.13596475577881948265e-11,  // 9: C6
+    2.08757232129817482790e-09,   // 10: C5
+    -2.75573143513906633035e-07,  // 11: C4
+    2.48015872894767294178e-05,   // 12: C3
+    -1.38888888888741095749e-03,  // 13: C2
+    4.16666666666666019037e-02,   // 14: C1
+    0.0};
+
 __device__ __forceinline__ void sincos_moderate(double x, double *sn, double *cs) {
     if (!(fabs(x) < 1.0e5)) {
         sincos(x, sn, cs);
         return;
     }
-    const double fn = rint(x * 6.36619772367581382433e-01);
+    const double fn = rint(x * c_sincos[0]);
     const int k = (int)fn;
-    double r = fma(-fn, 1.57079632679489655800e+00, x);
-    r = fma(-fn, 6.12323399573676603587e-17, r);
+    double r = fma(-fn, c_sincos[1], x);
+    r = fma(-fn, c_sincos[2], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, c_sincos[3], c_sincos[4]);
+    ps = fma(z, ps, c_sincos[5]);
+    ps = fma(z, ps, c_sincos[6]);
+    ps = fma(z, ps, c_sincos[7]);
+    ps = fma(z, ps, c_sincos[8]);
     const double ks = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, c_sincos[9], c_sincos[10]);
+    pc = fma(z, pc, c_sincos[11]);
+    pc = fma(z, pc, c_sincos[12]);
+    pc = fma(z, pc, c_sincos[13]);
+    pc = fma(z, pc, c_sincos[14]);
     pc = fma(z, pc, -0.5);
     const double kc = fma(z, pc, 1.0);
-    const double s0 = (k & 1) ? kc : ks, c0 = (k & 1) ? ks : kc;
-    *sn = (k & 2) ? -s0 : s0;
-    *cs = ((k + 1) & 2) ? -c0 : c0;
+    // quadrant: swap for odd k, then flip signs through the high words
+    const bool odd = k & 1;
+    const double s0 = odd ? kc : ks, c0 = odd ? ks : kc;
+    const int sflip = (k & 2) << 30, cflip = ((k + 1) & 2) << 30;
+    *sn = __hiloint2double(__double2hiint(s0) ^ sflip, __double2loint(s0));
+    *cs = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
 }
 
 // Per-state statistics of one (job, group) (reference compute_mean_var_power,
