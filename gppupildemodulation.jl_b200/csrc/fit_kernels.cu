@@ -107,94 +107,44 @@ __device__ __forceinline__ bool harm_quantum(double phi, const JobInfo &ji, doub
     return false;
 }
 
-template <bool OFFS>
-__device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const FitConsts &kc,
-                                              const JobInfo &ji, double b, double phi, double &f,
-                                              double &cre, double &cim, double &are, double &aim) {
-    double q;
-    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;
-    double J[HK + 1];
-    bessel_j(b, J);
-    double sq, cq;
-    sincos_moderate(q, &sq, &cq);
-    double sgdr = J[0] * H[(long long)HV_Z0R * nfits], sgdi = J[0] * H[(long long)HV_Z0I * nfits];
-    double sgr = 0.0, sgi = 0.0;
-    if (OFFS) {
-        sgr = J[0] * H[(long long)HV_Y0R * nfits];
-        sgi = J[0] * H[(long long)HV_Y0I * nfits];
-    }
-    double ck = 1.0, sk = 0.0;
-#pragma unroll 1
-    for (int k = 1; k <= HK; ++k) {
-        // (ck, sk) <- (cos kq, sin kq)
-        double cn = fma(ck, cq, -(sk * sq)), sn = fma(sk, cq, ck * sq);
-        ck = cn;
-        sk = sn;
-        const double tj = 2.0 * J[k];
-        const double *z = H + (long long)(HV_ZK + 4 * (k - 1)) * nfits;
-        const double A = z[0], B = z[nfits], C = z[2 * (long long)nfits], D = z[3 * (long long)nfits];
-        if ((k & 1) == 0) {
-            sgdr = fma(tj, fma(ck, A, -(sk * D)), sgdr);
-            sgdi = fma(tj, fma(ck, C, -(sk * B)), sgdi);
-        } else {
-            sgdr = fma(tj, fma(ck, B, sk * C), sgdr);
-            sgdi = fma(tj, -fma(ck, D, sk * A), sgdi);
-        }
-        if (OFFS) {
-            const double *y = H + (long long)(HV_YK + 4 * (k - 1)) * nfits;
-            const double Ay = y[0], By = y[nfits], Cy = y[2 * (long long)nfits],
-                         Dy = y[3 * (long long)nfits];
-            if ((k & 1) == 0) {
-                sgr = fma(tj, fma(ck, Ay, -(sk * Dy)), sgr);
-                sgi = fma(tj, fma(ck, Cy, -(sk * By)), sgi);
-            } else {
-                sgr = fma(tj, -fma(ck, By, sk * Cy), sgr);
-                sgi = fma(tj, fma(ck, Dy, sk * Ay), sgi);
-            }
-        }
-    }
-    f = solve_linear(kc, OFFS, sgdr, sgdi, sgr, sgi, cre, cim, are, aim);
-    return true;
-}
-
-// the solver's 49-angle table (newuoa2.cuh), filled by the first 50 threads of a block
-__device__ __forceinline__ void fill_angle_table(NuSinCos *tab) {
-    if (threadIdx.x <= NU_ANGLES) nu_angle_entry(threadIdx.x, &tab[threadIdx.x]);
-}
-
-// ---- one warp per fit ---------------------------------------------------------
+// Both harmonic evaluators (one warp per fit, one thread per fit) compute the SAME
+// 32 "lane terms" with the same operations and add them in the same (butterfly) order,
+// so a fit's chi2 values -- hence its trajectory -- do not depend on which kernel the
+// size of the batch selected.
 struct HarmLane {       // lane k = 1..HK: (A, B, C, D) of harmonic k; lane 0: (Z_0.re, Z_0.im)
     double zA, zB, zC, zD;
     double yA, yB, yC, yD;
 };
 
+// powers e^{j 2^i q}, i = 0..4
+struct QPowers {
+    double pr[5], pi[5];
+};
+__device__ __forceinline__ void q_powers(double cq, double sq, QPowers &P) {
+    P.pr[0] = cq;
+    P.pi[0] = sq;
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        P.pr[i] = fma(P.pr[i - 1], P.pr[i - 1], -(P.pi[i - 1] * P.pi[i - 1]));
+        P.pi[i] = 2.0 * (P.pr[i - 1] * P.pi[i - 1]);
+    }
+}
+
+// term of harmonic `lane` (0 = DC, 1..HK) of S_gd (tr, ti) and S_g (ur, ui); J = J_lane(b)
 template <bool OFFS>
-__device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitConsts &kc,
-                                                   const JobInfo &ji, int lane, double b, double phi,
-                                                   double &f, double &cre, double &cim, double &are,
-                                                   double &aim) {
-    double q;
-    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;   // warp-uniform
-    const double J = bessel_j_lane(b, lane);
-    double sq, cq;
-    sincos_moderate(q, &sq, &cq);
-    // (ck, sk) = (cos lane q, sin lane q): e^{jq} squared four times, then the product
-    // of the powers selected by the bits of the lane number
-    double ck = 1.0, sk = 0.0, pr = cq, pi = sq;
+__device__ __forceinline__ void lane_terms(int lane, double J, const QPowers &P, const HarmLane &h,
+                                           double &tr, double &ti, double &ur, double &ui) {
+    // (ck, sk) = (cos lane q, sin lane q): product of the powers selected by the bits of lane
+    double ck = 1.0, sk = 0.0;
 #pragma unroll
     for (int bit = 0; bit < 5; ++bit) {
         if ((lane >> bit) & 1) {
-            const double nr = fma(ck, pr, -(sk * pi)), ni = fma(ck, pi, sk * pr);
+            const double nr = fma(ck, P.pr[bit], -(sk * P.pi[bit])), ni = fma(ck, P.pi[bit], sk * P.pr[bit]);
             ck = nr;
             sk = ni;
         }
-        if (bit < 4) {
-            const double nr = fma(pr, pr, -(pi * pi)), ni = 2.0 * (pr * pi);
-            pr = nr;
-            pi = ni;
-        }
     }
-    double tr = 0.0, ti = 0.0, ur = 0.0, ui = 0.0;
+    tr = ti = ur = ui = 0.0;
     if (lane == 0) {
         tr = J * h.zA;
         ti = J * h.zB;
@@ -217,6 +167,82 @@ __device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitC
             }
         }
     }
+}
+
+// the harmonic table entries lane `lane` needs
+template <bool OFFS>
+__device__ __forceinline__ void load_lane(const double *H, int nfits, int lane, HarmLane &h) {
+    h.zA = h.zB = h.zC = h.zD = h.yA = h.yB = h.yC = h.yD = 0.0;
+    if (lane == 0) {
+        h.zA = H[(long long)HV_Z0R * nfits];
+        h.zB = H[(long long)HV_Z0I * nfits];
+        if (OFFS) {
+            h.yA = H[(long long)HV_Y0R * nfits];
+            h.yB = H[(long long)HV_Y0I * nfits];
+        }
+    } else if (lane <= HK) {
+        const double *z = H + (long long)(HV_ZK + 4 * (lane - 1)) * nfits;
+        h.zA = z[0]; h.zB = z[nfits]; h.zC = z[2 * (long long)nfits]; h.zD = z[3 * (long long)nfits];
+        if (OFFS) {
+            const double *y = H + (long long)(HV_YK + 4 * (lane - 1)) * nfits;
+            h.yA = y[0]; h.yB = y[nfits]; h.yC = y[2 * (long long)nfits]; h.yD = y[3 * (long long)nfits];
+        }
+    }
+}
+
+// ---- one thread per fit: the 32 lane terms one after the other, added in the order of
+// the warp kernel's xor butterfly (o = 16, 8, 4, 2, 1)
+template <bool OFFS>
+__device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const FitConsts &kc,
+                                              const JobInfo &ji, double b, double phi, double &f,
+                                              double &cre, double &cim, double &are, double &aim) {
+    double q;
+    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;
+    double J[HK + 1];
+    bessel_j(b, J);
+    double sq, cq;
+    sincos_moderate(q, &sq, &cq);
+    QPowers P;
+    q_powers(cq, sq, P);
+    double t[4][32];
+#pragma unroll 1
+    for (int lane = 0; lane <= HK; ++lane) {
+        HarmLane h;
+        load_lane<OFFS>(H, nfits, lane, h);
+        lane_terms<OFFS>(lane, J[lane], P, h, t[0][lane], t[1][lane], t[2][lane], t[3][lane]);
+    }
+#pragma unroll 1
+    for (int lane = HK + 1; lane < 32; ++lane)   // the warp kernel's idle lanes contribute +0.0
+        t[0][lane] = t[1][lane] = t[2][lane] = t[3][lane] = 0.0;
+#pragma unroll 1
+    for (int v = 0; v < (OFFS ? 4 : 2); ++v)
+        for (int o = 16; o > 0; o >>= 1)
+            for (int i = 0; i < o; ++i) t[v][i] = t[v][i] + t[v][i + o];
+    f = solve_linear(kc, OFFS, t[0][0], t[1][0], OFFS ? t[2][0] : 0.0, OFFS ? t[3][0] : 0.0, cre, cim,
+                     are, aim);
+    return true;
+}
+
+// the solver's 49-angle table (newuoa2.cuh), filled by the first 50 threads of a block
+__device__ __forceinline__ void fill_angle_table(NuSinCos *tab) {
+    if (threadIdx.x <= NU_ANGLES) nu_angle_entry(threadIdx.x, &tab[threadIdx.x]);
+}
+
+// ---- one warp per fit ---------------------------------------------------------
+template <bool OFFS>
+__device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitConsts &kc,
+                                                   const JobInfo &ji, int lane, double b, double phi,
+                                                   double &f, double &cre, double &cim, double &are,
+                                                   double &aim) {
+    double q;
+    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;   // warp-uniform
+    const double J = bessel_j_lane(b, lane);
+    double sq, cq;
+    sincos_moderate(q, &sq, &cq);
+    QPowers P;
+    q_powers(cq, sq, P);
+    double tr, ti, ur, ui;
+    lane_terms<OFFS>(lane, J, P, h, tr, ti, ur, ui);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {   // fixed-order butterfly: every lane gets the same bits
         tr += __shfl_xor_sync(0xffffffffu, tr, o);
@@ -262,22 +288,7 @@ k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *ht
         kc.mui = mu.y;
     }
     HarmLane h;
-    h.zA = h.zB = h.zC = h.zD = h.yA = h.yB = h.yC = h.yD = 0.0;
-    if (lane == 0) {
-        h.zA = H[(long long)HV_Z0R * nfits];
-        h.zB = H[(long long)HV_Z0I * nfits];
-        if (OFFS) {
-            h.yA = H[(long long)HV_Y0R * nfits];
-            h.yB = H[(long long)HV_Y0I * nfits];
-        }
-    } else if (lane <= HK) {
-        const double *z = H + (long long)(HV_ZK + 4 * (lane - 1)) * nfits;
-        h.zA = z[0]; h.zB = z[nfits]; h.zC = z[2 * (long long)nfits]; h.zD = z[3 * (long long)nfits];
-        if (OFFS) {
-            const double *y = H + (long long)(HV_YK + 4 * (lane - 1)) * nfits;
-            h.yA = y[0]; h.yB = y[nfits]; h.yC = y[2 * (long long)nfits]; h.yD = y[3 * (long long)nfits];
-        }
-    }
+    load_lane<OFFS>(H, nfits, lane, h);
 
     FitDriverT<true> &drv = s_drv[warp];
     drv.start(opt, s_ang);

@@ -163,7 +163,7 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     constexpr int NCONST = KIND == 0 ? 7 : 2;
     constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;   // sums a producer thread carries per diode
     constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
-    const int jg = blockIdx.y, p = blockIdx.x;
+    const int jg = blockIdx.x, p = blockIdx.y;   // x: up to 2^31 - 1 (job, group) pairs
     const int job = jg >> 3, group = jg & 7;
     const JobInfo ji = jobs[job];
     // by value: the table description must sit in registers, not be re-read from
@@ -511,7 +511,7 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
     cudaFuncSetAttribute(k_harm_accumulate<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(k_harm_accumulate<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(k_harm_accumulate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    dim3 grid(P, njobs * NGROUP);
+    dim3 grid(njobs * NGROUP, P);
     const bool offs = (flags & 2u) != 0;
     if (offs) {
         k_harm_accumulate<0, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,

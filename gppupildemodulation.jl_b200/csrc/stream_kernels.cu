@@ -337,8 +337,8 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
             unsigned flags, int P, double *part) {
     __shared__ double s_piv[16];
     __shared__ double s_red[STATS_VALS][STATS_THREADS / 32];
-    const int p = blockIdx.x;
-    const int job = faint_jobs[blockIdx.y >> 3], group = blockIdx.y & 7;
+    const int p = blockIdx.y;
+    const int job = faint_jobs[blockIdx.x >> 3], group = blockIdx.x & 7;
     const int jg = job * NGROUP + group;
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
@@ -480,7 +480,7 @@ void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_j
                   const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
                   double *d_part, double *d_table) {
     if (nfaint <= 0) return;
-    dim3 grid(P, nfaint * NGROUP);
+    dim3 grid(nfaint * NGROUP, P);
     k_stats_seg<<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt, flags, P,
                                                      d_part);
     const int njg = njobs * NGROUP;

@@ -498,3 +498,20 @@ def test_fallback_queue_large_b(gp, ora):
     assert np.all(r_auto[3][:, 2] == 1)          # every fit fell back
     assert r_auto[1].tobytes() == r_dir[1].tobytes() and r_auto[2].tobytes() == r_dir[2].tobytes()
     assert np.array_equal(r_auto[0], r_dir[0])
+
+
+def test_many_small_windows(gp, ora):
+    """More (job, group) pairs than a CUDA grid's y dimension holds (65 535): 9 000
+    windows of 12 rows; every window equals a separate call on its rows."""
+    n, w = 108_000, 12
+    tab = make_case(gp.synthetic, n, k=7)
+    off = gp.synthetic.stefan_centres()
+    t, z = gp.synthetic.to_complex(tab, off)
+    out, par, like, info = gp.demodulateall(t, z, raw=True, nwindow=w, return_info=True)
+    assert par.shape == (9000 * 32, 6) and np.all(info[:, 0] > 0)
+    assert np.allclose(np.abs(out[:, :32]), np.abs(z[:, :32]), rtol=1e-12, atol=1e-15)
+    for win in (0, 4321, 8999):
+        lo = win * w
+        o1, p1, l1 = gp.demodulateall(t[lo:lo + w], z[lo:lo + w], raw=True)
+        assert p1.tobytes() == par[win * 32:(win + 1) * 32].tobytes()
+        assert np.array_equal(o1, out[lo:lo + w])
