@@ -332,11 +332,15 @@ constexpr int STATS_THREADS = 256;
 constexpr int STATS_RPT = STATS_SEG_ROWS / STATS_THREADS;   // rows per thread
 constexpr int STATS_BATCH = 4;                              // rows loaded ahead of their use
 
-__global__ void __launch_bounds__(STATS_THREADS, 2)
+// A warp walks 32 consecutive rows at a time; states come in runs of hundreds of
+// rows, so the warp keeps the sums of ONE state in registers (9 doubles per lane) and
+// folds them into its shared-memory totals when the state changes (mixed 32-row
+// groups, i.e. run boundaries, take the states one after the other).
+__global__ void __launch_bounds__(STATS_THREADS, 3)
 k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, const int *jobcnt,
             unsigned flags, int P, double *part) {
     __shared__ double s_piv[16];
-    __shared__ double s_red[STATS_VALS][STATS_THREADS / 32];
+    __shared__ double s_acc[STATS_THREADS / 32][STATS_VALS];
     const int p = blockIdx.y;
     const int job = faint_jobs[blockIdx.x >> 3], group = blockIdx.x & 7;
     const int jg = job * NGROUP + group;
@@ -349,6 +353,7 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
     const TableView &tv = tb.tv;
     const bool vec = tv.kind == 0 && !tv.big_endian && (tv.volt_stride & 15) == 0 &&
                      (reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 16) {   // pivots
         const int dio = threadIdx.x >> 2, st = threadIdx.x & 3;
         const int first = jobcnt[JOBCNT * job + 1 + st];
@@ -359,85 +364,113 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
         }
         s_piv[threadIdx.x] = pv;
     }
+    for (int k = lane; k < STATS_VALS; k += 32) s_acc[w][k] = 0.0;
     double2 off[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
         off[d] = (tv.kind == 0 && tv.offsets) ? __ldg(tv.offsets + group * 4 + d) : make_double2(0.0, 0.0);
     __syncthreads();
 
-    double cnt[4], s1[16], s2[16];
+    int cur = -1;                 // state whose sums the registers hold (warp-uniform)
+    double a1[4], a2[4], ac = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s1[k] = s2[k] = 0.0;
+    for (int d = 0; d < 4; ++d) a1[d] = a2[d] = 0.0;
+    // registers -> the warp's shared totals: [0..3] counts, [4..19] S1, [20..35] S2
+    auto flush = [&]() {
+        if (cur < 0) return;
+        double v[9] = {ac, a1[0], a1[1], a1[2], a1[3], a2[0], a2[1], a2[2], a2[3]};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cnt[k] = 0.0;
+        for (int k = 0; k < 9; ++k)
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if (lane == 0) {
+            s_acc[w][cur] += v[0];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                s_acc[w][4 + d * 4 + cur] += v[1 + d];
+                s_acc[w][20 + d * 4 + cur] += v[5 + d];
+            }
+        }
+        ac = 0.0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) a1[d] = a2[d] = 0.0;
+    };
+
 #pragma unroll 1
     for (int j0 = 0; j0 < STATS_RPT; j0 += STATS_BATCH) {
         // the loads of a batch of rows are issued before their first use
         float4 ra[STATS_BATCH], rb[STATS_BATCH];
         int rs[STATS_BATCH];
-        if (vec) {
 #pragma unroll
-            for (int j = 0; j < STATS_BATCH; ++j) {
-                const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
-                rs[j] = -2;
-                if (i < nseg) {
-                    const long long r = ji.row0 + seg0 + i;
+        for (int j = 0; j < STATS_BATCH; ++j) {
+            const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
+            rs[j] = -1;
+            if (i < nseg) {
+                const long long r = ji.row0 + seg0 + i;
+                if (vec) {
                     const float4 *q = reinterpret_cast<const float4 *>(
                         reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride + 32 * group);
                     ra[j] = __ldg(q);
                     rb[j] = __ldg(q + 1);
-                    rs[j] = tb.state[r];
                 }
+                const int st = tb.state[r];
+                rs[j] = (row_valid(st, flags) && st >= 0 && st <= 3) ? st : -1;
             }
         }
 #pragma unroll
         for (int j = 0; j < STATS_BATCH; ++j) {
             const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
-            if (i >= nseg) continue;
-            const long long r = ji.row0 + seg0 + i;
-            int st = vec ? rs[j] : (int)tb.state[r];
-            if (!row_valid(st, flags) || st < 0 || st > 3) continue;
-            double2 dd[4];
-            if (vec) {
-                dd[0] = make_double2((double)ra[j].x - off[0].x, (double)ra[j].y - off[0].y);
-                dd[1] = make_double2((double)ra[j].z - off[1].x, (double)ra[j].w - off[1].y);
-                dd[2] = make_double2((double)rb[j].x - off[2].x, (double)rb[j].y - off[2].y);
-                dd[3] = make_double2((double)rb[j].z - off[3].x, (double)rb[j].w - off[3].y);
-            } else {
+            const int st = rs[j];
+            double x[4] = {0.0, 0.0, 0.0, 0.0};
+            if (st >= 0) {
+                double2 dd[4];
+                if (vec) {
+                    dd[0] = make_double2((double)ra[j].x - off[0].x, (double)ra[j].y - off[0].y);
+                    dd[1] = make_double2((double)ra[j].z - off[1].x, (double)ra[j].w - off[1].y);
+                    dd[2] = make_double2((double)rb[j].x - off[2].x, (double)rb[j].y - off[2].y);
+                    dd[3] = make_double2((double)rb[j].z - off[3].x, (double)rb[j].w - off[3].y);
+                } else {
+                    const long long r = ji.row0 + seg0 + i;
 #pragma unroll
-                for (int dio = 0; dio < 4; ++dio) dd[dio] = row_sample(tv, r, group * 4 + dio);
+                    for (int dio = 0; dio < 4; ++dio) dd[dio] = row_sample(tv, r, group * 4 + dio);
+                }
+#pragma unroll
+                for (int dio = 0; dio < 4; ++dio)
+                    x[dio] = sqrt(fma(dd[dio].x, dd[dio].x, dd[dio].y * dd[dio].y)) - s_piv[dio * 4 + st];
             }
+            const int st0 = __shfl_sync(0xffffffffu, st, 0);
+            if (__all_sync(0xffffffffu, st == st0)) {        // the usual case: one state (or no valid row)
+                if (st0 >= 0) {
+                    if (st0 != cur) { flush(); cur = st0; }
+                    ac += 1.0;
 #pragma unroll
-            for (int dio = 0; dio < 4; ++dio) {
-                const double e =
-                    sqrt(fma(dd[dio].x, dd[dio].x, dd[dio].y * dd[dio].y)) - s_piv[dio * 4 + st];
-                const double e2 = e * e;
-#pragma unroll
+                    for (int dio = 0; dio < 4; ++dio) {
+                        a1[dio] += x[dio];
+                        a2[dio] = fma(x[dio], x[dio], a2[dio]);
+                    }
+                }
+            } else {                                          // a run boundary inside the 32 rows
+#pragma unroll 1
                 for (int s = 0; s < 4; ++s) {
+                    if (!__any_sync(0xffffffffu, st == s)) continue;
+                    if (s != cur) { flush(); cur = s; }
                     if (st == s) {
-                        s1[dio * 4 + s] += e;
-                        s2[dio * 4 + s] += e2;
+                        ac += 1.0;
+#pragma unroll
+                        for (int dio = 0; dio < 4; ++dio) {
+                            a1[dio] += x[dio];
+                            a2[dio] = fma(x[dio], x[dio], a2[dio]);
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (st == s) cnt[s] += 1.0;
         }
     }
-    // block sums in a fixed order: [0..3] counts, [4..19] S1, [20..35] S2
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < STATS_VALS; ++k) {
-        double v = k < 4 ? cnt[k] : (k < 20 ? s1[k - 4] : s2[k - 20]);
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[k][w] = v;
-    }
+    flush();
     __syncthreads();
     if (threadIdx.x < STATS_VALS) {
         double v = 0.0;
 #pragma unroll
-        for (int j = 0; j < STATS_THREADS / 32; ++j) v += s_red[threadIdx.x][j];
+        for (int j = 0; j < STATS_THREADS / 32; ++j) v += s_acc[j][threadIdx.x];
         part[((long long)jg * P + p) * STATS_VALS + threadIdx.x] = v;
     }
 }
@@ -546,6 +579,7 @@ constexpr int DM_STAGE_BYTES = DM_ROWS * (320 + 16); // raw rows + basis
 constexpr int DM_SMEM_OUT = DM_ROWS * 144 * 4;      // keepraw staging
 constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + DM_SMEM_OUT + 64;
 
+template <bool BE>   // raw FITS byte order of the float32 tables (GPPD_BIG_ENDIAN, a batch-wide flag)
 __global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, const FitResult *results,
                                                          unsigned flags) {
     const TableDesc &tbg = tabs[blockIdx.y];
@@ -584,7 +618,8 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, 
     const long long in_stride = tbg.tv.volt_stride, out_stride = tbg.ov.volt_stride;
     const double2 *basis = tbg.basis;
     const double2 *offsets = tbg.tv.offsets;
-    const int be_in = tbg.tv.big_endian, be_out = tbg.ov.big_endian, keepraw = tbg.ov.keepraw;
+    constexpr bool be_in = BE, be_out = BE;
+    const int keepraw = tbg.ov.keepraw;
     const int job0 = tbg.job0, njobs = tbg.njobs;
     const int ow = keepraw ? 144 : 80;   // output words per row
     const bool bulk_in = in_stride == 320 && aligned16(volt_in);
@@ -756,12 +791,14 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, 
 
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
                   const FitResult *d_results, unsigned flags) {
-    cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+    cudaFuncSetAttribute(k_demod<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+    cudaFuncSetAttribute(k_demod<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
     const long long rows_per_block = (long long)DM_ROWS * DM_TPB;
     // the 144-float staging buffer is only needed with keepraw (flag bit 8 = GPPD_KEEPRAW)
     const int smem = (flags & 8u) ? DM_SMEM : DM_SMEM - DM_SMEM_OUT;
-    k_demod<<<dim3((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), ntables), DM_THREADS,
-              smem, L.stream>>>(d_tabs, d_results, flags);
+    const dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), ntables);
+    if (flags & 16u) k_demod<true><<<grid, DM_THREADS, smem, L.stream>>>(d_tabs, d_results, flags);
+    else k_demod<false><<<grid, DM_THREADS, smem, L.stream>>>(d_tabs, d_results, flags);
     *L.counter += 1;
 }
 
