@@ -67,6 +67,12 @@ enum { NU_SUCCESS = 0, NU_ROUNDING_ERRORS = -2, NU_TOO_MANY_EVALUATIONS = -3 };
 #else
 #define NU_ROLLED
 #endif
+// rarely executed, large routines: out of line on the device
+#ifdef __CUDACC__
+#define NU_COLD __noinline__
+#else
+#define NU_COLD
+#endif
 
 // The three angle searches (TRSAPP, BIGLAG, BIGDEN) always probe the same 49
 // angles 2 pi i / 50: their sines and cosines are tabulated once with nu_sincos
@@ -502,7 +508,7 @@ struct Newuoa2T {
     }
 
     // ------------------------------------------------------------------
-    __host__ __device__ void bigden() {
+    __host__ __device__ NU_COLD void bigden() {
         const double half = 0.5, one = 1.0, quart = 0.25, two = 2.0, zero = 0.0;
         const double twopi = 6.283185307179586476925;
         double s[N + 1];
@@ -838,6 +844,72 @@ struct Newuoa2T {
     }
 
     // ------------------------------------------------------------------
+    // Shift XBASE to XOPT (taken when the step is small against |xopt|): rare and
+    // large, kept out of line so that the hot path of step() stays compact.
+    __host__ __device__ NU_COLD void shift_xbase() {
+        const double half = 0.5, zero = 0.0;
+        double temp, tempq, sum, sumz;
+        int ih, ip;
+        tempq = 0.25 * xoptsq;
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) {
+            sum = zero;
+            for (int i = 1; i <= N; ++i) sum += XPT(k, i) * xopt[i];
+            temp = pq[k] * sum;
+            sum -= half * xoptsq;
+            w[NPT + k] = sum;
+            for (int i = 1; i <= N; ++i) {
+                gq[i] += temp * XPT(k, i);
+                XPT(k, i) -= half * xopt[i];
+                vlag[i] = BMAT(k, i);
+                w[i] = sum * XPT(k, i) + tempq * xopt[i];
+                ip = NPT + i;
+                for (int j = 1; j <= i; ++j)
+                    BMAT(ip, j) = BMAT(ip, j) + vlag[i] * w[j] + w[i] * vlag[j];
+            }
+        }
+        NU_ROLLED for (int k = 1; k <= NPTM; ++k) {
+            sumz = zero;
+            NU_ROLLED for (int i = 1; i <= NPT; ++i) {
+                sumz += ZMAT(i, k);
+                w[i] = w[NPT + i] * ZMAT(i, k);
+            }
+            for (int j = 1; j <= N; ++j) {
+                sum = tempq * sumz * xopt[j];
+                NU_ROLLED for (int i = 1; i <= NPT; ++i) sum += w[i] * XPT(i, j);
+                vlag[j] = sum;
+                if (k < idz) sum = -sum;
+                NU_ROLLED for (int i = 1; i <= NPT; ++i) BMAT(i, j) = BMAT(i, j) + sum * ZMAT(i, k);
+            }
+            for (int i = 1; i <= N; ++i) {
+                ip = i + NPT;
+                temp = vlag[i];
+                if (k < idz) temp = -temp;
+                for (int j = 1; j <= i; ++j) BMAT(ip, j) = BMAT(ip, j) + temp * vlag[j];
+            }
+        }
+        ih = 0;
+        for (int j = 1; j <= N; ++j) {
+            w[j] = zero;
+            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
+                w[j] += pq[k] * XPT(k, j);
+                XPT(k, j) -= half * xopt[j];
+            }
+            for (int i = 1; i <= j; ++i) {
+                ++ih;
+                if (i < j) gq[j] += hq[ih] * xopt[i];
+                gq[i] += hq[ih] * xopt[j];
+                hq[ih] = hq[ih] + w[i] * xopt[j] + xopt[i] * w[j];
+                BMAT(NPT + i, j) = BMAT(NPT + j, i);
+            }
+        }
+        for (int j = 1; j <= N; ++j) {
+            xbase[j] += xopt[j];
+            xopt[j] = zero;
+        }
+        xoptsq = zero;
+    }
+
+    // ------------------------------------------------------------------
     // Advance the solver.  On the first call `fin` is ignored; afterwards it
     // is the objective value at the point x[] returned by the previous call.
     // Returns true when x[] must be evaluated, false when finished.
@@ -975,65 +1047,7 @@ struct Newuoa2T {
             goto L490;
         }
     L120:
-        if (dsq <= 1.0e-3 * xoptsq) {
-            tempq = 0.25 * xoptsq;
-            NU_ROLLED for (int k = 1; k <= NPT; ++k) {
-                sum = zero;
-                for (int i = 1; i <= N; ++i) sum += XPT(k, i) * xopt[i];
-                temp = pq[k] * sum;
-                sum -= half * xoptsq;
-                w[NPT + k] = sum;
-                for (int i = 1; i <= N; ++i) {
-                    gq[i] += temp * XPT(k, i);
-                    XPT(k, i) -= half * xopt[i];
-                    vlag[i] = BMAT(k, i);
-                    w[i] = sum * XPT(k, i) + tempq * xopt[i];
-                    ip = NPT + i;
-                    for (int j = 1; j <= i; ++j)
-                        BMAT(ip, j) = BMAT(ip, j) + vlag[i] * w[j] + w[i] * vlag[j];
-                }
-            }
-            NU_ROLLED for (int k = 1; k <= NPTM; ++k) {
-                sumz = zero;
-                NU_ROLLED for (int i = 1; i <= NPT; ++i) {
-                    sumz += ZMAT(i, k);
-                    w[i] = w[NPT + i] * ZMAT(i, k);
-                }
-                for (int j = 1; j <= N; ++j) {
-                    sum = tempq * sumz * xopt[j];
-                    NU_ROLLED for (int i = 1; i <= NPT; ++i) sum += w[i] * XPT(i, j);
-                    vlag[j] = sum;
-                    if (k < idz) sum = -sum;
-                    NU_ROLLED for (int i = 1; i <= NPT; ++i) BMAT(i, j) = BMAT(i, j) + sum * ZMAT(i, k);
-                }
-                for (int i = 1; i <= N; ++i) {
-                    ip = i + NPT;
-                    temp = vlag[i];
-                    if (k < idz) temp = -temp;
-                    for (int j = 1; j <= i; ++j) BMAT(ip, j) = BMAT(ip, j) + temp * vlag[j];
-                }
-            }
-            ih = 0;
-            for (int j = 1; j <= N; ++j) {
-                w[j] = zero;
-                NU_ROLLED for (int k = 1; k <= NPT; ++k) {
-                    w[j] += pq[k] * XPT(k, j);
-                    XPT(k, j) -= half * xopt[j];
-                }
-                for (int i = 1; i <= j; ++i) {
-                    ++ih;
-                    if (i < j) gq[j] += hq[ih] * xopt[i];
-                    gq[i] += hq[ih] * xopt[j];
-                    hq[ih] = hq[ih] + w[i] * xopt[j] + xopt[i] * w[j];
-                    BMAT(NPT + i, j) = BMAT(NPT + j, i);
-                }
-            }
-            for (int j = 1; j <= N; ++j) {
-                xbase[j] += xopt[j];
-                xopt[j] = zero;
-            }
-            xoptsq = zero;
-        }
+        if (dsq <= 1.0e-3 * xoptsq) shift_xbase();
         if (knew > 0) biglag(dstep);
 
         NU_ROLLED for (int k = 1; k <= NPT; ++k) {
