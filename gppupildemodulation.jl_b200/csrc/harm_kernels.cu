@@ -52,6 +52,7 @@
 // the batch and of the launch shape), the consumer warps' partial C are added in warp
 // order, and k_harm_reduce adds the segments in index order, so a fit's sums -- hence
 // its whole NEWUOA trajectory -- do not depend on what else is in the batch.
+#include <cstdlib>
 #include <type_traits>
 
 #include "fit_math.cuh"
@@ -482,6 +483,313 @@ k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, in
     }
 }
 
+// ===========================================================================
+// Warp-synchronous variant: every warp does both jobs on its own 32-row chunks --
+// stage the raw bytes (cp.async, double buffered), turn them into a private 32-row
+// compute tile (one row per lane), run the 8 DMMA k-steps on it -- with no
+// inter-warp hand-over at all in the main loop.  While some warps of a sub-partition
+// are in their latency-bound "produce" phase the others keep the FP64 units busy
+// with DMMAs.
+// ===========================================================================
+constexpr int WS_WARPS = 8;                    // warps per block, two blocks per SM
+constexpr int WS_THREADS = WS_WARPS * 32;
+constexpr int WS_CH = 32;                      // rows per chunk (one per lane)
+constexpr int WS_CHP = WS_CH + 4;              // padded component stride (bank-conflict free)
+constexpr int HARM_SEG_ROWS = TR * HARM_SEG_TILES;
+
+struct WsRaw {                 // raw bytes of one chunk, as copied by cp.async
+    uint4 dio[4][WS_CH];
+    uint4 fc[WS_CH];
+    uint4 basis[WS_CH];
+    uint32_t state[WS_CH];
+};
+struct WsWarp {
+    double e[8][WS_CHP];
+    double v[8][WS_CHP];
+    WsRaw raw[2];
+};
+static_assert(sizeof(WsWarp) >= 48 * 8 * 8, "a warp's partial C is parked in its own area");
+constexpr int WS_SMEM = WS_WARPS * (int)sizeof(WsWarp);
+
+template <int KIND, bool OFFS>
+__global__ void __launch_bounds__(WS_THREADS, 2)
+k_harm_ws(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, const double *stats,
+          double *partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double2 s_stats[16];
+    __shared__ double2 s_off[5];
+    __shared__ double s_red[WS_WARPS][24];
+    __shared__ unsigned long long s_cnt[WS_WARPS];
+
+    constexpr int NCONST = KIND == 0 ? 7 : 2;
+    constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;
+    constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
+    const int jg = blockIdx.x, p = blockIdx.y;
+    const int job = jg >> 3, group = jg & 7;
+    const JobInfo ji = jobs[job];
+    const TableDesc tb = tabs[ji.table];
+    const TableView &tv = tb.tv;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long seg0 = (long long)p * HARM_SEG_ROWS;
+    if (seg0 >= ji.nrows) return;
+    const int nseg = (int)((ji.nrows - seg0) < HARM_SEG_ROWS ? (ji.nrows - seg0) : HARM_SEG_ROWS);
+    const int nchunks = (nseg + WS_CH - 1) / WS_CH;
+    WsWarp &W = reinterpret_cast<WsWarp *>(smem_raw)[warp];
+
+    if (threadIdx.x < 16) {
+        s_stats[threadIdx.x] = tb.state ? stats_mean_weight(stats, jg, threadIdx.x >> 2, threadIdx.x & 3)
+                                        : make_double2(1.0, 1.0);
+    } else if (threadIdx.x < 21) {
+        const int k = threadIdx.x - 16;
+        const int ch = k < 4 ? group * 4 + k : fc_channel(group);
+        s_off[k] = (tv.kind == 0 && tv.offsets) ? __ldg(tv.offsets + ch) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    const bool async_ok = tv.kind == 1 ||
+        ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
+    const bool faint = tb.state != nullptr;
+
+    // consumer-side lane constants (see k_harm_accumulate)
+    const int m8 = lane >> 2, r4 = lane & 3;
+    const int k0 = (m8 >> 1) + 1, trig = m8 & 1;
+    const int pidx = k0 < 4 ? 2 * (3 - k0) + trig : 0;
+    const double psgn = k0 < 4 ? (trig ? -1.0 : 1.0) : 0.0;
+    const double padd = (k0 == 4 && !trig) ? 1.0 : 0.0;
+    double c[MTILES][2];
+#pragma unroll
+    for (int j = 0; j < MTILES; ++j) c[j][0] = c[j][1] = 0.0;
+    double cst[NACC * 4];
+#pragma unroll
+    for (int q = 0; q < NACC * 4; ++q) cst[q] = 0.0;
+    unsigned long long cnt = 0;
+    double2 mu[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+        mu[d] = OFFS ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
+
+    auto issue = [&](int chunk, WsRaw &S) {     // lane -> row of the chunk
+        const int i = chunk * WS_CH + lane;
+        if (i >= nseg) return;
+        const long long r = ji.row0 + seg0 + i;
+        cp_async16(&S.basis[lane], tb.basis + r);
+        if (tv.kind == 0) {
+            const char *row = reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride;
+            cp_async16(&S.dio[0][lane], row + 32 * group);
+            cp_async16(&S.dio[1][lane], row + 32 * group + 16);
+            cp_async16(&S.fc[lane], row + 256 + 16 * (group >> 1));
+        } else {
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                cp_async16(&S.dio[d][lane], tv.data + (long long)(group * 4 + d) * tv.n + r);
+            cp_async16(&S.fc[lane], tv.data + (long long)fc_channel(group) * tv.n + r);
+        }
+        if (faint) {
+            const int8_t *sp = tb.state + r;
+            const unsigned long long aw = reinterpret_cast<unsigned long long>(sp) & ~3ull;
+            if (aw >= reinterpret_cast<unsigned long long>(tb.state) &&
+                aw + 4 <= reinterpret_cast<unsigned long long>(tb.state + tv.n)) {
+                cp_async4(&S.state[lane], reinterpret_cast<const void *>(aw));
+            } else {
+                const unsigned sh = 8u * (unsigned)(reinterpret_cast<unsigned long long>(sp) & 3ull);
+                S.state[lane] = ((unsigned)(unsigned char)*sp) << sh;
+            }
+        }
+    };
+
+    auto produce = [&](auto faint_tag, int chunk, const WsRaw &S) {
+        constexpr bool FAINT = decltype(faint_tag)::value;
+        const int i = chunk * WS_CH + lane;
+        double2 e1 = make_double2(1.0, 0.0);
+        double2 vv[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
+        if (i < nseg) {
+            const long long r = ji.row0 + seg0 + i;
+            double2 sc, fcs, dd[4];
+            int st = ST_NORMAL;
+            if (async_ok) {
+                const uint4 bw = S.basis[lane];
+                sc = make_double2(__hiloint2double(bw.y, bw.x), __hiloint2double(bw.w, bw.z));
+                if (tv.kind == 0) {
+                    uint4 a = S.dio[0][lane], b = S.dio[1][lane], f = S.fc[lane];
+                    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    uint32_t fx = (group & 1) ? f.z : f.x, fy = (group & 1) ? f.w : f.y;
+                    if (tv.big_endian) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
+                        fx = bswap32(fx);
+                        fy = bswap32(fy);
+                    }
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+                        dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - s_off[d].x,
+                                             (double)__uint_as_float(w[2 * d + 1]) - s_off[d].y);
+                    fcs = make_double2((double)__uint_as_float(fx) - s_off[4].x,
+                                       (double)__uint_as_float(fy) - s_off[4].y);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const uint4 q = S.dio[d][lane];
+                        dd[d] = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+                    }
+                    const uint4 q = S.fc[lane];
+                    fcs = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
+                }
+                if (FAINT) {
+                    const unsigned sh = 8u * (unsigned)(reinterpret_cast<unsigned long long>(tb.state + r) & 3ull);
+                    st = (int)(signed char)((S.state[lane] >> sh) & 0xffu);
+                }
+            } else {
+                sc = tb.basis[r];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, r, group * 4 + d);
+                fcs = row_sample(tv, r, fc_channel(group));
+                if (FAINT) st = tb.state[r];
+            }
+            e1 = make_double2(sc.y, sc.x);
+            const bool valid = FAINT ? row_valid(st, flags) : true;
+            if (valid) {
+                const double2 fc = fc_unit(fcs.x, fcs.y);
+                cnt += 1ull << (16 * (st & 3));
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    double wpr = fc.x, wpi = fc.y, w = 1.0;   // bright: w = 1, p = FCphasor
+                    if (FAINT) {
+                        const double2 mw = s_stats[d * 4 + (st & 3)];
+                        w = mw.y;
+                        const double wm = mw.y * mw.x;        // p = power .* FCphasor
+                        wpr = wm * fc.x;
+                        wpi = wm * fc.y;
+                    }
+                    if (KIND == 0) {
+                        double dr = dd[d].x, di = dd[d].y;
+                        if (OFFS) { dr -= mu[d].x; di -= mu[d].y; }
+                        vv[d].x = fma(wpr, dr, wpi * di);
+                        vv[d].y = fma(wpr, di, -(wpi * dr));
+                        cst[d * NACC + 0] = fma(w, fma(dr, dr, di * di), cst[d * NACC + 0]);
+                        cst[d * NACC + 1] += vv[d].x;
+                        cst[d * NACC + 2] += vv[d].y;
+                        if (OFFS) {
+                            cst[d * NACC + 3] = fma(w, dr, cst[d * NACC + 3]);
+                            cst[d * NACC + 4] = fma(w, di, cst[d * NACC + 4]);
+                        }
+                    } else {
+                        vv[d].x = wpr;
+                        vv[d].y = wpi;
+                        cst[d * NACC + 0] += wpr;
+                        cst[d * NACC + 1] += wpi;
+                    }
+                }
+            }
+        }
+        const double2 e2 = csqr(e1), e3 = cmul(e2, e1), e4 = csqr(e2);
+        W.e[0][lane] = e1.x; W.e[1][lane] = e1.y;
+        W.e[2][lane] = e2.x; W.e[3][lane] = e2.y;
+        W.e[4][lane] = e3.x; W.e[5][lane] = e3.y;
+        W.e[6][lane] = e4.x; W.e[7][lane] = e4.y;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            W.v[2 * d][lane] = vv[d].x;
+            W.v[2 * d + 1][lane] = vv[d].y;
+        }
+    };
+
+    // chunks warp, warp + WS_WARPS, ... of the segment
+    int ck = warp;
+    if (async_ok && ck < nchunks) issue(ck, W.raw[0]);
+    cp_async_commit();
+    for (int n = 0; ck < nchunks; ck += WS_WARPS, ++n) {
+        if (async_ok) {
+            if (ck + WS_WARPS < nchunks) issue(ck + WS_WARPS, W.raw[(n + 1) & 1]);
+            cp_async_commit();
+            cp_async_wait<1>();          // this chunk's bytes have landed (each lane reads its own)
+        }
+        if (faint) produce(std::true_type{}, ck, W.raw[n & 1]);
+        else produce(std::false_type{}, ck, W.raw[n & 1]);
+        __syncwarp();
+#pragma unroll 4
+        for (int ks = 0; ks < WS_CH / 4; ++ks) {
+            const int row = ks * 4 + r4;
+            const double a0 = W.e[m8][row];
+            const double c4 = W.e[6][row];
+            const double pv = W.e[pidx][row];
+            const double bv = W.v[m8][row];
+            const double tc = c4 + c4;
+            double am = fma(psgn, pv, padd);
+            double ak = a0;
+#pragma unroll
+            for (int j = 0; j < MTILES; ++j) {
+                dmma_m8n8k4(c[j][0], c[j][1], ak, bv);
+                if (j + 1 < MTILES) {
+                    const double an = fma(tc, ak, -am);
+                    am = ak;
+                    ak = an;
+                }
+            }
+        }
+        __syncwarp();                    // the tile is rewritten by the next chunk
+    }
+    if (async_ok) cp_async_wait<0>();
+    __syncwarp();
+
+    // park the warp's partial C in its own area, reduce the constant sums
+    double *cpart = reinterpret_cast<double *>(&W);
+#pragma unroll
+    for (int j = 0; j < MTILES; ++j) {
+        double *dst = cpart + ((8 * j + m8) * 8 + 2 * r4);
+        dst[0] = c[j][0];
+        dst[1] = c[j][1];
+    }
+#pragma unroll
+    for (int q = 0; q < NACC * 4; ++q) {
+        double sv = cst[q];
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (lane == 0) s_red[warp][q] = sv;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+
+    double *out = partial + ((long long)jg * P + p) * 4 * HP;
+    for (int idx = threadIdx.x; idx < 48 * 8; idx += WS_THREADS) {
+        const int m = idx >> 3, n = idx & 7;
+        double sv = 0.0;
+#pragma unroll
+        for (int w = 0; w < WS_WARPS; ++w)
+            sv += reinterpret_cast<const double *>(&reinterpret_cast<WsWarp *>(smem_raw)[w])[m * 8 + n];
+        const int k = m >> 1, sn = m & 1, d = n >> 1, im = n & 1;
+        const int slot = sn ? (im ? 1 : 3) : (im ? 2 : 0);
+        out[d * HP + NCONST + k * 4 + slot] = sv;
+    }
+    if (threadIdx.x < NCONST * 4) {
+        const int d = threadIdx.x / NCONST, cc = threadIdx.x % NCONST;
+        unsigned long long cn = 0;
+        for (int w = 0; w < WS_WARPS; ++w) cn += s_cnt[w];
+        double sv = 0.0;
+        int src = -1;
+        if (KIND == 0) {
+            if (cc == 1) src = 0;
+            else if (cc == 5) src = 1;
+            else if (cc == 6) src = 2;
+            else if (OFFS && cc == 3) src = 3;
+            else if (OFFS && cc == 4) src = 4;
+        } else {
+            src = cc;
+        }
+        if (src >= 0) {
+            for (int w = 0; w < WS_WARPS; ++w) sv += s_red[w][d * NACC + src];
+        } else if (cc == 0 || cc == 2) {
+            for (int st = 0; st < 4; ++st) {
+                const double n_s = (double)((cn >> (16 * st)) & 0xffffull);
+                const double2 mw = s_stats[d * 4 + st];
+                if (n_s > 0.0) sv += cc == 0 ? n_s * mw.y : n_s * (mw.y * (mw.x * mw.x));
+            }
+        }
+        out[d * HP + cc] = sv;
+    }
+}
+
 // partial sums -> per-fit harmonic table, the job's segments added in index order
 __global__ void k_harm_reduce(const JobInfo *jobs, const double *partZ, const double *partY, int P,
                               int nfits, double *htab) {
@@ -513,7 +821,20 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
     cudaFuncSetAttribute(k_harm_accumulate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dim3 grid(njobs * NGROUP, P);
     const bool offs = (flags & 2u) != 0;
-    if (offs) {
+    static const bool use_ws = getenv("GPPD_HARM_PIPELINE") == nullptr;   // default: warp-synchronous
+    if (use_ws) {
+        cudaFuncSetAttribute(k_harm_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+        cudaFuncSetAttribute(k_harm_ws<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+        cudaFuncSetAttribute(k_harm_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+        if (offs) {
+            k_harm_ws<0, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
+            k_harm_ws<1, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);
+            *L.counter += 2;
+        } else {
+            k_harm_ws<0, false><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
+            *L.counter += 1;
+        }
+    } else if (offs) {
         k_harm_accumulate<0, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
                                                                           d_spart1, d_spart2, d_partZ);
         k_harm_accumulate<1, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
