@@ -31,71 +31,42 @@
 //     trig((k + 4) t) = 2 cos(4 t) trig(k t) - trig((k - 4) t)      (one FMA each)
 // from the row's (cos, sin)(t .. 4t), which the producers tabulate.
 //
-// Kernel structure (k_harm_accumulate): one block of 8 warps per (job, group,
-// segment), persistent over the segment's row tiles of TR = 128 rows; TWO blocks are
-// resident per SM, so that one block's pipeline fill and final reduction overlap the
-// other's steady state (measured: one 16-warp block per SM 3.5 ms, two 8-warp blocks
-// 3.1 ms, four 4-warp blocks 3.3 ms).
-//   * Four PRODUCER warps (one row per thread and tile) stream the raw table bytes
-//     of the next-but-one tile into a 3-stage shared-memory ring with cp.async
-//     (16-byte copies: the group's 8 VOLT floats, its FC pair, the row's basis, the
-//     state byte) -- no register dependency, so the global-memory latency is off the
-//     critical path -- and turn the previous stage into a compute tile:
-//     (cos, sin)(theta) and the four diodes' z (or y) values.
-//   * Four CONSUMER warps each take 32 rows of the tile: they first extend their
-//     rows' (cos, sin) to k = 2..4, then run 8 k-steps of 4 rows, per k-step 5
-//     recurrence FMAs and 6 DMMAs into the 12 accumulator registers that hold the
-//     warp's 48 x 8 partial C.
-// Compute tiles are triple buffered and handed over with mbarriers (full / empty
-// per buffer), so consumer warps never wait for each other, only for data.
-// A segment is a FIXED run of HARM_SEG_TILES tiles of the job (independent of
-// the batch and of the launch shape), the consumer warps' partial C are added in warp
-// order, and k_harm_reduce adds the segments in index order, so a fit's sums -- hence
-// its whole NEWUOA trajectory -- do not depend on what else is in the batch.
+// Kernel structure (k_harm_ws): one block of 8 warps per (job, group, 12 288-row
+// segment), two blocks per SM.  The kernel is WARP-SYNCHRONOUS: every warp owns the
+// 32-row chunks warp, warp + 8, ... of the segment and does everything for them --
+//   1. stages the raw table bytes of its next chunk with cp.async (16-byte copies: the
+//      group's 8 VOLT floats, its FC pair, the row's basis, the state byte; double
+//      buffered, no register dependency, so the global-memory latency is off the
+//      critical path),
+//   2. "produces" a private 32-row compute tile, one row per lane: (cos, sin)(k theta),
+//      k = 1..4, and the four diodes' z (or y) values, plus the constant sums,
+//   3. "consumes" it: 8 k-steps of 4 rows, per k-step 5 recurrence FMAs and 6 DMMAs
+//      into the 12 accumulator registers that hold the warp's 48 x 8 partial C --
+// with only __syncwarp in the main loop.  While some warps of a sub-partition are in
+// their latency-bound produce phase the others keep the FP64 units busy with DMMAs
+// (ncu: the FP64 "shared" pipe 75 % busy, DMMA 56 %).  An earlier version with
+// dedicated producer and consumer warps handing tiles over through mbarriers was
+// slower (3.1 ms against 2.96 ms per 100-table night): the producers' in-order FP64
+// chains queued behind the consumers' 16-cycle DMMAs and stalled the hand-over.
+// A segment is a FIXED run of rows of the job (independent of the batch and of the
+// launch shape), the warps' partial C are added in warp order, and k_harm_reduce adds
+// the segments in index order, so a fit's sums -- hence its whole NEWUOA trajectory --
+// do not depend on what else is in the batch.
 #include <cstdlib>
 #include <type_traits>
 
 #include "fit_math.cuh"
 #include "gppd_device.cuh"
 #include "kernels.h"
-#include "tma.cuh"
 
 namespace gppd {
 
-constexpr int TR = 128;                       // rows per tile
-constexpr int HARM_SEG_TILES = 96;            // tiles per segment (12288 rows)
-constexpr int NCONS = 4;                      // consumer warps, 32 rows of a tile each
-constexpr int NPROD = 4;                      // producer warps
-constexpr int HARM_THREADS = (NCONS + NPROD) * 32;
-constexpr int RAW_STAGES = 3;
-constexpr int TILE_BUFS = 3;                   // compute tiles in flight
-constexpr int ROWS_PER_PROD = TR / (NPROD * 32);
+constexpr int HARM_SEG_ROWS = 12288;          // rows per segment
 constexpr int MTILES = 2 * HK / 8;            // 8-row tiles of the 48 (harmonic, cos|sin) rows of C
 static_assert(2 * HK == 8 * MTILES && MTILES == 6, "lane k0 + 4j must cover k = 1..HK");
-static_assert(ROWS_PER_PROD * NPROD * 32 == TR, "TR must be a multiple of the producer threads");
-static_assert(NCONS * 32 == TR, "each consumer warp takes 32 rows of a tile");
-
-// Component-major with a 4-double pad: the producers' stores (32 consecutive rows of
-// one component) and the consumers' fragment loads (8 components x 4 consecutive rows)
-// are both bank-conflict free.
-constexpr int TRP = TR + 4;
-struct HarmTile {
-    double e[8][TRP];          // (cos t, sin t, cos 2t, sin 2t, cos 3t, sin 3t, cos 4t, sin 4t)
-    double v[8][TRP];          // stream values of the group's 4 diodes: (x0, y0, ..., x3, y3)
-};
-
-struct RawStage {              // raw bytes of one tile, as copied by cp.async
-    uint4 dio[4][TR];          // kind 0: [0],[1] = the group's 8 VOLT floats; kind 1: 4 complex128
-    uint4 fc[TR];              // kind 0: 16-byte chunk holding the FC pair; kind 1: the FC complex128
-    uint4 basis[TR];           // (sin theta, cos theta)
-    uint32_t state[TR];        // aligned word holding the row's state byte
-};
-
-constexpr int HARM_SMEM = TILE_BUFS * (int)sizeof(HarmTile) + RAW_STAGES * (int)sizeof(RawStage) + 64;
 
 __host__ __device__ inline int harm_segments(long long nrows) {
-    long long ntiles = (nrows + TR - 1) / TR;
-    return (int)((ntiles + HARM_SEG_TILES - 1) / HARM_SEG_TILES);
+    return (int)((nrows + HARM_SEG_ROWS - 1) / HARM_SEG_ROWS);
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -117,9 +88,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // unit phasor of the FC sample: (x, y) / |(x, y)|  (= exp(1im*angle(fc)), :388)
@@ -144,358 +112,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 //   [0] sum w, [1] sum w |d - mu|^2, [2] sum w |p|^2, [3..4] sum w (d - mu), [5..6] Z_0
 // sum w and sum w |p|^2 (|FCphasor| = 1) follow from the per-state row counts of the
 // segment: sum_s n_s w_s and sum_s n_s w_s m_s^2.
-template <int KIND, bool OFFS>  // KIND 0: z = w conj(p) (d - mu);  1: y = w p
-__global__ void __launch_bounds__(HARM_THREADS, 2)
-k_harm_accumulate(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, int SP,
-                  const double *spart1, const double *spart2, double *partial) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    HarmTile *tiles = reinterpret_cast<HarmTile *>(smem_raw);
-    RawStage *raws = reinterpret_cast<RawStage *>(smem_raw + TILE_BUFS * sizeof(HarmTile));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + TILE_BUFS * sizeof(HarmTile) +
-                                                  RAW_STAGES * sizeof(RawStage));
-    uint64_t *full = bars, *empty = bars + TILE_BUFS;
-    __shared__ double2 s_stats[16];
-    __shared__ double2 s_off[5];      // centres of the 4 diodes + FC (kind-0 tables)
-    __shared__ double s_red[NPROD][24];
-    __shared__ unsigned long long s_cnt[NPROD];
-    double *s_cpart = reinterpret_cast<double *>(smem_raw);   // [NCONS][48][8], reuses tile 0 at the end
-    static_assert(NCONS * 48 * 8 * 8 <= (int)sizeof(HarmTile), "partial C must fit in a tile buffer");
-
-    constexpr int NCONST = KIND == 0 ? 7 : 2;
-    constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;   // sums a producer thread carries per diode
-    constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
-    const int jg = blockIdx.x, p = blockIdx.y;   // x: up to 2^31 - 1 (job, group) pairs
-    const int job = jg >> 3, group = jg & 7;
-    const JobInfo ji = jobs[job];
-    // by value: the table description must sit in registers, not be re-read from
-    // global memory after every asm memory clobber of the pipeline below
-    const TableDesc tb = tabs[ji.table];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool producer = warp >= NCONS;
-    // segment p of the job: tiles [p*HARM_SEG_TILES, ...)
-    const int ntiles = (ji.nrows + TR - 1) / TR;
-    const int tile0 = p * HARM_SEG_TILES;
-    if (tile0 >= ntiles) return;
-    const int nt = (ntiles - tile0) < HARM_SEG_TILES ? (ntiles - tile0) : HARM_SEG_TILES;
-
-    if (threadIdx.x < 16) {
-        s_stats[threadIdx.x] = tb.state
-            ? stats_mean_weight(spart2, jg, threadIdx.x >> 2, threadIdx.x & 3)
-            : make_double2(1.0, 1.0);
-    } else if (threadIdx.x < 21) {
-        const int k = threadIdx.x - 16;
-        const int ch = k < 4 ? group * 4 + k : fc_channel(group);
-        s_off[k] = (tb.tv.kind == 0 && tb.tv.offsets) ? __ldg(tb.tv.offsets + ch) : make_double2(0.0, 0.0);
-    } else if (threadIdx.x == 32) {
-        for (int b = 0; b < TILE_BUFS; ++b) {
-            mbar_init(&full[b], NPROD);
-            mbar_init(&empty[b], NCONS);
-        }
-    }
-    __syncthreads();
-
-    double *out = partial + ((long long)jg * P + p) * 4 * HP;
-
-    if (!producer) {
-        // =================== consumers ===================
-        // lane (m8, r) owns A[m8][r] = trig(k theta_row) of harmonic k = k0 + 4j in
-        // m-tile j (k0 = m8/2 + 1, trig = cos for even m8, sin for odd) and B[r][m8] =
-        // V[row][m8], row = (k-step base) + r
-        const int m8 = lane >> 2, r4 = lane & 3;
-        const int k0 = (m8 >> 1) + 1, trig = m8 & 1;
-        // trig((k0 - 4) t) = +cos((4 - k0) t) or -sin((4 - k0) t); k0 = 4: cos 0 = 1, sin 0 = 0
-        const int pidx = k0 < 4 ? 2 * (3 - k0) + trig : 0;
-        const double psgn = k0 < 4 ? (trig ? -1.0 : 1.0) : 0.0;
-        const double padd = (k0 == 4 && !trig) ? 1.0 : 0.0;
-        double c[MTILES][2];
-#pragma unroll
-        for (int j = 0; j < MTILES; ++j) c[j][0] = c[j][1] = 0.0;
-
-        for (int it = 0; it < nt; ++it) {
-            const int b = it % TILE_BUFS;
-            HarmTile &T = tiles[b];
-            mbar_wait(&full[b], (unsigned)(it / TILE_BUFS) & 1u);
-            {   // (cos, sin)(k theta), k = 2..4, of the warp's 32 rows, one row per lane
-                const int row = warp * 32 + lane;
-                const double2 e1 = make_double2(T.e[0][row], T.e[1][row]);
-                const double2 e2 = csqr(e1), e3 = cmul(e2, e1), e4 = csqr(e2);
-                T.e[2][row] = e2.x; T.e[3][row] = e2.y;
-                T.e[4][row] = e3.x; T.e[5][row] = e3.y;
-                T.e[6][row] = e4.x; T.e[7][row] = e4.y;
-            }
-            __syncwarp();
-#pragma unroll 4
-            for (int ks = 0; ks < 8; ++ks) {
-                const int row = warp * 32 + ks * 4 + r4;
-                const double a0 = T.e[m8][row];
-                const double c4 = T.e[6][row];
-                const double pv = T.e[pidx][row];
-                const double bv = T.v[m8][row];
-                const double tc = c4 + c4;
-                double am = fma(psgn, pv, padd);        // harmonic k0 - 4
-                double ak = a0;                         // harmonic k0
-#pragma unroll
-                for (int j = 0; j < MTILES; ++j) {
-                    dmma_m8n8k4(c[j][0], c[j][1], ak, bv);
-                    if (j + 1 < MTILES) {
-                        const double an = fma(tc, ak, -am);
-                        am = ak;
-                        ak = an;
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[b]);
-        }
-        // park the warp's partial C; added over the warps in order after the barrier below
-        __syncthreads();   // every tile has been consumed: tile buffer 0 is free
-#pragma unroll
-        for (int j = 0; j < MTILES; ++j) {
-            double *dst = s_cpart + ((warp * 48 + 8 * j + m8) * 8 + 2 * r4);
-            dst[0] = c[j][0];
-            dst[1] = c[j][1];
-        }
-    } else {
-        // =================== producers ===================
-        const TableView &tv = tb.tv;
-        // cp.async needs 16-byte aligned sources
-        const bool async_ok = tv.kind == 1 ||
-            ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
-        const int ptid = threadIdx.x - NCONS * 32;
-        double cst[NACC * 4];
-#pragma unroll
-        for (int c = 0; c < NACC * 4; ++c) cst[c] = 0.0;
-        unsigned long long cnt = 0;   // valid rows per state, four 16-bit fields
-        double2 mu[4];
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-            mu[d] = OFFS ? row_sample(tv, ji.row0, group * 4 + d) : make_double2(0.0, 0.0);
-
-        // ---- step 1: raw bytes of a tile -> ring stage (asynchronous) ----
-        auto issue = [&](int tile, RawStage &S) {
-#pragma unroll
-            for (int j = 0; j < ROWS_PER_PROD; ++j) {
-                const int rr = ptid + j * NPROD * 32;
-                const int i = tile * TR + rr;
-                if (i >= ji.nrows) continue;
-                const long long r = ji.row0 + i;
-                cp_async16(&S.basis[rr], tb.basis + r);
-                if (tv.kind == 0) {
-                    const char *row = reinterpret_cast<const char *>(tv.volt) + r * tv.volt_stride;
-                    cp_async16(&S.dio[0][rr], row + 32 * group);
-                    cp_async16(&S.dio[1][rr], row + 32 * group + 16);
-                    cp_async16(&S.fc[rr], row + 256 + 16 * (group >> 1));
-                } else {
-#pragma unroll
-                    for (int d = 0; d < 4; ++d)
-                        cp_async16(&S.dio[d][rr], tv.data + (long long)(group * 4 + d) * tv.n + r);
-                    cp_async16(&S.fc[rr], tv.data + (long long)fc_channel(group) * tv.n + r);
-                }
-                if (tb.state) {
-                    const int8_t *sp = tb.state + r;
-                    const unsigned long long aw = reinterpret_cast<unsigned long long>(sp) & ~3ull;
-                    if (aw >= reinterpret_cast<unsigned long long>(tb.state) &&
-                        aw + 4 <= reinterpret_cast<unsigned long long>(tb.state + tv.n)) {
-                        cp_async4(&S.state[rr], reinterpret_cast<const void *>(aw));
-                    } else {  // first / last rows: do not read outside the state array
-                        const unsigned sh = 8u * (unsigned)(reinterpret_cast<unsigned long long>(sp) & 3ull);
-                        S.state[rr] = ((unsigned)(unsigned char)*sp) << sh;
-                    }
-                }
-            }
-        };
-
-        // ---- step 2: ring stage (or, unaligned tables, global memory) -> compute tile
-        auto produce = [&](auto faint_tag, int tile, const RawStage &S, HarmTile &T) {
-            constexpr bool FAINT = decltype(faint_tag)::value;   // the table has states
-#pragma unroll
-            for (int j = 0; j < ROWS_PER_PROD; ++j) {
-                const int rr = ptid + j * NPROD * 32;
-                const int i = tile * TR + rr;
-                double2 e1 = make_double2(1.0, 0.0);
-                double2 vv[4];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
-                if (i < ji.nrows) {
-                    const long long r = ji.row0 + i;
-                    double2 sc, fcs, dd[4];
-                    int st = ST_NORMAL;
-                    if (async_ok) {
-                        const uint4 bw = S.basis[rr];
-                        sc = make_double2(__hiloint2double(bw.y, bw.x), __hiloint2double(bw.w, bw.z));
-                        if (tv.kind == 0) {
-                            uint4 a = S.dio[0][rr], b = S.dio[1][rr], f = S.fc[rr];
-                            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                            uint32_t fx = (group & 1) ? f.z : f.x, fy = (group & 1) ? f.w : f.y;
-                            if (tv.big_endian) {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
-                                fx = bswap32(fx);
-                                fy = bswap32(fy);
-                            }
-#pragma unroll
-                            for (int d = 0; d < 4; ++d)
-                                dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - s_off[d].x,
-                                                     (double)__uint_as_float(w[2 * d + 1]) - s_off[d].y);
-                            fcs = make_double2((double)__uint_as_float(fx) - s_off[4].x,
-                                               (double)__uint_as_float(fy) - s_off[4].y);
-                        } else {
-#pragma unroll
-                            for (int d = 0; d < 4; ++d) {
-                                const uint4 q = S.dio[d][rr];
-                                dd[d] = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
-                            }
-                            const uint4 q = S.fc[rr];
-                            fcs = make_double2(__hiloint2double(q.y, q.x), __hiloint2double(q.w, q.z));
-                        }
-                        if (FAINT) {
-                            const unsigned sh =
-                                8u * (unsigned)(reinterpret_cast<unsigned long long>(tb.state + r) & 3ull);
-                            st = (int)(signed char)((S.state[rr] >> sh) & 0xffu);
-                        }
-                    } else {
-                        sc = tb.basis[r];
-#pragma unroll
-                        for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, r, group * 4 + d);
-                        fcs = row_sample(tv, r, fc_channel(group));
-                        if (FAINT) st = tb.state[r];
-                    }
-                    e1 = make_double2(sc.y, sc.x);
-                    const bool valid = FAINT ? row_valid(st, flags) : true;
-                    if (valid) {
-                        const double2 fc = fc_unit(fcs.x, fcs.y);
-                        cnt += 1ull << (16 * (st & 3));
-#pragma unroll
-                        for (int d = 0; d < 4; ++d) {
-                            double wpr = fc.x, wpi = fc.y, w = 1.0;   // bright: w = 1, p = FCphasor
-                            if (FAINT) {
-                                const double2 mw = s_stats[d * 4 + (st & 3)];
-                                w = mw.y;
-                                const double wm = mw.y * mw.x;        // p = power .* FCphasor
-                                wpr = wm * fc.x;
-                                wpi = wm * fc.y;
-                            }
-                            if (KIND == 0) {
-                                double dr = dd[d].x, di = dd[d].y;
-                                if (OFFS) { dr -= mu[d].x; di -= mu[d].y; }
-                                vv[d].x = fma(wpr, dr, wpi * di);
-                                vv[d].y = fma(wpr, di, -(wpi * dr));
-                                cst[d * NACC + 0] = fma(w, fma(dr, dr, di * di), cst[d * NACC + 0]);
-                                cst[d * NACC + 1] += vv[d].x;
-                                cst[d * NACC + 2] += vv[d].y;
-                                if (OFFS) {
-                                    cst[d * NACC + 3] = fma(w, dr, cst[d * NACC + 3]);
-                                    cst[d * NACC + 4] = fma(w, di, cst[d * NACC + 4]);
-                                }
-                            } else {
-                                vv[d].x = wpr;
-                                vv[d].y = wpi;
-                                cst[d * NACC + 0] += wpr;
-                                cst[d * NACC + 1] += wpi;
-                            }
-                        }
-                    }
-                }
-                // (cos, sin)(theta); the consumer warp that owns the row adds k = 2..4
-                T.e[0][rr] = e1.x;
-                T.e[1][rr] = e1.y;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    T.v[2 * d][rr] = vv[d].x;
-                    T.v[2 * d + 1][rr] = vv[d].y;
-                }
-            }
-        };
-
-        // Pipeline: stage (it+2) is being copied while stage (it+1) is turned into
-        // compute tile (it+1) while the consumers work on compute tile it.  Every
-        // producer thread reads back only the ring bytes it copied itself, so its own
-        // cp.async.wait_group is the only synchronisation the ring needs.
-        if (async_ok) {
-            issue(tile0, raws[0]);
-            cp_async_commit();
-            if (nt > 1) issue(tile0 + 1, raws[1]);
-            cp_async_commit();
-        }
-        for (int it = 0; it < nt; ++it) {
-            const int b = it % TILE_BUFS;
-            if (async_ok) {
-                if (it + 2 < nt) issue(tile0 + it + 2, raws[(it + 2) % RAW_STAGES]);
-                cp_async_commit();
-                cp_async_wait<2>();      // tile it's bytes have landed
-            }
-            if (it >= TILE_BUFS) mbar_wait(&empty[b], (unsigned)(it / TILE_BUFS - 1) & 1u);
-            if (tb.state) produce(std::true_type{}, tile0 + it, raws[it % RAW_STAGES], tiles[b]);
-            else produce(std::false_type{}, tile0 + it, raws[it % RAW_STAGES], tiles[b]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[b]);
-        }
-        if (async_ok) cp_async_wait<0>();
-        __syncthreads();   // pairs with the consumers' barrier before they park their partial C
-
-        const int pw = warp - NCONS;
-#pragma unroll
-        for (int c = 0; c < NACC * 4; ++c) {
-            double s = cst[c];
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_red[pw][c] = s;
-        }
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) s_cnt[pw] = cnt;
-    }
-    __syncthreads();
-    // C[m][n], m = 2(k-1) + {cos, sin}, n = 2d + {x, y}  ->  (A, B, C, D) of harmonic k, diode d
-    for (int idx = threadIdx.x; idx < 48 * 8; idx += HARM_THREADS) {
-        const int m = idx >> 3, n = idx & 7;
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NCONS; ++w) s += s_cpart[(w * 48 + m) * 8 + n];
-        const int k = m >> 1, sn = m & 1, d = n >> 1, im = n & 1;
-        // (cos, x) -> A = 0, (sin, y) -> B = 1, (cos, y) -> C = 2, (sin, x) -> D = 3
-        const int slot = sn ? (im ? 1 : 3) : (im ? 2 : 0);
-        out[d * HP + NCONST + k * 4 + slot] = s;
-    }
-    if (threadIdx.x < NCONST * 4) {
-        const int d = threadIdx.x / NCONST, c = threadIdx.x % NCONST;
-        unsigned long long cn = 0;
-        for (int w = 0; w < NPROD; ++w) cn += s_cnt[w];
-        double s = 0.0;
-        int src = -1;   // index into the carried sums, or -1: from the state counts
-        if (KIND == 0) {
-            if (c == 1) src = 0;
-            else if (c == 5) src = 1;
-            else if (c == 6) src = 2;
-            else if (OFFS && c == 3) src = 3;
-            else if (OFFS && c == 4) src = 4;
-        } else {
-            src = c;
-        }
-        if (src >= 0) {
-            for (int w = 0; w < NPROD; ++w) s += s_red[w][d * NACC + src];
-        } else if (c == 0 || c == 2) {
-            for (int st = 0; st < 4; ++st) {
-                const double n_s = (double)((cn >> (16 * st)) & 0xffffull);
-                const double2 mw = s_stats[d * 4 + st];
-                if (n_s > 0.0) s += c == 0 ? n_s * mw.y : n_s * (mw.y * (mw.x * mw.x));
-            }
-        }
-        out[d * HP + c] = s;
-    }
-}
-
-// ===========================================================================
-// Warp-synchronous variant: every warp does both jobs on its own 32-row chunks --
-// stage the raw bytes (cp.async, double buffered), turn them into a private 32-row
-// compute tile (one row per lane), run the 8 DMMA k-steps on it -- with no
-// inter-warp hand-over at all in the main loop.  While some warps of a sub-partition
-// are in their latency-bound "produce" phase the others keep the FP64 units busy
-// with DMMAs.
-// ===========================================================================
 constexpr int WS_WARPS = 8;                    // warps per block, two blocks per SM
 constexpr int WS_THREADS = WS_WARPS * 32;
 constexpr int WS_CH = 32;                      // rows per chunk (one per lane)
 constexpr int WS_CHP = WS_CH + 4;              // padded component stride (bank-conflict free)
-constexpr int HARM_SEG_ROWS = TR * HARM_SEG_TILES;
 
 struct WsRaw {                 // raw bytes of one chunk, as copied by cp.async
     uint4 dio[4][WS_CH];
@@ -550,7 +170,10 @@ k_harm_ws(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         ((reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0 && (tv.volt_stride & 15) == 0);
     const bool faint = tb.state != nullptr;
 
-    // consumer-side lane constants (see k_harm_accumulate)
+    // consumer side: lane (m8, r) owns A[m8][r] = trig(k theta_row) of harmonic
+    // k = k0 + 4j in m-tile j (k0 = m8/2 + 1, trig = cos for even m8, sin for odd) and
+    // B[r][m8] = V[row][m8], row = (k-step base) + r;
+    // trig((k0 - 4) t) = +cos((4 - k0) t) or -sin((4 - k0) t); k0 = 4: cos 0 = 1, sin 0 = 0
     const int m8 = lane >> 2, r4 = lane & 3;
     const int k0 = (m8 >> 1) + 1, trig = m8 & 1;
     const int pidx = k0 < 4 ? 2 * (3 - k0) + trig : 0;
@@ -815,34 +438,17 @@ int harm_max_segments(long long max_rows_per_job) { return harm_segments(max_row
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab) {
-    const int smem = HARM_SMEM;
-    cudaFuncSetAttribute(k_harm_accumulate<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_harm_accumulate<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_harm_accumulate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_harm_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+    cudaFuncSetAttribute(k_harm_ws<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
+    cudaFuncSetAttribute(k_harm_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
     dim3 grid(njobs * NGROUP, P);
     const bool offs = (flags & 2u) != 0;
-    static const bool use_ws = getenv("GPPD_HARM_PIPELINE") == nullptr;   // default: warp-synchronous
-    if (use_ws) {
-        cudaFuncSetAttribute(k_harm_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
-        cudaFuncSetAttribute(k_harm_ws<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
-        cudaFuncSetAttribute(k_harm_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
-        if (offs) {
-            k_harm_ws<0, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
-            k_harm_ws<1, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);
-            *L.counter += 2;
-        } else {
-            k_harm_ws<0, false><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
-            *L.counter += 1;
-        }
-    } else if (offs) {
-        k_harm_accumulate<0, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
-                                                                          d_spart1, d_spart2, d_partZ);
-        k_harm_accumulate<1, true><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
-                                                                          d_spart1, d_spart2, d_partY);
+    if (offs) {
+        k_harm_ws<0, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
+        k_harm_ws<1, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);
         *L.counter += 2;
     } else {
-        k_harm_accumulate<0, false><<<grid, HARM_THREADS, smem, L.stream>>>(d_tabs, d_jobs, flags, P, SP,
-                                                                           d_spart1, d_spart2, d_partZ);
+        k_harm_ws<0, false><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
         *L.counter += 1;
     }
     const int nfits = njobs * NDIODE;
