@@ -163,6 +163,23 @@ __device__ __forceinline__ void sincos_moderate(double x, double *sn, double *cs
     *cs = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
 }
 
+// sin and cos of theta = fl(omega t) ~ 3e10 (any |x| < 2^40): two-constant Cody-Waite
+// reduction by 2 pi done with FMAs.  k = rint(x / 2 pi) < 2^38 and x is a multiple of
+// its ulp >= 2^-13... so x - k * fl(2 pi) is a multiple of 2^-50 below 8 in magnitude:
+// the first FMA is exact, the second rounds once; the reduced argument is within one
+// ulp of x mod 2 pi.  The general-purpose sincos() spends ~300 instructions on its
+// Payne-Hanek path for such arguments.
+__device__ __forceinline__ void sincos_large(double x, double *sn, double *cs) {
+    if (!(fabs(x) < 1.099511627776e12)) {   // 2^40
+        sincos(x, sn, cs);
+        return;
+    }
+    const double k = rint(x * 1.59154943091895345554e-01);          // 1 / (2 pi)
+    double r = fma(-k, 6.28318530717958623200e+00, x);               // fl(2 pi)
+    r = fma(-k, 2.44929359829470641435e-16, r);                      // 2 pi - fl(2 pi)
+    sincos_moderate(r, sn, cs);
+}
+
 // Per-state statistics of one (job, group) (reference compute_mean_var_power,
 // src/Faint.jl:89-100): the statistics pass leaves, per (job, group), a table of 16
 // (mean |d|, weight = 1 / var |d|) pairs indexed [diode * 4 + state].

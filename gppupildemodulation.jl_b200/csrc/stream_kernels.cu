@@ -242,51 +242,83 @@ __global__ void k_init_thkeys(unsigned long long *thkeys, int *nvalid, int njobs
     for (int s = 0; s < 4; ++s) nvalid[JOBCNT * j + 1 + s] = 0x7fffffff;
 }
 
-__global__ void k_basis(const TableDesc *tabs, unsigned flags, unsigned long long *thkeys,
-                        int *nvalid) {
-    const TableDesc &tb = tabs[blockIdx.y];
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= tb.tv.n) return;
-    double th = row_theta(tb.tv, i);
-    double s, c;
-    sincos(th, &s, &c);
-    tb.basis[i] = make_double2(s, c);
-    long long job = tb.job0 + i / tb.wrows;
-    unsigned long long key = f64_key(th);
-    int st = ST_NORMAL, valid = 1;
-    if (tb.state) {
-        st = tb.state[i];
-        valid = row_valid(st, flags) ? 1 : 0;
-        // first row of every run of a state: candidates for the job's first row of it
-        const long long il = i - (i / tb.wrows) * tb.wrows;
-        if (valid && st >= 0 && st <= 3 && (il == 0 || tb.state[i - 1] != st))
-            atomicMin(nvalid + JOBCNT * job + 1 + st, (int)il);
+constexpr int BASIS_RPT = 4;          // rows per thread, 1024 per block
+
+__global__ void __launch_bounds__(256) k_basis(const TableDesc *tabs, unsigned flags,
+                                               unsigned long long *thkeys, int *nvalid) {
+    __shared__ unsigned long long s_min[8], s_max[8];
+    __shared__ int s_cnt[8];
+    const TableDesc &tbg = tabs[blockIdx.y];
+    // table description in registers (one round trip instead of one per use)
+    const TableView tv = tbg.tv;
+    const long long n = tv.n, wrows = tbg.wrows;
+    const int job0 = tbg.job0, njobs = tbg.njobs;
+    const int8_t *state = tbg.state;
+    double2 *basis = tbg.basis;
+    const long long base = (long long)blockIdx.x * (256 * BASIS_RPT);
+    if (base >= n) return;
+    // the theta of the thread's rows first (independent loads), then the arithmetic
+    double th[BASIS_RPT];
+#pragma unroll
+    for (int j = 0; j < BASIS_RPT; ++j) {
+        const long long i = base + j * 256 + threadIdx.x;
+        th[j] = i < n ? row_theta(tv, i) : 0.0;
     }
-    // warp-aggregate when a full warp sits in one job
-    unsigned mask = __activemask();
-    if (mask == 0xffffffffu) {
-        long long job0 = __shfl_sync(mask, job, 0);
-        if (__all_sync(mask, job == job0)) {
-            unsigned long long kmin = key, kmax = key;
-            int cnt = valid;
-            for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long a = __shfl_xor_sync(mask, kmin, o);
-                unsigned long long b = __shfl_xor_sync(mask, kmax, o);
-                cnt += __shfl_xor_sync(mask, cnt, o);
-                kmin = a < kmin ? a : kmin;
-                kmax = b > kmax ? b : kmax;
-            }
-            if ((threadIdx.x & 31) == 0) {
-                atomicMin(thkeys + 2 * job, kmin);
-                atomicMax(thkeys + 2 * job + 1, kmax);
-                if (cnt) atomicAdd(nvalid + JOBCNT * job, cnt);
-            }
-            return;
+    const long long last = (base + 256 * BASIS_RPT < n ? base + 256 * BASIS_RPT : n) - 1;
+    const long long jfirst = njobs == 1 ? 0 : base / wrows, jlast = njobs == 1 ? 0 : last / wrows;
+    const bool one_job = jfirst == jlast;          // block-uniform
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < BASIS_RPT; ++j) {
+        const long long i = base + j * 256 + threadIdx.x;
+        if (i >= n) continue;
+        double s, c;
+        sincos_large(th[j], &s, &c);
+        basis[i] = make_double2(s, c);
+        const long long jl = one_job ? jfirst : i / wrows;
+        const unsigned long long key = f64_key(th[j]);
+        int valid = 1;
+        if (state) {
+            const int st = state[i];
+            valid = row_valid(st, flags) ? 1 : 0;
+            // first row of every run of a state: candidates for the job's first row of it
+            const long long il = i - jl * wrows;
+            if (valid && st >= 0 && st <= 3 && (il == 0 || state[i - 1] != st))
+                atomicMin(nvalid + JOBCNT * (job0 + jl) + 1 + st, (int)il);
+        }
+        if (one_job) {
+            kmin = key < kmin ? key : kmin;
+            kmax = key > kmax ? key : kmax;
+            cnt += valid;
+        } else {      // a block straddling jobs (small windows): per-row atomics
+            atomicMin(thkeys + 2 * (job0 + jl), key);
+            atomicMax(thkeys + 2 * (job0 + jl) + 1, key);
+            if (valid) atomicAdd(nvalid + JOBCNT * (job0 + jl), 1);
         }
     }
-    atomicMin(thkeys + 2 * job, key);
-    atomicMax(thkeys + 2 * job + 1, key);
-    if (valid) atomicAdd(nvalid + JOBCNT * job, 1);
+    if (!one_job) return;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o);
+        const unsigned long long b = __shfl_xor_sync(0xffffffffu, kmax, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b > kmax ? b : kmax;
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_min[w] = kmin; s_max[w] = kmax; s_cnt[w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            kmin = s_min[k] < kmin ? s_min[k] : kmin;
+            kmax = s_max[k] > kmax ? s_max[k] : kmax;
+            cnt += s_cnt[k];
+        }
+        const long long job = job0 + jfirst;
+        atomicMin(thkeys + 2 * job, kmin);
+        atomicMax(thkeys + 2 * job + 1, kmax);
+        if (cnt) atomicAdd(nvalid + JOBCNT * job, cnt);
+    }
 }
 
 __global__ void k_jobinfo(const TableDesc *tabs, const unsigned long long *thkeys,
@@ -312,7 +344,7 @@ void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
                   int max_jobs_per_table, int njobs, unsigned flags,
                   unsigned long long *d_thkeys, int *d_nvalid, JobInfo *d_jobs) {
     k_init_thkeys<<<(njobs + 255) / 256, 256, 0, L.stream>>>(d_thkeys, d_nvalid, njobs);
-    k_basis<<<dim3((unsigned)((max_rows + 255) / 256), ntables), 256, 0, L.stream>>>(
+    k_basis<<<dim3((unsigned)((max_rows + 256 * BASIS_RPT - 1) / (256 * BASIS_RPT)), ntables), 256, 0, L.stream>>>(
         d_tabs, flags, d_thkeys, d_nvalid);
     k_jobinfo<<<dim3((max_jobs_per_table + 127) / 128, ntables), 128, 0, L.stream>>>(
         d_tabs, d_thkeys, d_nvalid, d_jobs);
