@@ -590,11 +590,6 @@ __device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned fl
                         __dadd_rn(__dmul_rn(d.y, ca), -__dmul_rn(d.x, sa)));
 }
 
-// Demodulation constants of one fit held in registers by the streaming kernel.
-struct DemodK {
-    double b, alpha, cq, sq, cre, cim;
-};
-
 // One thread per (row, group): 4 diodes + the group's FC channel.  A block walks
 // DM_TPB consecutive tiles of DM_ROWS rows of one table.  Dense float32 tables (the
 // METROLOGY layout) are moved as whole row tiles by the TMA: cp.async.bulk
@@ -612,7 +607,7 @@ constexpr int DM_SMEM_OUT = DM_ROWS * 144 * 4;      // keepraw staging
 constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + DM_SMEM_OUT + 64;
 
 template <bool BE>   // raw FITS byte order of the float32 tables (GPPD_BIG_ENDIAN, a batch-wide flag)
-__global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, const FitResult *results,
+__global__ void __launch_bounds__(DM_THREADS, 3) k_demod(const TableDesc *tabs, const FitResult *results,
                                                          unsigned flags) {
     const TableDesc &tbg = tabs[blockIdx.y];
     // table description in registers (the asm memory clobbers below would otherwise
@@ -684,34 +679,34 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, 
         }
     }
 
-    // fit constants of this thread's 4 diodes (re-read only when the job changes)
-    DemodK kk[4];
-    int uni = 1;
-    long long job_cur = -1;
-    auto load_consts = [&](long long job) {
-        const FitResult *fr = results + ((long long)job0 + job) * NDIODE + group * 4;
-        uni = 1;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const double2 a = *reinterpret_cast<const double2 *>(&fr[d].b);
-            const double2 q = *reinterpret_cast<const double2 *>(&fr[d].cq);
-            kk[d].b = a.x; kk[d].alpha = a.y; kk[d].cq = q.x; kk[d].sq = q.y;
-            kk[d].cre = kk[d].cim = 0.0;
-            if (offs) {
-                const double2 c = *reinterpret_cast<const double2 *>(&fr[d].cre);
-                kk[d].cre = c.x; kk[d].cim = c.y;
-            }
-            uni &= fr[d].uniform;
+    // Fit constants of one job (32 diodes) and the 40 centres live in shared memory: in
+    // registers they cost 68 registers per thread and a third of the occupancy.
+    // (indexed [diode of the group][group]: the 8 groups of a warp read 8 consecutive
+    // 16-byte words, one conflict-free wavefront)
+    __shared__ double2 s_ba[4][NGROUP], s_cs[4][NGROUP], s_cc[4][NGROUP];   // (b, alpha), (cq, sq), c
+    __shared__ int s_uni[4][NGROUP];
+    __shared__ double2 s_off[5][NGROUP];               // centres of the 4 diodes and the FC channel
+    long long job_cached = -1;                         // block-uniform
+    auto cache_job = [&](long long job) {              // called by all threads of the block
+        __syncthreads();                               // the previous job's readers are done
+        if (threadIdx.x < NDIODE) {
+            const FitResult &fr = results[((long long)job0 + job) * NDIODE + threadIdx.x];
+            const int g = threadIdx.x >> 2, d = threadIdx.x & 3;
+            s_ba[d][g] = make_double2(fr.b, fr.alpha);
+            s_cs[d][g] = make_double2(fr.cq, fr.sq);
+            s_cc[d][g] = offs ? make_double2(fr.cre, fr.cim) : make_double2(0.0, 0.0);
+            s_uni[d][g] = fr.uniform;
         }
-        job_cur = job;
+        __syncthreads();
+        job_cached = job;
     };
-    if (njobs == 1) load_consts(0);
-    double2 off[5];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) {
-        const int ch = d < 4 ? group * 4 + d : fc_channel(group);
-        off[d] = offsets ? __ldg(offsets + ch) : make_double2(0.0, 0.0);
+    if (threadIdx.x < NCHAN) {
+        const int ch = threadIdx.x;
+        const int g = ch < NDIODE ? ch >> 2 : ch - NDIODE, d = ch < NDIODE ? ch & 3 : 4;
+        s_off[d][g] = offsets ? __ldg(offsets + ch) : make_double2(0.0, 0.0);
     }
+    if (njobs == 1) cache_job(0);
+    else __syncthreads();
 
 #pragma unroll 1
     for (int k = 0; k < T; ++k) {
@@ -746,13 +741,17 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, 
             __syncthreads();
         }
 
+        // one job per tile (the usual case) -> its constants from shared memory
+        bool tile_one_job = true;
+        if (njobs != 1) {
+            const long long jf = row_base / wrows, jl = (row_base + nrow - 1) / wrows;
+            tile_one_job = jf == jl;
+            if (tile_one_job && jf != job_cached) cache_job(jf);
+        }
+
 #pragma unroll 1
         for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
             const long long i = row_base + rr;
-            if (njobs != 1) {
-                const long long job = i / wrows;
-                if (job != job_cur) load_consts(job);
-            }
             const uint4 w0 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group);
             const uint4 w1 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group + 4);
             const uint2 wf = *reinterpret_cast<const uint2 *>(s_in + rr * 80 + 64 + 2 * group);
@@ -761,26 +760,32 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_demod(const TableDesc *tabs, 
             const double2 sc = s_basis[rr];
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
+                const int ch = d < 4 ? group * 4 + d : fc_channel(group);
                 uint32_t a = raw[2 * d], b = raw[2 * d + 1];
                 if (be_in) { a = bswap32(a); b = bswap32(b); }
-                double vr = (double)__uint_as_float(a) - off[d].x;
-                double vi = (double)__uint_as_float(b) - off[d].y;
+                const double2 off = s_off[d][group];
+                double vr = (double)__uint_as_float(a) - off.x;
+                double vi = (double)__uint_as_float(b) - off.y;
                 double2 o;
                 if (d == 4) {
                     o = make_double2(vr, vi);                       // centred FC channel, :170-171
-                } else if (recenter && uni) {
+                } else if (recenter && tile_one_job && s_uni[d][group]) {
                     // psi = fl(fl(b sin(theta + q)) + alpha) - alpha), out = (d - c) exp(-j psi)
-                    const double sn = fma(sc.x, kk[d].cq, sc.y * kk[d].sq);
-                    const double gp = __dadd_rn(__dmul_rn(kk[d].b, sn), kk[d].alpha);
-                    const double psi = __dadd_rn(gp, -kk[d].alpha);
+                    const double2 ba = s_ba[d][group], cs = s_cs[d][group];
+                    const double sn = fma(sc.x, cs.x, sc.y * cs.y);
+                    const double gp = __dadd_rn(__dmul_rn(ba.x, sn), ba.y);
+                    const double psi = __dadd_rn(gp, -ba.y);
                     double sp, cp;
                     sincos_moderate(psi, &sp, &cp);
-                    vr -= kk[d].cre;
-                    vi -= kk[d].cim;
+                    if (offs) {
+                        const double2 cc = s_cc[d][group];
+                        vr -= cc.x;
+                        vi -= cc.y;
+                    }
                     o = make_double2(fma(vr, cp, vi * sp), fma(vi, cp, -(vr * sp)));
-                } else {
+                } else {     // tile straddling two jobs, no uniform quantum, or recenter = false
                     const FitResult *fr = results + ((long long)job0 + i / wrows) * NDIODE;
-                    o = demod_sample(fr[group * 4 + d], flags, row_theta(tbg.tv, i), sc, make_double2(vr, vi));
+                    o = demod_sample(fr[ch], flags, row_theta(tbg.tv, i), sc, make_double2(vr, vi));
                 }
                 a = __float_as_uint(__double2float_rn(o.x));
                 b = __float_as_uint(__double2float_rn(o.y));
