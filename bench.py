@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--window-rows", type=int, default=0,
                     help="fit windows of this many rows instead of whole tables (reference --window); "
                          "an exploration switch, the headline workload is whole-file")
+    ap.add_argument("--chains", type=int, default=1,
+                    help="exploration: split the resident night into this many concurrent launch sequences")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -279,10 +281,41 @@ def main():
 
     bench_stream = torch.cuda.Stream(device=dev)   # a real (non-NULL) stream: events see it
 
+    NCH = max(1, min(args.chains, h.num_slots, F))
+    chain_streams = [torch.cuda.Stream(device=dev) for _ in range(NCH)] if NCH > 1 else []
+
+    def sub(arr, idx, typ):
+        return None if arr is None else (typ * len(idx))(*[arr[i] for i in idx])
+
+    chains = []
+    for c in range(NCH):
+        idx = list(range(c, F, NCH))
+        chains.append(dict(n=len(idx), b_n=sub(b_n, idx, C.c_int64), b_w=sub(b_w, idx, C.c_int64),
+                           b_time=sub(b_time, idx, C.c_void_p), b_mjd=sub(b_mjd, idx, C.c_double),
+                           b_volt=sub(b_volt, idx, C.c_void_p), b_t1=sub(b_t1, idx, _lib._dp),
+                           b_n1=sub(b_n1, idx, C.c_int64), b_t2=sub(b_t2, idx, _lib._dp),
+                           b_n2=sub(b_n2, idx, C.c_int64), b_out=sub(b_out, idx, C.c_void_p),
+                           b_par=sub(b_par, idx, C.c_void_p), b_chi=sub(b_chi, idx, C.c_void_p),
+                           b_info=sub(b_info, idx, C.c_void_p)))
+
     def step_resident():
-        _lib.check(L.gppd_process_tables_f32_dev(
-            h.raw, 0, C.c_void_p(bench_stream.cuda_stream), F, b_n, b_w, b_time, b_mjd, b_volt, p(offsets),
-            b_t1, b_n1, b_t2, b_n2, C.byref(opt), b_out, b_par, b_chi, b_info, None))
+        if NCH == 1:
+            _lib.check(L.gppd_process_tables_f32_dev(
+                h.raw, 0, C.c_void_p(bench_stream.cuda_stream), F, b_n, b_w, b_time, b_mjd, b_volt, p(offsets),
+                b_t1, b_n1, b_t2, b_n2, C.byref(opt), b_out, b_par, b_chi, b_info, None))
+            return
+        fork = torch.cuda.Event()
+        fork.record(bench_stream)
+        for c, ch in enumerate(chains):
+            st = chain_streams[c]
+            st.wait_event(fork)
+            _lib.check(L.gppd_process_tables_f32_dev(
+                h.raw, c, C.c_void_p(st.cuda_stream), ch["n"], ch["b_n"], ch["b_w"], ch["b_time"],
+                ch["b_mjd"], ch["b_volt"], p(offsets), ch["b_t1"], ch["b_n1"], ch["b_t2"], ch["b_n2"],
+                C.byref(opt), ch["b_out"], ch["b_par"], ch["b_chi"], ch["b_info"], None))
+            ev = torch.cuda.Event()
+            ev.record(st)
+            bench_stream.wait_event(ev)
 
     def barrier():
         torch.cuda.synchronize()

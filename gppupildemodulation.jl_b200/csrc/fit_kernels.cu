@@ -225,7 +225,7 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
 
 // the solver's 49-angle table (newuoa2.cuh), filled by the first 50 threads of a block
 __device__ __forceinline__ void fill_angle_table(NuSinCos *tab) {
-    if (threadIdx.x <= NU_ANGLES) nu_angle_entry(threadIdx.x, &tab[threadIdx.x]);
+    for (int i = threadIdx.x; i <= NU_ANGLES; i += blockDim.x) nu_angle_entry(i, &tab[i]);
 }
 
 // ---- one warp per fit ---------------------------------------------------------
@@ -256,7 +256,8 @@ __device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitC
     return true;
 }
 
-constexpr int FITW_WARPS = 4;   // fits per block
+constexpr int FITW_WARPS = 1;   // fits per block: fits differ 4x in length (25..131 objective
+                                // calls), a block would wait for its slowest one
 
 template <bool OFFS>
 __global__ void __launch_bounds__(FITW_WARPS * 32)
