@@ -934,6 +934,11 @@ struct Newuoa2T {
         NU_ROLLED for (int k = 1; k <= NPT; ++k) pq[k] = zero;
         for (int k = 0; k <= NPT; ++k) fval[k] = zero;
         for (int k = 0; k <= N; ++k) gq[k] = zero;
+        // the rest of the work space starts from zero as well (the oracle's is calloc'ed):
+        // with maxfun < npt the solver returns xbase + xopt before xopt is ever assigned
+        for (int k = 0; k <= N; ++k) xopt[k] = xnew[k] = d[k] = zero;
+        for (int k = 0; k <= NDIM; ++k) vlag[k] = zero;
+        for (int k = 0; k <= 2 * NDIM + 2 * NPT; ++k) w[k] = zero;
         rhosq = rhobeg * rhobeg;
         recip = one / rhosq;
         reciq = sqrt(half) / rhosq;
