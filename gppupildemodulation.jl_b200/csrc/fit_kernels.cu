@@ -191,7 +191,7 @@ __device__ __forceinline__ void load_lane(const double *H, int nfits, int lane, 
 }
 
 // ---- one thread per fit: the 32 lane terms one after the other, added in the order of
-// the warp kernel's xor butterfly (o = 16, 8, 4, 2, 1)
+// the warp kernel's xor butterfly (o = 1, 2, 4, 8, 16)
 template <bool OFFS>
 __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const FitConsts &kc,
                                               const JobInfo &ji, double b, double phi, double &f,
@@ -204,22 +204,27 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
     sincos_moderate(q, &sq, &cq);
     QPowers P;
     q_powers(cq, sq, P);
-    double t[4][32];
+    // pairwise summation in the order of the warp kernel's butterfly (xor 1, 2, 4, 8, 16):
+    // lanes stream in, a 6-level carry stack merges equal-sized partial sums
+    double st[6][4];
 #pragma unroll 1
-    for (int lane = 0; lane <= HK; ++lane) {
-        HarmLane h;
-        load_lane<OFFS>(H, nfits, lane, h);
-        lane_terms<OFFS>(lane, J[lane], P, h, t[0][lane], t[1][lane], t[2][lane], t[3][lane]);
+    for (int lane = 0; lane < 32; ++lane) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};     // the warp kernel's idle lanes contribute +0.0
+        if (lane <= HK) {
+            HarmLane h;
+            load_lane<OFFS>(H, nfits, lane, h);
+            lane_terms<OFFS>(lane, J[lane], P, h, v[0], v[1], v[2], v[3]);
+        }
+        int lvl = 0;
+        for (int idx = lane; idx & 1; idx >>= 1, ++lvl) {
+#pragma unroll
+            for (int c = 0; c < (OFFS ? 4 : 2); ++c) v[c] = st[lvl][c] + v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < (OFFS ? 4 : 2); ++c) st[lvl][c] = v[c];
     }
-#pragma unroll 1
-    for (int lane = HK + 1; lane < 32; ++lane)   // the warp kernel's idle lanes contribute +0.0
-        t[0][lane] = t[1][lane] = t[2][lane] = t[3][lane] = 0.0;
-#pragma unroll 1
-    for (int v = 0; v < (OFFS ? 4 : 2); ++v)
-        for (int o = 16; o > 0; o >>= 1)
-            for (int i = 0; i < o; ++i) t[v][i] = t[v][i] + t[v][i + o];
-    f = solve_linear(kc, OFFS, t[0][0], t[1][0], OFFS ? t[2][0] : 0.0, OFFS ? t[3][0] : 0.0, cre, cim,
-                     are, aim);
+    f = solve_linear(kc, OFFS, st[5][0], st[5][1], OFFS ? st[5][2] : 0.0, OFFS ? st[5][3] : 0.0, cre,
+                     cim, are, aim);
     return true;
 }
 
@@ -244,7 +249,7 @@ __device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitC
     double tr, ti, ur, ui;
     lane_terms<OFFS>(lane, J, P, h, tr, ti, ur, ui);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {   // fixed-order butterfly: every lane gets the same bits
+    for (int o = 1; o < 32; o <<= 1) {   // fixed-order butterfly: every lane gets the same bits
         tr += __shfl_xor_sync(0xffffffffu, tr, o);
         ti += __shfl_xor_sync(0xffffffffu, ti, o);
         if (OFFS) {
