@@ -188,7 +188,7 @@ __device__ __forceinline__ void sincos_large(double x, double *sn, double *cs) {
 //       per (diode, state); the pivot is |d| at the job's first row of the state
 //   table[jg*16 + diode*4 + state] = (mean, weight), segments added in index order,
 // so the values are deterministic and independent of the batch the job is in.
-constexpr int STATS_SEG_ROWS = 4096;
+constexpr int STATS_SEG_ROWS = 1024;
 __host__ __device__ inline int stats_segments(long long nrows) {
     return (int)((nrows + STATS_SEG_ROWS - 1) / STATS_SEG_ROWS);
 }

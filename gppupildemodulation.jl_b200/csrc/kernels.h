@@ -34,7 +34,7 @@ void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_j
 
 // Jacobi-Anger harmonic sums of every fit + reduction into the harmonic table
 int harm_max_segments(long long max_rows_per_job);   // fixed 12288-row segments
-int stats_max_segments(long long max_rows_per_job);  // fixed 4096-row segments
+int stats_max_segments(long long max_rows_per_job);  // fixed 1024-row segments
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab);

@@ -360,43 +360,48 @@ void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
 // cancellation of raw moments.  One block per (job, group, FIXED segment of
 // STATS_SEG_ROWS rows); k_stats_final adds the segments of a job in index order.
 // ===========================================================================
-constexpr int STATS_THREADS = 256;
-constexpr int STATS_RPT = STATS_SEG_ROWS / STATS_THREADS;   // rows per thread
+// |d| of one sample (sqrt() is correctly rounded; an rsqrt-based form measured slower)
+__device__ __forceinline__ double abs_fast(double2 d) { return sqrt(fma(d.x, d.x, d.y * d.y)); }
+
+constexpr int STATS_THREADS = 256;                          // 32 rows x 8 groups per iteration
+constexpr int STATS_ITERS = STATS_SEG_ROWS / 32;            // iterations per segment
 constexpr int STATS_BATCH = 4;                              // rows loaded ahead of their use
 
-// A warp walks 32 consecutive rows at a time; states come in runs of hundreds of
-// rows, so the warp keeps the sums of ONE state in registers (9 doubles per lane) and
-// folds them into its shared-memory totals when the state changes (mixed 32-row
-// groups, i.e. run boundaries, take the states one after the other).
-__global__ void __launch_bounds__(STATS_THREADS, 3)
+// One block per (job, segment) for all 8 groups; thread (row lane, group) like the
+// demod pass, so that a warp reads 4 rows x 256 contiguous bytes.  States come in runs
+// of hundreds of rows: a thread keeps the sums of ONE state in registers (9 doubles)
+// and folds them into the warp's shared-memory totals when the warp's state changes
+// (32-row groups that straddle a run boundary take the states one after the other).
+__global__ void __launch_bounds__(STATS_THREADS, 2)
 k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, const int *jobcnt,
             unsigned flags, int P, double *part) {
-    __shared__ double s_piv[16];
-    __shared__ double s_acc[STATS_THREADS / 32][STATS_VALS];
+    __shared__ double s_piv[NGROUP][16];
+    __shared__ double s_acc[STATS_THREADS / 32][NGROUP][STATS_VALS];
     const int p = blockIdx.y;
-    const int job = faint_jobs[blockIdx.x >> 3], group = blockIdx.x & 7;
-    const int jg = job * NGROUP + group;
+    const int job = faint_jobs[blockIdx.x];
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
     if (!tb.state) return;
     const long long seg0 = (long long)p * STATS_SEG_ROWS;
     if (seg0 >= ji.nrows) return;
     const int nseg = (int)((ji.nrows - seg0) < STATS_SEG_ROWS ? (ji.nrows - seg0) : STATS_SEG_ROWS);
-    const TableView &tv = tb.tv;
+    const TableView tv = tb.tv;
+    const int8_t *state = tb.state;
     const bool vec = tv.kind == 0 && !tv.big_endian && (tv.volt_stride & 15) == 0 &&
                      (reinterpret_cast<unsigned long long>(tv.volt) & 15ull) == 0;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 16) {   // pivots
-        const int dio = threadIdx.x >> 2, st = threadIdx.x & 3;
+    const int rl = threadIdx.x >> 3, group = threadIdx.x & 7;
+    if (threadIdx.x < 128) {   // pivots: |d| at the job's first row of each state
+        const int g = threadIdx.x >> 4, dio = (threadIdx.x >> 2) & 3, st = threadIdx.x & 3;
         const int first = jobcnt[JOBCNT * job + 1 + st];
         double pv = 0.0;
         if (first != 0x7fffffff) {
-            const double2 d = row_sample(tv, ji.row0 + first, group * 4 + dio);
-            pv = sqrt(fma(d.x, d.x, d.y * d.y));
+            pv = abs_fast(row_sample(tv, ji.row0 + first, g * 4 + dio));
         }
-        s_piv[threadIdx.x] = pv;
+        s_piv[g][dio * 4 + st] = pv;
     }
-    for (int k = lane; k < STATS_VALS; k += 32) s_acc[w][k] = 0.0;
+    for (int k = threadIdx.x; k < (STATS_THREADS / 32) * NGROUP * STATS_VALS; k += STATS_THREADS)
+        (&s_acc[0][0][0])[k] = 0.0;
     double2 off[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
@@ -407,19 +412,23 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
     double a1[4], a2[4], ac = 0.0;
 #pragma unroll
     for (int d = 0; d < 4; ++d) a1[d] = a2[d] = 0.0;
-    // registers -> the warp's shared totals: [0..3] counts, [4..19] S1, [20..35] S2
+    // registers -> the warp's shared totals: [0..3] counts, [4..19] S1, [20..35] S2 per group;
+    // the 4 rows a warp holds per group are lanes g, g + 8, g + 16, g + 24
     auto flush = [&]() {
         if (cur < 0) return;
         double v[9] = {ac, a1[0], a1[1], a1[2], a1[3], a2[0], a2[1], a2[2], a2[3]};
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
-            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-        if (lane == 0) {
-            s_acc[w][cur] += v[0];
+        for (int k = 0; k < 9; ++k) {
+            v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+            v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+        }
+        if (lane < NGROUP) {
+            double *acc = s_acc[w][lane];
+            acc[cur] += v[0];
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                s_acc[w][4 + d * 4 + cur] += v[1 + d];
-                s_acc[w][20 + d * 4 + cur] += v[5 + d];
+                acc[4 + d * 4 + cur] += v[1 + d];
+                acc[20 + d * 4 + cur] += v[5 + d];
             }
         }
         ac = 0.0;
@@ -428,13 +437,12 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
     };
 
 #pragma unroll 1
-    for (int j0 = 0; j0 < STATS_RPT; j0 += STATS_BATCH) {
-        // the loads of a batch of rows are issued before their first use
+    for (int j0 = 0; j0 < STATS_ITERS; j0 += STATS_BATCH) {
         float4 ra[STATS_BATCH], rb[STATS_BATCH];
         int rs[STATS_BATCH];
 #pragma unroll
         for (int j = 0; j < STATS_BATCH; ++j) {
-            const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
+            const int i = (j0 + j) * 32 + rl;
             rs[j] = -1;
             if (i < nseg) {
                 const long long r = ji.row0 + seg0 + i;
@@ -444,13 +452,13 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
                     ra[j] = __ldg(q);
                     rb[j] = __ldg(q + 1);
                 }
-                const int st = tb.state[r];
+                const int st = state[r];
                 rs[j] = (row_valid(st, flags) && st >= 0 && st <= 3) ? st : -1;
             }
         }
 #pragma unroll
         for (int j = 0; j < STATS_BATCH; ++j) {
-            const int i = threadIdx.x + (j0 + j) * STATS_THREADS;
+            const int i = (j0 + j) * 32 + rl;
             const int st = rs[j];
             double x[4] = {0.0, 0.0, 0.0, 0.0};
             if (st >= 0) {
@@ -467,7 +475,7 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
                 }
 #pragma unroll
                 for (int dio = 0; dio < 4; ++dio)
-                    x[dio] = sqrt(fma(dd[dio].x, dd[dio].x, dd[dio].y * dd[dio].y)) - s_piv[dio * 4 + st];
+                    x[dio] = abs_fast(dd[dio]) - s_piv[group][dio * 4 + st];
             }
             const int st0 = __shfl_sync(0xffffffffu, st, 0);
             if (__all_sync(0xffffffffu, st == st0)) {        // the usual case: one state (or no valid row)
@@ -480,7 +488,7 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
                         a2[dio] = fma(x[dio], x[dio], a2[dio]);
                     }
                 }
-            } else {                                          // a run boundary inside the 32 rows
+            } else {                                          // a run boundary inside the warp's 4 rows
 #pragma unroll 1
                 for (int s = 0; s < 4; ++s) {
                     if (!__any_sync(0xffffffffu, st == s)) continue;
@@ -499,11 +507,12 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
     }
     flush();
     __syncthreads();
-    if (threadIdx.x < STATS_VALS) {
-        double v = 0.0;
+    for (int k = threadIdx.x; k < NGROUP * STATS_VALS; k += STATS_THREADS) {
+        const int g = k / STATS_VALS, v = k - g * STATS_VALS;
+        double sum = 0.0;
 #pragma unroll
-        for (int j = 0; j < STATS_THREADS / 32; ++j) v += s_acc[j][threadIdx.x];
-        part[((long long)jg * P + p) * STATS_VALS + threadIdx.x] = v;
+        for (int j = 0; j < STATS_THREADS / 32; ++j) sum += s_acc[j][g][v];
+        part[((long long)(job * NGROUP + g) * P + p) * STATS_VALS + v] = sum;
     }
 }
 
@@ -528,8 +537,7 @@ __global__ void k_stats_final(const TableDesc *tabs, const JobInfo *jobs, const 
     double pv = 0.0;
     const int first = jobcnt[JOBCNT * job + 1 + st];
     if (first != 0x7fffffff) {
-        const double2 d = row_sample(tb.tv, ji.row0 + first, group * 4 + (ds >> 2));
-        pv = sqrt(fma(d.x, d.x, d.y * d.y));
+        pv = abs_fast(row_sample(tb.tv, ji.row0 + first, group * 4 + (ds >> 2)));
     }
     // mean of an empty state: 0/0 = NaN like Julia's mean of an empty vector;
     // weight = 1 / var = (n - 1) / sum (x - mean)^2   (n == 1 -> 0/0 = NaN as in Julia)
@@ -545,7 +553,7 @@ void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_j
                   const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
                   double *d_part, double *d_table) {
     if (nfaint <= 0) return;
-    dim3 grid(nfaint * NGROUP, P);
+    dim3 grid(nfaint, P);
     k_stats_seg<<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt, flags, P,
                                                      d_part);
     const int njg = njobs * NGROUP;
