@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libgppd.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0
-ONLYHIGH, FITOFFSETS, NO_RECENTER, KEEPRAW, BIG_ENDIAN = 1, 2, 4, 8, 16
+ONLYHIGH, FITOFFSETS, NO_RECENTER, KEEPRAW, BIG_ENDIAN, CENTER_EMPIRICAL = 1, 2, 4, 8, 16, 32
 METHOD_AUTO, METHOD_DIRECT, METHOD_HARMONIC = 0, 1, 2
 INFO_STRIDE = 4
 TRACE_MAX = 160
@@ -79,6 +79,7 @@ def lib():
         _dp, C.c_int64, _dp, C.c_int64, C.c_double, C.POINTER(Options), C.c_void_p, _dp, _dp,
         _i32p, _i8p]
     L.gppd_wait.argtypes = [H, C.c_int]
+    L.gppd_centres.argtypes = [H, C.c_int, C.c_int64, _dp]
     L.gppd_num_slots.argtypes = [H]
     L.gppd_process_table_f32_dev.argtypes = [
         H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
@@ -96,7 +97,7 @@ def lib():
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
-                 "gppd_submit_fits_rows",
+                 "gppd_submit_fits_rows", "gppd_centres",
                  "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",
                  "gppd_process_tables_f32_dev", "gppd_enable_timing",
                  "gppd_pass_times", "gppd_measure_fp64_peak"):

@@ -133,10 +133,11 @@ def buildstates(faintstates: FaintStates, timestamp, lag: int = 0, preswitchdela
 
 
 def _options(onlyhigh=False, fitoffsets=False, recenter=True, keepraw=False, init="auto",
-             method="auto", maxfun=0) -> Options:
+             method="auto", maxfun=0, empirical=False) -> Options:
     o = Options()
     o.flags = ((_lib.ONLYHIGH if onlyhigh else 0) | (_lib.FITOFFSETS if fitoffsets else 0) |
-               (0 if recenter else _lib.NO_RECENTER) | (_lib.KEEPRAW if keepraw else 0))
+               (0 if recenter else _lib.NO_RECENTER) | (_lib.KEEPRAW if keepraw else 0) |
+               (_lib.CENTER_EMPIRICAL if empirical else 0))
     o.method = {"auto": _lib.METHOD_AUTO, "direct": _lib.METHOD_DIRECT,
                 "harmonic": _lib.METHOD_HARMONIC}[method]
     o.maxfun = int(maxfun)
@@ -223,18 +224,23 @@ def table_windows(time_us, mjd, window):
 
 def process_table(time_us, volt, mjd, offsets=None, faintparam: FaintStates | None = None,
                   window=None, keepraw=False, onlyhigh=False, method="auto", maxfun=0,
-                  handle=None):
+                  handle=None, centres_out=None):
     """Array-level fast path (C ABI ``gppd_process_table_f32``): returns
-    (volt_out float32 (N, 80|144), params (nwin*32, 6), chi2, info, state|None)."""
+    (volt_out float32 (N, 80|144), params (nwin*32, 6), chi2, info, state|None).
+    ``offsets``: (40,) complex128 centres, ``None`` (fit the centres) or ``True``
+    (empirical circle centres, fitted on the device; ``centres_out``, a (40,)
+    complex128 array, then receives them)."""
     h = handle or _lib.default_handle()
     tu = np.ascontiguousarray(time_us, dtype=np.int32)
     v = np.ascontiguousarray(volt, dtype=np.float32)
     n = tu.size
     if v.shape != (n, 80):
         raise ValueError("VOLT must be (N, 80) float32")
-    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.complex128)
+    empirical = offsets is True
+    off = None if (offsets is None or empirical) else np.ascontiguousarray(offsets, dtype=np.complex128)
     _, nwin = table_windows(tu, mjd, window)
-    o = _options(onlyhigh=onlyhigh, keepraw=keepraw, method=method, maxfun=maxfun)
+    o = _options(onlyhigh=onlyhigh, keepraw=keepraw, method=method, maxfun=maxfun,
+                 empirical=empirical)
     vout = np.empty((n, 144 if keepraw else 80), dtype=np.float32)
     params = np.empty((nwin * 32, 6))
     chi2 = np.empty(nwin * 32)
@@ -248,6 +254,10 @@ def process_table(time_us, volt, mjd, offsets=None, faintparam: FaintStates | No
         0 if t1 is None else t1.size, ptr(t2), 0 if t2 is None else t2.size,
         float(window or 0.0), C.byref(o), ptr(vout, _lib._fp), ptr(params), ptr(chi2),
         ptr(info, _lib._i32p), ptr(state, _lib._i8p)))
+    if empirical and centres_out is not None:
+        c = np.empty(40, dtype=np.complex128)
+        check(lib().gppd_centres(h.raw, 0, 1, ptr(c.view(np.float64))))
+        centres_out[:] = c
     return vout, params, chi2, info, state
 
 
@@ -308,14 +318,17 @@ def processmetrology(table, mjd, window=None, faintparam: FaintStates | None = N
 
     ``table``: mapping with the METROLOGY columns ``TIME`` (N,) int32 and ``VOLT``
     (N, 80) float32 (other columns are passed through).  ``offsets``: (40,)
-    complex128 centres, ``False`` (fit the centres) or ``True`` (empirical circle
-    fit: ``Circle`` is undefined in the reference, :108/:120, so this raises as
-    the reference does)."""
-    if offsets is True:
-        raise NameError("Circle not defined (--center empirical is broken in the reference)")
+    complex128 centres, ``False`` (fit the centres) or ``True`` (the default:
+    empirical centres, ``compute_offsets`` :105-125 -- one least-squares circle per
+    channel over the HIGH samples of a FAINT table, all samples otherwise.  The
+    reference throws here because its ``Circle`` is undefined; this is the algebraic
+    circle fit that call stands for)."""
     out = dict(table)
     hdr = {}
-    off = None if offsets is False else np.asarray(offsets, dtype=np.complex128)
+    if offsets is True:
+        off = True
+    else:
+        off = None if offsets is False else np.asarray(offsets, dtype=np.complex128)
     fitoffsets = off is None
     vout, params, chi2, info, state = process_table(
         table["TIME"], table["VOLT"], mjd, offsets=off, faintparam=faintparam, window=window,

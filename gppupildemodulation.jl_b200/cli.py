@@ -118,7 +118,9 @@ class NightScheduler:
 
     def __init__(self, handle, offsets, onlyhigh, method="auto"):
         self.h, self.L = handle, _lib.lib()
-        self.offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.complex128)
+        self.empirical = offsets is True       # --center empirical: centres fitted on the device
+        self.offsets = (None if (offsets is None or self.empirical)
+                        else np.ascontiguousarray(offsets, dtype=np.complex128))
         self.onlyhigh, self.method = onlyhigh, method
         self.nslots = handle.num_slots
         self.busy = [None] * self.nslots       # (job, buffers) per slot
@@ -158,7 +160,8 @@ class NightScheduler:
         params = np.empty((nwin * 32, 6))
         chi2 = np.empty(nwin * 32)
         state = np.empty(n, dtype=np.int8) if job.faintparam is not None else None
-        o = _options(onlyhigh=self.onlyhigh, keepraw=job.keepraw, method=self.method)
+        o = _options(onlyhigh=self.onlyhigh, keepraw=job.keepraw, method=self.method,
+                     empirical=self.empirical)
         fp = job.faintparam
         t1 = fp.timer1 if fp is not None else None
         t2 = fp.timer2 if fp is not None else None
@@ -178,7 +181,7 @@ class NightScheduler:
         self.busy[slot] = None
         _lib.check(self.L.gppd_wait(self.h.raw, slot))
         n = job.n
-        fitoffsets = self.offsets is None
+        fitoffsets = self.offsets is None and not self.empirical
         records = b["rows_out"].reshape(n, b["rb_out"])
         keys, newcols = [], []
         if job.window is None:
@@ -243,8 +246,8 @@ def main(argv=None) -> int:
         offsets = read_stefan_file()
     elif args.center == "uncentered":
         offsets = np.zeros(40, dtype=np.complex128)
-    elif args.center == "empirical":
-        raise NameError("Circle not defined (--center empirical is broken in the reference)")
+    elif args.center == "empirical":     # offsets = true: compute_offsets, :105-125
+        offsets = True
     elif args.center == "fit":
         offsets = None
     else:

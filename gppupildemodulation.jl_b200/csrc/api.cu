@@ -92,6 +92,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     // staging of caller data (host-buffer entry points)
     DevBuf time, volt, volt_out, t, data, out, state_in, offsets, rows, rows_out;
+    DevBuf centres, cpart;          // --center empirical: [T][40] complex128 + partial sums
+    int ncentres = 0;               // tables whose centres the last batch of this slot fitted
     DevBuf params, chi2, info, trace, state_out;
     // batch scratch
     DevBuf state, basis, z, y, thkeys, nvalid, jobs, results;
@@ -234,6 +236,11 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     }
     const int njobs = (int)njobs_ll, nfits = njobs * NDIODE, njg = njobs * NGROUP;
     const bool offs = (fo.flags & GPPD_FITOFFSETS) != 0;
+    const bool empirical = (fo.flags & GPPD_CENTER_EMPIRICAL) != 0 && !segment_only;
+    if (empirical && offs) {
+        g_last_error = "GPPD_CENTER_EMPIRICAL and GPPD_FITOFFSETS exclude each other";
+        return GPPD_ERR_ARG;
+    }
     const bool direct = method == GPPD_METHOD_DIRECT;
 
     // partial sums are taken over FIXED row segments of each job (so that a fit's
@@ -274,6 +281,23 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
             if ((rc = s.htab.ensure(sizeof(double) * HV_COUNT * (size_t)nfits))) return rc;
             if ((rc = s.fbq.ensure(sizeof(int) * ((size_t)nfits + 1)))) return rc;
         }
+    }
+
+    s.ncentres = 0;
+    if (empirical) {
+        // offsets === true: every table gets its own 40 centres, fitted on the device
+        if ((rc = s.centres.ensure(sizeof(double2) * NCHAN * (size_t)T))) return rc;
+        if ((rc = s.cpart.ensure(sizeof(double) * CIRC_VALS * NCHAN * (size_t)T *
+                                 circle_max_segments(max_rows))))
+            return rc;
+        for (int t = 0; t < T; ++t) {
+            if (td[t].tv.kind != 0) {
+                g_last_error = "GPPD_CENTER_EMPIRICAL applies to METROLOGY tables only";
+                return GPPD_ERR_ARG;
+            }
+            td[t].tv.offsets = s.centres.as<double2>() + (size_t)t * NCHAN;
+        }
+        s.ncentres = T;
     }
 
     // ---- carve per-table slices, upload descriptors ---------------------------
@@ -338,6 +362,11 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         CK(cudaGetLastError());
         return GPPD_OK;
     }
+    if (empirical) {
+        PassScope ps(h, s, stream, GPPD_PASS_BASIS);
+        launch_circle(L, d_tabs, T, max_rows, s.cpart.as<double>());
+    }
+    DBG(stream, "centres");
     {
         PassScope ps(h, s, stream, GPPD_PASS_BASIS);
         launch_basis(L, d_tabs, T, max_rows, max_jobs, njobs, fo.flags,
@@ -399,6 +428,14 @@ int check_handle(gppd_handle h) {
     }
     CK(cudaSetDevice(h->device));
     return GPPD_OK;
+}
+
+// offsets of processmetrology (src/GPPupilDemodulation.jl:150-157): a vector => subtract it;
+// true (GPPD_CENTER_EMPIRICAL) => circle centres fitted here; false (NULL) => fitoffsets
+void centre_mode(gppd_options &o, bool have_offsets) {
+    if (o.flags & GPPD_CENTER_EMPIRICAL) o.flags &= ~GPPD_FITOFFSETS;
+    else if (!have_offsets) o.flags |= GPPD_FITOFFSETS;
+    else o.flags &= ~GPPD_FITOFFSETS;
 }
 
 void table_views(int64_t n, double mjd, const int32_t *d_time, const float *d_volt,
@@ -537,6 +574,21 @@ int gppd_free_pinned(gppd_handle h, void *p) {
 }
 
 int gppd_num_slots(gppd_handle) { return NSLOTS; }
+
+int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS || !centres || ntables < 1) return GPPD_ERR_ARG;
+    Slot &s = h->slots[slot];
+    if (ntables > s.ncentres) {
+        g_last_error = "centres: the last call on this slot fitted fewer tables' centres";
+        return GPPD_ERR_ARG;
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaMemcpy(centres, s.centres.p, sizeof(double2) * NCHAN * (size_t)ntables,
+                  cudaMemcpyDeviceToHost));
+    return GPPD_OK;
+}
 
 int64_t gppd_launch_count(gppd_handle h) { return h ? h->launches : 0; }
 
@@ -740,8 +792,7 @@ int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n, const int32_t *tim
     gppd_options o;
     memset(&o, 0, sizeof o);
     if (opt) o = *opt;
-    if (!offsets) o.flags |= GPPD_FITOFFSETS;   // offsets === false  => fitoffsets, :156
-    else o.flags &= ~GPPD_FITOFFSETS;
+    centre_mode(o, offsets != nullptr);
     int64_t wrows = n, nwin = 1;
     if ((rc = gppd_table_windows(n, time_us, mjd, window_s, &wrows, &nwin))) return rc;
     size_t nfits = (size_t)nwin * NDIODE;
@@ -804,8 +855,7 @@ int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, 
     gppd_options o;
     memset(&o, 0, sizeof o);
     if (opt) o = *opt;
-    if (!offsets) o.flags |= GPPD_FITOFFSETS;
-    else o.flags &= ~GPPD_FITOFFSETS;
+    centre_mode(o, offsets != nullptr);
     o.flags &= ~GPPD_BIG_ENDIAN;    // the unpack pass delivers little-endian arrays
     const int out_floats = (o.flags & GPPD_KEEPRAW) ? 144 : 80;
     const int64_t row_bytes_out = row_bytes + 4 * (out_floats - 80);
@@ -905,8 +955,7 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
     gppd_options o;
     memset(&o, 0, sizeof o);
     if (opt) o = *opt;
-    if (!d_offsets) o.flags |= GPPD_FITOFFSETS;
-    else o.flags &= ~GPPD_FITOFFSETS;
+    centre_mode(o, d_offsets != nullptr);
     Slot &s = h->slots[slot];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
     std::vector<TableArgs> tabs((size_t)ntables);
@@ -938,7 +987,8 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
     // so that one launch of each pass covers the whole batch and per-pass timings stay
     // unambiguous)
     static const bool split = getenv("GPPD_SPLIT_CHAINS") != nullptr;
-    if (faint.empty() || bright.empty() || !split) return run_batch(h, s, st, tabs, &o, nullptr, false);
+    if (faint.empty() || bright.empty() || !split || (o.flags & GPPD_CENTER_EMPIRICAL))
+        return run_batch(h, s, st, tabs, &o, nullptr, false);
     Slot &sb = h->aux[slot];
     CK(cudaEventRecord(sb.fork, st));
     CK(cudaStreamWaitEvent(sb.stream, sb.fork, 0));

@@ -32,6 +32,16 @@ void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_j
                   const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
                   double *d_part, double *d_table);
 
+// `--center empirical` (reference compute_offsets, src/GPPupilDemodulation.jl:105-125):
+// algebraic circle fit of each of the 40 channels of every kind-0 table whose
+// tv.offsets is set, over all rows or the HIGH rows of a table with states; writes the
+// 40 centres INTO tv.offsets.  d_part: [ntables][circle_max_segments][CIRC_VALS][40]
+constexpr int CIRC_SEG_ROWS = 4096;
+constexpr int CIRC_VALS = 10;
+int circle_max_segments(long long max_rows);
+void launch_circle(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
+                   double *d_part);
+
 // Jacobi-Anger harmonic sums of every fit + reduction into the harmonic table
 int harm_max_segments(long long max_rows_per_job);   // fixed 12288-row segments
 int stats_max_segments(long long max_rows_per_job);  // fixed 1024-row segments

@@ -38,7 +38,7 @@ extern "C" {
 #define GPPD_ERR_CUDA 2       /* a CUDA call failed; see gppd_last_error() */
 #define GPPD_ERR_NO_DEVICE 3  /* no usable sm_100 device: there is no CPU fallback */
 #define GPPD_ERR_NOMEM 4
-#define GPPD_ERR_UNSUPPORTED 5 /* e.g. --center empirical (broken in the reference too) */
+#define GPPD_ERR_UNSUPPORTED 5
 
 /* ---- option flags ------------------------------------------------------ */
 #define GPPD_ONLYHIGH 1u    /* demodulateall(onlyhigh=true)   src/Modulation.jl:348 */
@@ -46,6 +46,14 @@ extern "C" {
 #define GPPD_NO_RECENTER 4u /* demodulateall(recenter=false)  src/Modulation.jl:346 */
 #define GPPD_KEEPRAW 8u     /* processmetrology(keepraw=true) src/GPPupilDemodulation.jl:163 */
 #define GPPD_BIG_ENDIAN 16u /* table buffers are raw FITS (big-endian) bytes */
+#define GPPD_CENTER_EMPIRICAL 32u /* processmetrology(offsets=true), `--center empirical`:
+                               the centres are fitted here, one algebraic least-squares
+                               circle per channel over the table's samples (the HIGH
+                               samples of a FAINT table), compute_offsets,
+                               src/GPPupilDemodulation.jl:105-125,153-154.  Table entry
+                               points only; their `offsets` argument is then ignored and
+                               GPPD_FITOFFSETS is off.  (The reference itself throws on
+                               this path: its `Circle` type is undefined.) */
 
 /* which evaluator computes chi2(b, phi) inside the fit */
 #define GPPD_METHOD_AUTO 0     /* harmonic when its validity conditions hold, else direct */
@@ -216,6 +224,14 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
                                 const gppd_options *opt, float *const *d_volt_out,
                                 double *const *d_params, double *const *d_chi2,
                                 int32_t *const *d_info, int8_t *const *d_state_out);
+
+/*
+ * The centres the last GPPD_CENTER_EMPIRICAL call on pipeline slot `slot` fitted and
+ * subtracted: centres [ntables][40] complex128 (ntables = 1 for the single-table entry
+ * points).  Waits for the slot's stream.  A channel without a circle (fewer than 3
+ * samples, or all on one line) has centre 0.
+ */
+int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres);
 
 /* number of kernels this library has launched on the handle so far */
 int64_t gppd_launch_count(gppd_handle h);

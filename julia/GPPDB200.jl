@@ -24,6 +24,7 @@ const GPPD_ONLYHIGH    = UInt32(1)
 const GPPD_FITOFFSETS  = UInt32(2)
 const GPPD_NO_RECENTER = UInt32(4)
 const GPPD_KEEPRAW     = UInt32(8)
+const GPPD_CENTER_EMPIRICAL = UInt32(32)
 
 # struct gppd_options (include/gppd.h)
 struct Options
@@ -124,15 +125,19 @@ Table-level fast path on the raw bytes of the METROLOGY BINTABLE (big-endian rec
 `row_bytes` bytes, TIME at byte `time_off`, VOLT at byte `volt_off`), replacing the array
 work of `processmetrology` (src/GPPupilDemodulation.jl:139-171,192-253) and the column
 decoding of `Dict(hdu)` (src/FitsUtils.jl:31-37).  `rows_out` receives the output records
-(`row_bytes + 256` bytes each with `keepraw`).  `offsets === nothing` fits the centres.
+(`row_bytes + 256` bytes each with `keepraw`).  `offsets === nothing` fits the centres;
+`offsets === true` (processmetrology's default, `--center empirical`) has the library fit
+one circle per channel (compute_offsets, :105-125) -- `centres(slot)` returns them.
 """
 function processrows!(rows_out::Vector{UInt8}, rows::Vector{UInt8}, row_bytes::Integer,
                       time_off::Integer, volt_off::Integer, mjd::Real;
-                      offsets::Union{Nothing,Vector{ComplexF64}} = nothing,
+                      offsets::Union{Nothing,Bool,Vector{ComplexF64}} = nothing,
                       faintparam::Union{Nothing,FaintStates} = nothing,
                       window::Real = 0.0, keepraw::Bool = false, onlyhigh::Bool = false, slot::Integer = 0)
     n = length(rows) ÷ row_bytes
-    flags = (onlyhigh ? GPPD_ONLYHIGH : UInt32(0)) | (keepraw ? GPPD_KEEPRAW : UInt32(0))
+    flags = (onlyhigh ? GPPD_ONLYHIGH : UInt32(0)) | (keepraw ? GPPD_KEEPRAW : UInt32(0)) |
+            (offsets === true ? GPPD_CENTER_EMPIRICAL : UInt32(0))
+    offsets isa Bool && (offsets = nothing)
     opt = Options(flags, 0, 0, 0, (0.0, 0.0), 0.0, 0.0)
     nwrows = Ref{Int64}(0); nwin = Ref{Int64}(1)
     if window > 0
@@ -157,6 +162,14 @@ function processrows!(rows_out::Vector{UInt8}, rows::Vector{UInt8}, row_bytes::I
         gppd_assert_ok(ccall((:gppd_wait, libgppd), Cint, (Ptr{Cvoid}, Cint), gethandle(), slot))
     end
     return (params, chi2, isnothing(faintparam) ? nothing : state)
+end
+
+"centres fitted by the last `offsets = true` call on `slot` (40 complex values)"
+function centres(slot::Integer = 0)
+    c = Vector{ComplexF64}(undef, 40)
+    gppd_assert_ok(ccall((:gppd_centres, libgppd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{ComplexF64}),
+                         gethandle(), slot, 1, c))
+    return c
 end
 
 end # module

@@ -310,6 +310,37 @@ def make_times(time_us, mjd):
     return np.asarray(time_us).astype(np.float64) * 1e-6 + (DAY_TO_SEC * float(mjd))
 
 
+def circle_centre(x, y):
+    """Centre of the least-squares circle through the points (x, y): the algebraic
+    (Kasa) fit, minimise sum (x^2 + y^2 - 2 x0 x - 2 y0 y - c)^2, solved as the linear
+    least-squares problem [2x 2y 1] (x0, y0, c)' = x^2 + y^2 by SVD.  No circle (fewer
+    than 3 points, or all on one line) -> 0."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if x.size < 3:
+        return 0j
+    # shift to the centroid first: lstsq on raw volts squares the offset / radius ratio
+    xm, ym = x.mean(), y.mean()
+    u, v = x - xm, y - ym
+    A = np.stack([2 * u, 2 * v, np.ones_like(u)], axis=1)
+    sol, _, rank, _ = np.linalg.lstsq(A, u * u + v * v, rcond=1e-9)
+    if rank < 3:
+        return 0j
+    return complex(xm + sol[0], ym + sol[1])
+
+
+def compute_offsets(cmplxV, state=None):
+    """src/GPPupilDemodulation.jl:105-125: `fit(Circle, reim(channel)...)` for each of
+    the 40 channels, over the HIGH samples when there are states (:108), over all
+    samples otherwise (:120); returns the 40 complex centres.  `Circle` is not defined
+    in the reference's environment (the call throws there); the fit restated here is the
+    algebraic least-squares circle that call stands for (`circle_centre`)."""
+    cmplxV = np.asarray(cmplxV)
+    sel = slice(None) if state is None else (np.asarray(state) == HIGH)
+    return np.array([circle_centre(cmplxV[sel, ch].real, cmplxV[sel, ch].imag)
+                     for ch in range(40)], dtype=np.complex128)
+
+
 def processmetrology(time_us, volt, mjd, window=None, faintparam=None,
                      keepraw=False, onlyhigh=False, offsets=True, nthreads=1,
                      maxfun=60):
@@ -317,12 +348,9 @@ def processmetrology(time_us, volt, mjd, window=None, faintparam=None,
 
     time_us: (N,) int32; volt: (N, 80) float32 (row n = the 80 VOLT values of
     table row n, i.e. Julia's 80 x N column-major matrix); offsets: (40,)
-    complex128 centres, or False (fit the centres).  ``offsets=True``
-    (empirical circle fit) is broken in the reference (``Circle`` undefined,
-    :108,:120) and is rejected here too.
+    complex128 centres, False (fit the centres) or True (``compute_offsets``: the
+    reference throws there, see that function).
     Returns (table dict, hdr dict) with the reference's column/keyword names."""
-    if offsets is True:
-        raise NotImplementedError("--center empirical: `Circle` is undefined in the reference")
     volt32 = np.asarray(volt, dtype=np.float32)
     n = volt32.shape[0]
     times = make_times(time_us, mjd)
@@ -332,6 +360,8 @@ def processmetrology(time_us, volt, mjd, window=None, faintparam=None,
     fitoffsets = False
     if offsets is False:
         fitoffsets = True
+    elif offsets is True:
+        cmplx = cmplx - compute_offsets(cmplx, state).reshape(1, 40)             # :154
     else:
         cmplx = cmplx - np.asarray(offsets, dtype=np.complex128).reshape(1, 40)  # :152
     table, hdr = {}, {}

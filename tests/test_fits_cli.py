@@ -71,16 +71,17 @@ def test_cli_gating_without_gpu(gp, ora, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["whole", "keepraw", "window", "fit"])
+@pytest.mark.parametrize("mode", ["whole", "keepraw", "window", "fit", "empirical"])
 def test_cli_night_end_to_end(gp, ora, tmp_path, mode):
     from gppd_b200 import cli, fits
     d, out = str(tmp_path / "night"), str(tmp_path / "out")
     tabs = _night(gp, ora, d)
     argv = ["-r", "-d", out, "-s", "_demod"]
-    argv += {"whole": [], "keepraw": ["-k"], "window": ["-w", "2.0"], "fit": ["-c", "fit"]}[mode]
+    argv += {"whole": [], "keepraw": ["-k"], "window": ["-w", "2.0"], "fit": ["-c", "fit"],
+             "empirical": ["-c", "empirical"]}[mode]
     assert cli.main(argv + [d]) == 0
     assert sorted(os.listdir(out)) == ["bright_demod.fits", "faint_demod.fits"]
-    off = False if mode == "fit" else gp.synthetic.stefan_centres()
+    off = {"fit": False, "empirical": True}.get(mode, gp.synthetic.stefan_centres())
     for name, sub in (("bright", ""), ("faint", "sub")):
         tab = tabs[name]
         src = fits.read_fits(os.path.join(d, sub, name + ".fits"))
