@@ -80,6 +80,7 @@ def lib():
         _i32p, _i8p]
     L.gppd_wait.argtypes = [H, C.c_int]
     L.gppd_centres.argtypes = [H, C.c_int, C.c_int64, _dp]
+    L.gppd_debug_harmonics.argtypes = [H, C.c_int, _dp, C.c_int64]
     L.gppd_num_slots.argtypes = [H]
     L.gppd_process_table_f32_dev.argtypes = [
         H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
@@ -97,7 +98,7 @@ def lib():
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
-                 "gppd_submit_fits_rows", "gppd_centres",
+                 "gppd_submit_fits_rows", "gppd_centres", "gppd_debug_harmonics",
                  "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",
                  "gppd_process_tables_f32_dev", "gppd_enable_timing",
                  "gppd_pass_times", "gppd_measure_fp64_peak"):

@@ -92,6 +92,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     // staging of caller data (host-buffer entry points)
     DevBuf time, volt, volt_out, t, data, out, state_in, offsets, rows, rows_out;
+    long long htab_vals = 0;        // values in htab after the last batch (test hook)
     DevBuf centres, cpart;          // --center empirical: [T][40] complex128 + partial sums
     int ncentres = 0;               // tables whose centres the last batch of this slot fitted
     DevBuf params, chi2, info, trace, state_out;
@@ -242,6 +243,16 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         return GPPD_ERR_ARG;
     }
     const bool direct = method == GPPD_METHOD_DIRECT;
+    // the int8 tensor-core form of the harmonic sums takes dense METROLOGY tables (rows of
+    // 80 floats, 16-byte aligned); the other layouts use the FP64 DMMA kernel.
+    // GPPD_HARMONICS=dmma|tensor overrides (tensor is ignored for layouts it cannot take).
+    bool tensor = max_wrows >= harm_tc_min_rows();
+    for (int t = 0; t < T; ++t) {
+        const TableView &v = td[t].tv;
+        if (v.kind != 0 || (reinterpret_cast<unsigned long long>(v.volt) & 15ull) || (v.volt_stride & 15) ||
+            v.volt_stride < 320)
+            tensor = false;
+    }
 
     // partial sums are taken over FIXED row segments of each job (so that a fit's
     // result does not depend on the rest of the batch); P / SP = segments of the
@@ -389,7 +400,8 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
             PassScope ps(h, s, stream, GPPD_PASS_HARMONICS);
             launch_harmonics(L, d_tabs, s.jobs.as<JobInfo>(), njobs, fo.flags, P, SP,
                              s.spart1.as<double>(), s.spart2.as<double>(), s.partZ.as<double>(),
-                             s.partY.as<double>(), s.htab.as<double>());
+                             s.partY.as<double>(), s.htab.as<double>(), tensor);
+            s.htab_vals = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
         }
         DBG(stream, "harmonics");
         {
@@ -587,6 +599,20 @@ int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres) {
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaMemcpy(centres, s.centres.p, sizeof(double2) * NCHAN * (size_t)ntables,
                   cudaMemcpyDeviceToHost));
+    return GPPD_OK;
+}
+
+int gppd_debug_harmonics(gppd_handle h, int slot, double *htab, int64_t nvals) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS || !htab) return GPPD_ERR_ARG;
+    Slot &s = h->slots[slot];
+    CK(cudaStreamSynchronize(s.stream));
+    if (nvals > s.htab_vals) {
+        g_last_error = "debug_harmonics: the slot's last batch has fewer values";
+        return GPPD_ERR_ARG;
+    }
+    CK(cudaMemcpy(htab, s.htab.p, sizeof(double) * (size_t)nvals, cudaMemcpyDeviceToHost));
     return GPPD_OK;
 }
 

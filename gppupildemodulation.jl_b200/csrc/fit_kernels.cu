@@ -197,7 +197,7 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
                                               const JobInfo &ji, double b, double phi, double &f,
                                               double &cre, double &cim, double &are, double &aim) {
     double q;
-    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;
+    if (!(fabs(b) <= HARM_BMAX) || !(kc.sdd == kc.sdd) || !harm_quantum(phi, ji, q)) return false;
     double J[HK + 1];
     bessel_j(b, J);
     double sq, cq;
@@ -240,7 +240,7 @@ __device__ __forceinline__ bool eval_harmonic_warp(const HarmLane &h, const FitC
                                                    double &f, double &cre, double &cim, double &are,
                                                    double &aim) {
     double q;
-    if (!(fabs(b) <= HARM_BMAX) || !harm_quantum(phi, ji, q)) return false;   // warp-uniform
+    if (!(fabs(b) <= HARM_BMAX) || !(kc.sdd == kc.sdd) || !harm_quantum(phi, ji, q)) return false;   // warp-uniform
     const double J = bessel_j_lane(b, lane);
     double sq, cq;
     sincos_moderate(q, &sq, &cq);

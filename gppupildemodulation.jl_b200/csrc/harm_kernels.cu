@@ -437,12 +437,22 @@ int harm_max_segments(long long max_rows_per_job) { return harm_segments(max_row
 
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
-                      const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab) {
+                      const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab,
+                      bool tensor) {
+    const bool offs = (flags & 2u) != 0;
+    const int nfits = njobs * NDIODE;
+    const long long tot = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
+    if (tensor) {
+        launch_harmonics_tc(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
+        k_harm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
+            d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, d_htab);
+        *L.counter += 1;
+        return;
+    }
     cudaFuncSetAttribute(k_harm_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
     cudaFuncSetAttribute(k_harm_ws<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
     cudaFuncSetAttribute(k_harm_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
     dim3 grid(njobs * NGROUP, P);
-    const bool offs = (flags & 2u) != 0;
     if (offs) {
         k_harm_ws<0, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
         k_harm_ws<1, true><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);
@@ -451,8 +461,6 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
         k_harm_ws<0, false><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
         *L.counter += 1;
     }
-    const int nfits = njobs * NDIODE;
-    const long long tot = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
     k_harm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
         d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, d_htab);
     *L.counter += 1;

@@ -1,0 +1,652 @@
+// harm_tc_kernels.cu -- the harmonic sums on the 5th-generation tensor cores.
+//
+// Same sums as harm_kernels.cu (reference src/Modulation.jl:137-145 rewritten with the
+// Jacobi-Anger expansion): per job and 12 288-row segment
+//     C[64 x 48] = V^T[64 x rows] E[rows x 48],
+//     V[row][8 g + 2 d + {0,1}] = (x, y) of the stream value of diode d of group g,
+//     E[row][2 (k - 1) + {0,1}] = (cos, sin)(k theta_row),  k = 1..24,
+// for ALL 8 groups of a table at once (E depends on the row only).  FP64 has no fast
+// tensor path on sm_100a (DMMA shares the FP64 pipe: 37 TFLOP/s), but the int8 path
+// (tcgen05.mma kind::i8, exact int32 accumulation in TMEM) runs two orders of magnitude
+// faster, and a fixed-point product is exact: both factors are rounded once to 48-bit
+// fixed point (E: 2^-46 absolute; V: 2^-43 of the largest sampled |V| of the diode in the
+// segment), split into six balanced base-256 digits (signed bytes),
+//     X = sum_i a_i 256^i,  a_i in [-128, 127],
+// and  sum_rows X_V X_E = sum_{i,j} 256^(i+j) sum_rows a_i b_j  is accumulated digit pair
+// by digit pair in int32.  Pairs with i + j < 5 (below 2^-45 of the result) are not all
+// formed.  The digits come for free: v 2^F + (2^52 + 2^51 + 0x808080808080) puts
+// X + 0x80..80 into the low 48 mantissa bits, whose bytes are a_i + 128.
+//
+// One MMA takes A = [V digit i ; V digit i + 3] (M = 128: two digits stacked along M) and
+// B = [E digit j0 | E digit j0 + 1 | ...] (N = 48 per digit): the product of digit i with
+// digit j lands in TMEM column block i + j - 2, so every block collects one power of 256
+// (2 + block for lanes 0..63, 5 + block for lanes 64..127) and four MMAs per 32 rows do
+// all 36 digit pairs (measured issue cost 46 + N / 2 cycles per MMA: ~540 cycles per 32
+// rows against ~2750 for the DMMA kernel).
+//
+// Block = (job, segment).  Warp roles: 8 V producers (thread = (row, group): stream
+// values, constant sums, digits -> MN-major operand tile), 4 E producers (lane = row:
+// the 24 harmonics by complex products of depth <= 5, digits -> operand tile), 1 MMA
+// issuer, 1 TMA loader (raw rows + basis, cp.async.bulk into an 8-deep ring).  mbarriers
+// hand the raw ring (loader -> producers) and the operand ring (producers -> MMA ->
+// tcgen05.commit) over.  The epilogue reads the six int32 blocks from TMEM, combines them
+// in FP64 (exact up to the final roundings) and writes the same partial-sum layout as
+// k_harm_ws, so k_harm_reduce and the fit are unchanged.  Integer accumulation makes the
+// result independent of any summation order.
+//
+// A value outside the sampled range (16x headroom) would wrap: it is detected from the
+// mantissa bits, the group's sums of that segment are poisoned with NaN and its fits go
+// to the direct evaluator through the fallback queue.
+#include <cstdlib>
+
+#include "fit_math.cuh"
+#include "gppd_device.cuh"
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace gppd {
+
+constexpr int TC_SEG_ROWS = 12288;            // = HARM_SEG_ROWS (harm_kernels.cu)
+constexpr int TC_KB = 32;                     // rows per K-block = K of one int8 MMA
+constexpr int TC_RS = 8;                      // raw ring stages
+constexpr int TC_OS = 4;                      // operand ring stages
+constexpr int TC_VSETS = 2;                   // V producer sets: set s takes K-blocks s, s + 2, ...
+constexpr int TC_VW = 8 * TC_VSETS, TC_EW = 2; // V / E producer warps (8 V warps per K-block)
+constexpr int TC_MMA_WARP = TC_VW + TC_EW, TC_LOAD_WARP = TC_MMA_WARP + 1;
+constexpr int TC_WARPS = TC_LOAD_WARP + 1;
+constexpr int TC_THREADS = TC_WARPS * 32;
+constexpr int TC_RAW_VOLT = TC_KB * 320;
+constexpr int TC_RAW_BYTES = TC_RAW_VOLT + TC_KB * 16;         // + basis
+constexpr int TC_ND = 6;                      // digits per value
+// operand tiles (MN-major, no swizzle): byte (mn, k) of an operand at
+//   (mn % 16) + 16 (k % 8) + SBO (mn / 16) + LBO (k / 8)
+constexpr int V_SBO = 160;                    // 128 + 32: conflict-free 8-byte stores
+constexpr int V_LBO = 4 * TC_ND * V_SBO, V_TILE = 4 * V_LBO;
+constexpr int E_SBO = 128;
+constexpr int E_LBO = 3 * TC_ND * E_SBO, E_TILE = 4 * E_LBO;
+constexpr int TC_OP_BYTES = V_TILE + E_TILE;
+constexpr int TC_SMEM = TC_RS * TC_RAW_BYTES + TC_OS * TC_OP_BYTES + 128;
+constexpr int TC_TMEM_COLS = 512;             // 6 blocks x 48 columns used
+constexpr int TC_EBITS = 46;                  // E = X 2^-46
+constexpr int TC_VBITS = 43;                  // sampled max |V| -> below 2^43
+static_assert(TC_SMEM <= 227 * 1024, "shared memory");
+static_assert(TC_SEG_ROWS * 3ll * 16384 < (1ll << 31), "int32 accumulators");
+
+// 2^52 + 2^51 + 0x808080808080: ulp 1, bytes 0..5 of (v + this) are the digits + 128
+#define TC_MAGIC 6896688841130112.0
+constexpr uint32_t TC_MAGIC_HI = 0x43388080u;  // high word of TC_MAGIC
+
+__device__ __forceinline__ bool tc_elect() {
+    uint32_t pred;
+    asm volatile("{\n .reg .b32 rx;\n .reg .pred px;\n elect.sync rx|px, %1;\n selp.u32 %0, 1, 0, px;\n}\n"
+                 : "=r"(pred)
+                 : "r"(0xffffffffu));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = s32, A = B = signed int8, both MN-major, M = 128
+__host__ __device__ constexpr uint32_t tc_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// digits of four values: byte j of (lo, hi)[i] -> byte i of out[j], minus the 128 bias
+__device__ __forceinline__ void tc_digits4(const uint32_t (&lo)[4], const uint32_t (&hi)[4], uint32_t (&out)[TC_ND]) {
+    const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+    const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+    const uint32_t u0 = __byte_perm(hi[0], hi[1], 0x5140), u1 = __byte_perm(hi[2], hi[3], 0x5140);
+    out[0] = __byte_perm(t0, t1, 0x5410) ^ 0x80808080u;
+    out[1] = __byte_perm(t0, t1, 0x7632) ^ 0x80808080u;
+    out[2] = __byte_perm(t2, t3, 0x5410) ^ 0x80808080u;
+    out[3] = __byte_perm(t2, t3, 0x7632) ^ 0x80808080u;
+    out[4] = __byte_perm(u0, u1, 0x5410) ^ 0x80808080u;
+    out[5] = __byte_perm(u0, u1, 0x7632) ^ 0x80808080u;
+}
+
+__device__ __forceinline__ double2 tc_cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 tc_csqr(double2 a) {
+    return make_double2(fma(a.x, a.x, -(a.y * a.y)), 2.0 * (a.x * a.y));
+}
+__device__ __forceinline__ double2 tc_fc_unit(double x, double y) {
+    const double h2 = fma(x, x, y * y);
+    if (h2 > 1.0e-280 && h2 < 1.0e280) {
+        const double inv = rsqrt(h2);
+        return make_double2(x * inv, y * inv);
+    }
+    return fc_phasor(make_double2(x, y));
+}
+
+// stream values of the 4 diodes of a group for one row (the arithmetic of k_harm_ws):
+// KIND 0: z = w conj(p) (d - mu), p = power FCphasor;  KIND 1 (fitoffsets): y = w p
+template <int KIND, bool OFFS, bool ACC, bool FAINT>
+__device__ __forceinline__ void tc_values(int st, const double2 (&dd)[4], double2 fcs,
+                                          const double2 *stats16, const double2 (&mu)[4], double2 (&vv)[4],
+                                          double *cst) {
+    constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;
+    const double2 fc = tc_fc_unit(fcs.x, fcs.y);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        double wpr = fc.x, wpi = fc.y, w = 1.0;
+        if (FAINT) {
+            const double2 mw = stats16[(d * 4 + (st & 3)) * NGROUP];
+            w = mw.y;
+            const double wm = mw.y * mw.x;
+            wpr = wm * fc.x;
+            wpi = wm * fc.y;
+        }
+        if (KIND == 0) {
+            double dr = dd[d].x, di = dd[d].y;
+            if (OFFS) { dr -= mu[d].x; di -= mu[d].y; }
+            vv[d].x = fma(wpr, dr, wpi * di);
+            vv[d].y = fma(wpr, di, -(wpi * dr));
+            if (ACC) {
+                cst[d * NACC + 0] = fma(w, fma(dr, dr, di * di), cst[d * NACC + 0]);
+                cst[d * NACC + 1] += vv[d].x;
+                cst[d * NACC + 2] += vv[d].y;
+                if (OFFS) {
+                    cst[d * NACC + 3] = fma(w, dr, cst[d * NACC + 3]);
+                    cst[d * NACC + 4] = fma(w, di, cst[d * NACC + 4]);
+                }
+            }
+        } else {
+            vv[d].x = wpr;
+            vv[d].y = wpi;
+            if (ACC) {
+                cst[d * NACC + 0] += wpr;
+                cst[d * NACC + 1] += wpi;
+            }
+        }
+    }
+}
+
+// mbarrier operations on precomputed shared-window addresses (the generic -> shared
+// conversion is not free inside the K-block loops)
+__device__ __forceinline__ void tc_wait(uint32_t bar, unsigned parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tc_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcShared {
+    uint64_t raw_full[TC_RS], raw_empty[TC_RS], op_full[TC_OS], op_empty[TC_OS], acc_full;
+    double2 stats[16][NGROUP];     // [diode * 4 + state][group]: a quarter warp reads 128 contiguous bytes
+    double2 off[NCHAN];
+    double scale[NDIODE], inv[NDIODE];
+    double2 voff[5][NGROUP];       // centres of a group's 4 diodes + FC, [channel][group]
+    double vscale[4][NGROUP];      // scale, [diode][group]
+    unsigned long long vmax[NDIODE];
+    int ovf[NGROUP];
+    uint32_t tmem;
+};
+
+// V producer: thread = (row 4 wv + r4 of the K-block, group g), K-blocks vset, vset + 2, ...
+template <int KIND, bool OFFS, bool FAINT>
+__device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ring, unsigned char *op_ring,
+                                              const TableDesc &tb, unsigned flags, long long rbase, int nseg,
+                                              int nkb, int warp, int lane, const double2 (&mu)[4], double *cst,
+                                              unsigned long long &cnt) {
+    const int r4 = lane >> 3, g = lane & 7;
+    const int vset = warp >> 3, krow = 4 * (warp & 7) + r4;
+    const uint32_t b_raw_full = smem_u32(&S.raw_full[0]), b_raw_empty = smem_u32(&S.raw_empty[0]);
+    const uint32_t b_op_full = smem_u32(&S.op_full[0]), b_op_empty = smem_u32(&S.op_empty[0]);
+    const int8_t *stp = FAINT ? tb.state + rbase + krow : nullptr;
+    int st_next = ST_NORMAL;
+    if (FAINT && vset * TC_KB + krow < nseg) st_next = stp[vset * TC_KB];
+    uint32_t ovf = 0;
+    const bool be = tb.tv.big_endian != 0;
+    const double2 *off = &S.voff[0][g];                 // off[d * NGROUP]
+    const double *sc = &S.vscale[0][g];
+    const unsigned char *rw0 = raw_ring + krow * 320 + 32 * g;
+    unsigned char *vt0 = op_ring + (g >> 1) * V_SBO + (krow >> 3) * V_LBO + (krow & 7) * 16 + 8 * (g & 1);
+#pragma unroll 1
+    for (int kb = vset; kb < nkb; kb += TC_VSETS) {
+        const int rs = kb % TC_RS, os = kb % TC_OS;
+        const int i = kb * TC_KB + krow;
+        const int st = st_next;
+        if (FAINT && i + TC_VSETS * TC_KB < nseg) st_next = stp[(long long)(kb + TC_VSETS) * TC_KB];
+        if (!(flags & (32u << 24))) tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+        const unsigned char *rw = rw0 + rs * TC_RAW_BYTES;
+        if (flags & (16u << 24)) {
+            __syncwarp();
+            if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
+            tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
+            __syncwarp();
+            if (lane == 0) tc_arrive(b_op_full + 8 * os);
+            continue;
+        }
+        const uint4 wa = *reinterpret_cast<const uint4 *>(rw);
+        const uint4 wb = *reinterpret_cast<const uint4 *>(rw + 16);
+        uint2 wf = *reinterpret_cast<const uint2 *>(rw + 256 - 24 * g);     // row + 256 + 8 g
+        uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        if (be) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
+            wf.x = bswap32(wf.x);
+            wf.y = bswap32(wf.y);
+        }
+        double2 vv[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
+        const bool valid = i < nseg && (!FAINT || row_valid(st, flags)) && !(flags & (4u << 24));
+        if (valid) {
+            double2 dd[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - off[d * NGROUP].x,
+                                     (double)__uint_as_float(w[2 * d + 1]) - off[d * NGROUP].y);
+            }
+            const double2 fcs = make_double2((double)__uint_as_float(wf.x) - off[4 * NGROUP].x,
+                                             (double)__uint_as_float(wf.y) - off[4 * NGROUP].y);
+            cnt += 1ull << (16 * (st & 3));
+            tc_values<KIND, OFFS, true, FAINT>(st, dd, fcs, &S.stats[0][g], mu, vv, cst);
+        }
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const double tx = fma(vv[d].x, sc[d * NGROUP], TC_MAGIC), ty = fma(vv[d].y, sc[d * NGROUP], TC_MAGIC);
+            lo[2 * d] = (uint32_t)__double2loint(tx);
+            hi[2 * d] = (uint32_t)__double2hiint(tx);
+            lo[2 * d + 1] = (uint32_t)__double2loint(ty);
+            hi[2 * d + 1] = (uint32_t)__double2hiint(ty);
+            ovf |= (hi[2 * d] ^ TC_MAGIC_HI) | (hi[2 * d + 1] ^ TC_MAGIC_HI);
+        }
+        uint32_t dlo[TC_ND], dhi[TC_ND];
+        {
+            const uint32_t l0[4] = {lo[0], lo[1], lo[2], lo[3]}, h0[4] = {hi[0], hi[1], hi[2], hi[3]};
+            const uint32_t l1[4] = {lo[4], lo[5], lo[6], lo[7]}, h1[4] = {hi[4], hi[5], hi[6], hi[7]};
+            tc_digits4(l0, h0, dlo);
+            tc_digits4(l1, h1, dhi);
+        }
+        __syncwarp();                                   // every lane has consumed its raw bytes
+        if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
+        tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
+        unsigned char *vt = vt0 + os * TC_OP_BYTES;
+#pragma unroll
+        for (int j = 0; j < TC_ND; ++j)
+            *reinterpret_cast<uint2 *>(vt + ((j % 3) * 8 + (j / 3) * 4) * V_SBO) = make_uint2(dlo[j], dhi[j]);
+        if (!(flags & (2u << 24))) fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tc_arrive(b_op_full + 8 * os);
+    }
+    if (ovf & 0xffff0000u) S.ovf[g] = 1;
+}
+
+template <int KIND, bool OFFS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, const double *stats,
+          double *partial) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ __align__(16) TcShared S;
+
+    constexpr int NCONST = KIND == 0 ? 7 : 2;
+    constexpr int NACC = KIND == 0 ? (OFFS ? 5 : 3) : 2;
+    constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
+    const int job = blockIdx.x, p = blockIdx.y;
+    const JobInfo ji = jobs[job];
+    const long long seg0 = (long long)p * TC_SEG_ROWS;
+    if (seg0 >= ji.nrows) return;
+    const TableDesc tb = tabs[ji.table];
+    const TableView &tv = tb.tv;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nseg = (int)((ji.nrows - seg0) < TC_SEG_ROWS ? (ji.nrows - seg0) : TC_SEG_ROWS);
+    const int nkb = (nseg + TC_KB - 1) / TC_KB;
+    const bool faint = tb.state != nullptr;
+    const long long rbase = ji.row0 + seg0;           // first table row of the segment
+
+    unsigned char *raw_ring = tc_smem;
+    unsigned char *op_ring = tc_smem + TC_RS * TC_RAW_BYTES;
+
+    // ---- set-up: barriers, TMEM, tables, per-diode scales ------------------------------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_RS; ++i) {
+            mbar_init(&S.raw_full[i], 1);
+            mbar_init(&S.raw_empty[i], 8 + 1);        // 8 V warps + 1 E warp per K-block
+        }
+        for (int i = 0; i < TC_OS; ++i) {
+            mbar_init(&S.op_full[i], 8 + 1);
+            mbar_init(&S.op_empty[i], 1);
+        }
+        mbar_init(&S.acc_full, 1);
+    }
+    if (warp == TC_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&S.tmem)),
+                     "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (threadIdx.x < NGROUP * 16) {
+        const int g = threadIdx.x >> 4, k = threadIdx.x & 15;
+        S.stats[k][g] = faint ? stats_mean_weight(stats, job * NGROUP + g, k >> 2, k & 3) : make_double2(1.0, 1.0);
+    } else if (threadIdx.x < NGROUP * 16 + NCHAN) {
+        const int ch = threadIdx.x - NGROUP * 16;
+        S.off[ch] = tv.offsets ? __ldg(tv.offsets + ch) : make_double2(0.0, 0.0);
+    } else if (threadIdx.x < NGROUP * 16 + NCHAN + NDIODE) {
+        S.vmax[threadIdx.x - NGROUP * 16 - NCHAN] = 0ull;
+    } else if (threadIdx.x < NGROUP * 16 + NCHAN + NDIODE + NGROUP) {
+        S.ovf[threadIdx.x - NGROUP * 16 - NCHAN - NDIODE] = 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem;
+
+    const int r4 = lane >> 3, g = lane & 7;
+    double2 mu[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+        mu[d] = (OFFS && warp < TC_VW) ? row_sample(tv, ji.row0, g * 4 + d) : make_double2(0.0, 0.0);
+
+    if (warp < 8) {
+        // 128 rows spread over the segment: the largest |V| component of each diode
+        double mx[4] = {0.0, 0.0, 0.0, 0.0};
+        const int r = threadIdx.x >> 3;
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const int i = (int)(((long long)(it * 32 + r) * nseg) >> 7);
+            const long long row = rbase + i;
+            const int st = faint ? tb.state[row] : ST_NORMAL;
+            if (faint && !row_valid(st, flags)) continue;
+            double2 dd[4], vv[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, row, g * 4 + d);
+            const double2 fcs = row_sample(tv, row, fc_channel(g));
+            if (faint) tc_values<KIND, OFFS, false, true>(st, dd, fcs, &S.stats[0][g], mu, vv, nullptr);
+            else tc_values<KIND, OFFS, false, false>(st, dd, fcs, &S.stats[0][g], mu, vv, nullptr);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) mx[d] = fmax(mx[d], fmax(fabs(vv[d].x), fabs(vv[d].y)));
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (mx[d] > 0.0 && mx[d] < 1.0e300)
+                atomicMax(&S.vmax[g * 4 + d], (unsigned long long)__double_as_longlong(mx[d]));
+    }
+    __syncthreads();
+    if (threadIdx.x < NDIODE) {
+        const double m = __longlong_as_double((long long)S.vmax[threadIdx.x]);
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);                       // m < 2^e
+        const int F = TC_VBITS - e;
+        S.scale[threadIdx.x] = scalbn(1.0, F);
+        S.vscale[threadIdx.x & 3][threadIdx.x >> 2] = scalbn(1.0, F);
+        S.inv[threadIdx.x] = scalbn(1.0, -(F + TC_EBITS));
+    } else if (threadIdx.x < NDIODE + NCHAN) {
+        const int ch = threadIdx.x - NDIODE;
+        if (ch < 32) S.voff[ch & 3][ch >> 2] = S.off[ch];
+        else S.voff[4][ch - 32] = S.off[ch];
+    }
+    __syncthreads();
+
+    double cst[NACC * 4];
+#pragma unroll
+    for (int q = 0; q < NACC * 4; ++q) cst[q] = 0.0;
+    unsigned long long cnt = 0;
+
+    if (warp == TC_LOAD_WARP) {
+        // ---- TMA loader: raw rows + basis of K-block kb into ring stage kb % TC_RS --------
+        const char *volt = reinterpret_cast<const char *>(tv.volt);
+        const bool dense = tv.volt_stride == 320;
+        for (int kb = 0; kb < ((flags & (32u << 24)) ? 0 : nkb); ++kb) {
+            const int rs = kb % TC_RS;
+            mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
+            const int rows = min(TC_KB, nseg - kb * TC_KB);
+            const long long row = rbase + (long long)kb * TC_KB;
+            unsigned char *dst = raw_ring + rs * TC_RAW_BYTES;
+            if (lane == 0) {
+                mbar_expect_tx(&S.raw_full[rs], (unsigned)rows * 336u);
+                bulk_g2s(dst + TC_RAW_VOLT, tb.basis + row, (unsigned)rows * 16u, &S.raw_full[rs]);
+                if (dense) bulk_g2s(dst, volt + row * 320, (unsigned)rows * 320u, &S.raw_full[rs]);
+            }
+            __syncwarp();
+            if (!dense && lane < rows)
+                bulk_g2s(dst + lane * 320, volt + (row + lane) * tv.volt_stride, 320u, &S.raw_full[rs]);
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ---- MMA issuer ----------------------------------------------------------------------
+        constexpr uint32_t ID144 = tc_idesc(144), ID192 = tc_idesc(192), ID240 = tc_idesc(240);
+        const uint32_t b_op_full = smem_u32(&S.op_full[0]);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int os = kb % TC_OS;
+            tc_wait(b_op_full + 8 * os, (kb / TC_OS) & 1);
+            tc_fence_after();
+            if (tc_elect()) {
+                const uint32_t vb = smem_u32(op_ring + os * TC_OP_BYTES), eb = vb + V_TILE;
+                const uint32_t acc = kb > 0 ? 1u : 0u;
+                // digits (2, 5) x E digits 0..2 and 3..5 first: they cover all six blocks
+                const uint64_t a2 = tc_desc(vb + 2 * 8 * V_SBO, V_LBO, V_SBO);
+                if (!(flags & (1u << 24))) {
+                tc_mma(tmem, a2, tc_desc(eb, E_LBO, E_SBO), ID144, acc);
+                tc_mma(tmem + 144, a2, tc_desc(eb + 9 * E_SBO, E_LBO, E_SBO), ID144, acc);
+                // digits (1, 4) x E digits 1..5 -> blocks 0..4;  digits (0, 3) x E digits 2..5 -> blocks 0..3
+                tc_mma(tmem, tc_desc(vb + 8 * V_SBO, V_LBO, V_SBO), tc_desc(eb + 3 * E_SBO, E_LBO, E_SBO), ID240, 1u);
+                tc_mma(tmem, tc_desc(vb, V_LBO, V_SBO), tc_desc(eb + 6 * E_SBO, E_LBO, E_SBO), ID192, 1u);
+                }
+                tc_commit(&S.op_empty[os]);
+                if (kb == nkb - 1) tc_commit(&S.acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= TC_VW) {
+        // ---- E producers: lane = row, K-blocks e, e + 4, ... ---------------------------------
+        const int e = warp - TC_VW;
+        const uint32_t b_raw_full = smem_u32(&S.raw_full[0]), b_raw_empty = smem_u32(&S.raw_empty[0]);
+        const uint32_t b_op_full = smem_u32(&S.op_full[0]), b_op_empty = smem_u32(&S.op_empty[0]);
+#pragma unroll 1
+        for (int kb = e; kb < nkb; kb += TC_EW) {
+            const int rs = kb % TC_RS, os = kb % TC_OS;
+            if (!(flags & (32u << 24))) tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+            const uint4 bw = *reinterpret_cast<const uint4 *>(raw_ring + rs * TC_RAW_BYTES + TC_RAW_VOLT + lane * 16);
+            // basis = (sin theta, cos theta)
+            double2 e1 = make_double2(__hiloint2double(bw.w, bw.z), __hiloint2double(bw.y, bw.x));
+            if (kb * TC_KB + lane >= nseg) e1 = make_double2(1.0, 0.0);
+            double2 eh[8];
+            eh[0] = e1;
+            eh[1] = tc_csqr(e1);
+            eh[2] = tc_cmul(eh[1], e1);
+            eh[3] = tc_csqr(eh[1]);
+            eh[4] = tc_cmul(eh[3], e1);
+            eh[5] = tc_csqr(eh[2]);
+            eh[6] = tc_cmul(eh[5], e1);
+            eh[7] = tc_csqr(eh[3]);
+            const double2 e8 = eh[7];
+            __syncwarp();
+            if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
+            tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
+            unsigned char *et = op_ring + os * TC_OP_BYTES + V_TILE + (lane >> 3) * E_LBO + (lane & 7) * 16;
+            if (!(flags & (8u << 24)))
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                // harmonics 8 a + 1 .. 8 a + 8: 16 values = one 16-byte atom row per digit
+                uint32_t dg[4][TC_ND];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t lo[4], hi[4];
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const double2 v = eh[2 * q + s];
+                        const double tx = fma(v.x, 70368744177664.0, TC_MAGIC);   // 2^46
+                        const double ty = fma(v.y, 70368744177664.0, TC_MAGIC);
+                        lo[2 * s] = (uint32_t)__double2loint(tx);
+                        hi[2 * s] = (uint32_t)__double2hiint(tx);
+                        lo[2 * s + 1] = (uint32_t)__double2loint(ty);
+                        hi[2 * s + 1] = (uint32_t)__double2hiint(ty);
+                    }
+                    tc_digits4(lo, hi, dg[q]);
+                }
+#pragma unroll
+                for (int j = 0; j < TC_ND; ++j)
+                    *reinterpret_cast<uint4 *>(et + (3 * j + a) * E_SBO) = make_uint4(dg[0][j], dg[1][j], dg[2][j], dg[3][j]);
+                if (a < 2) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) eh[q] = tc_cmul(eh[q], e8);
+                }
+            }
+            if (!(flags & (2u << 24))) fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc_arrive(b_op_full + 8 * os);
+        }
+    } else {
+        if (faint) tc_v_producer<KIND, OFFS, true>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
+        else tc_v_producer<KIND, OFFS, false>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
+    }
+    __syncthreads();      // every producer is done with the raw ring: it now holds the reductions
+
+    double *s_red = reinterpret_cast<double *>(raw_ring);                          // [TC_VW][NGROUP][20]
+    unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(s_red + TC_VW * NGROUP * 20);
+    if (warp < TC_VW) {
+        // constant sums: the 4 row lanes of a group, then (below) the V warps in order
+#pragma unroll
+        for (int q = 0; q < NACC * 4; ++q) {
+            double sv = cst[q];
+            sv += __shfl_xor_sync(0xffffffffu, sv, 8);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 16);
+            if (r4 == 0) s_red[(warp * NGROUP + g) * 20 + q] = sv;
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+        if (r4 == 0) s_cnt[warp * NGROUP + g] = cnt;
+    }
+    __syncthreads();
+
+    // ---- epilogue: TMEM -> FP64 sums -> the partial layout of k_harm_ws ---------------------
+    double *stage = reinterpret_cast<double *>(op_ring);         // [64][49] upper-half sums
+    if (warp < 4) {
+        mbar_wait(&S.acc_full, 0);
+        tc_fence_after();
+        const int tl = warp * 32 + lane;                          // TMEM lane
+        const int h = tl >> 6, c = tl & 63;                       // digit half, V column
+        const int cg = c >> 3, d = (c >> 1) & 3, im = c & 1;
+        const double inv = S.inv[cg * 4 + d];
+        double *out = partial + ((long long)(job * NGROUP + cg) * P + p) * 4 * HP + d * HP + NCONST;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {                             // 16 of the 48 E columns at a time
+            double acc[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc[t] = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const double wgt = scalbn(1.0, 8 * (b + (h ? 5 : 2)));
+                uint32_t v[16];
+                tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 48 + q * 16), v);
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc[t] = fma((double)(int)v[t], wgt, acc[t]);
+            }
+            if (h) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) stage[c * 49 + q * 16 + t] = acc[t];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!h) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int m = q * 16 + t, k = m >> 1, sn = m & 1;
+                    const int slot = sn ? (im ? 1 : 3) : (im ? 2 : 0);
+                    out[k * 4 + slot] = (acc[t] + stage[c * 49 + m]) * inv;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    // constants: thread = (group, diode, constant)
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + NGROUP * 4 * NCONST) {
+        const int t = threadIdx.x - 128;
+        const int cg = t / (4 * NCONST), d = (t / NCONST) & 3, cc = t % NCONST;
+        unsigned long long cn = 0;
+        for (int w = 0; w < TC_VW; ++w) cn += s_cnt[w * NGROUP + cg];
+        double sv = 0.0;
+        int src = -1;
+        if (KIND == 0) {
+            if (cc == 1) src = 0;
+            else if (cc == 5) src = 1;
+            else if (cc == 6) src = 2;
+            else if (OFFS && cc == 3) src = 3;
+            else if (OFFS && cc == 4) src = 4;
+        } else {
+            src = cc;
+        }
+        if (src >= 0) {
+            for (int w = 0; w < TC_VW; ++w) sv += s_red[(w * NGROUP + cg) * 20 + d * NACC + src];
+        } else if (cc == 0 || cc == 2) {
+            for (int st = 0; st < 4; ++st) {
+                const double n_s = (double)((cn >> (16 * st)) & 0xffffull);
+                const double2 mw = S.stats[d * 4 + st][cg];
+                if (n_s > 0.0) sv += cc == 0 ? n_s * mw.y : n_s * (mw.y * (mw.x * mw.x));
+            }
+        }
+        if (S.ovf[cg] && cc == (KIND == 0 ? 1 : 0)) sv = __longlong_as_double(0x7ff8000000000000ll);
+        partial[((long long)(job * NGROUP + cg) * P + p) * 4 * HP + d * HP + cc] = sv;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_TMEM_COLS));
+}
+
+// A block pays ~10 us of set-up (TMEM, scale sampling, epilogue): short windows stay on
+// the DMMA kernel.  GPPD_HARMONICS=tensor / dmma forces one or the other.
+int harm_tc_min_rows() {
+    const char *e = getenv("GPPD_HARMONICS");     // read at every batch: the tests switch it
+    if (e && e[0] == 't') return 1;
+    if (e && e[0] == 'd') return 0x7fffffff;
+    return 4096;
+}
+
+void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                         unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_harm_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        cudaFuncSetAttribute(k_harm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        cudaFuncSetAttribute(k_harm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        attr = true;
+    }
+    dim3 grid(njobs, P);
+    if (const char *e = getenv("GPPD_TC_DBG")) flags |= (unsigned)atoi(e) << 24;   // timing experiments
+    if (flags & 2u) {
+        k_harm_tc<0, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
+        k_harm_tc<1, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);
+        *L.counter += 2;
+    } else {
+        k_harm_tc<0, false><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
+        *L.counter += 1;
+    }
+}
+
+}  // namespace gppd

@@ -45,9 +45,15 @@ void launch_circle(const Launcher &L, const TableDesc *d_tabs, int ntables, long
 // Jacobi-Anger harmonic sums of every fit + reduction into the harmonic table
 int harm_max_segments(long long max_rows_per_job);   // fixed 12288-row segments
 int stats_max_segments(long long max_rows_per_job);  // fixed 1024-row segments
+// tensor: the int8 tensor-core kernel (harm_tc_kernels.cu; dense METROLOGY tables only)
+// instead of the FP64 DMMA kernel (harm_kernels.cu; any layout)
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
-                      const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab);
+                      const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab,
+                      bool tensor);
+int harm_tc_min_rows();   // shortest job the tensor kernel is used for (GPPD_HARMONICS overrides)
+void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                         unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY);
 
 // the fit, harmonic evaluator (one thread per fit)
 void launch_fit_harmonic(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,

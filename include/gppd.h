@@ -233,6 +233,13 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
  */
 int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres);
 
+/*
+ * Test hook: the harmonic-sum table of the last batch of pipeline slot `slot`
+ * (value-major, [value][fit]; see csrc/gppd_device.cuh), so that the tests can hold the
+ * two implementations of the sums (FP64 DMMA, int8 tensor cores) against each other.
+ */
+int gppd_debug_harmonics(gppd_handle h, int slot, double *htab, int64_t nvals);
+
 /* number of kernels this library has launched on the handle so far */
 int64_t gppd_launch_count(gppd_handle h);
 

@@ -429,10 +429,11 @@ def test_edge_cases(gp, ora, method):
 
 
 @pytest.mark.parametrize("method", METHODS)
-def test_full_size_properties(gp, ora, method):
+def test_full_size_properties(gp, ora, method, monkeypatch):
     """BASELINE config sizes (1e5 rows): size-independent properties instead of
     an oracle run -- rotation preserves |d - c|, FC pass-through, b >= 0,
     recovery of the generating parameters, repeatability."""
+    monkeypatch.setenv("GPPD_HARMONICS", "dmma")   # one kernel for both layouts: bit-identical fits
     tab = make_case(gp.synthetic, 100_000, k=1)
     off = gp.synthetic.stefan_centres()
     t, z = gp.synthetic.to_complex(tab, off)
@@ -449,6 +450,16 @@ def test_full_size_properties(gp, ora, method):
     ref32 = np.empty((100_000, 80), np.float32)
     ref32[:, 0::2], ref32[:, 1::2] = out.real, out.imag
     assert np.array_equal(vout, ref32)
+    # default dispatch: the table's harmonic sums come from the int8 tensor-core kernel
+    # (sums equal to ~1e-15, so a NEWUOA trajectory can fork at a rounding-level tie)
+    monkeypatch.delenv("GPPD_HARMONICS")
+    vout3, p3, c3, i3, _ = gp.process_table(tab["time_us"], tab["volt"], tab["mjd"], offsets=off,
+                                            method=method)
+    same = np.abs(p3[:, 4] - par[:, 4]) <= REL_FIT * np.abs(par[:, 4])
+    assert same.sum() >= 24 and np.abs(p3[:, 4:6] - par[:, 4:6]).max() <= SOLVER_TOL
+    assert np.abs(c3 - like).max() <= 1e-6 * np.abs(like).max()
+    cols = np.repeat(same, 2)
+    assert np.abs(vout3[:, :64][:, cols] - ref32[:, :64][:, cols]).max() <= 2.0 ** -22 * np.abs(ref32[:, :64]).max()
 
 
 @pytest.mark.parametrize("n,window", [(5, None), (63, None), (257, None), (1237, 0.35), (2051, 1.0),

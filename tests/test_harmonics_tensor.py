@@ -1,0 +1,67 @@
+"""The two implementations of the harmonic sums (csrc/harm_kernels.cu: FP64 DMMA;
+csrc/harm_tc_kernels.cu: int8 tensor cores, 48-bit fixed point) held against each other
+through the `gppd_debug_harmonics` hook, and the tensor kernel's overflow fallback."""
+import numpy as np
+import pytest
+
+from conftest import make_case
+
+pytestmark = pytest.mark.gpu
+
+SUM_TOL = 2e-14      # |tensor - dmma| / largest sum of the fit (48-bit operands, exact products)
+
+
+def _htab(gp, monkeypatch, mode, tab, faint, offsets, nvals, **kw):
+    from gppd_b200 import _lib
+    monkeypatch.setenv("GPPD_HARMONICS", mode)
+    fs = tab["faintstates"]
+    fs_g = gp.FaintStates(fs.timer1, fs.timer2, 1.0, 2.0) if faint else None
+    res = gp.process_table(tab["time_us"], tab["volt"], tab["mjd"], offsets=offsets, faintparam=fs_g, **kw)
+    out = np.empty(nvals)
+    _lib.check(_lib.lib().gppd_debug_harmonics(_lib.default_handle().raw, 0, _lib.ptr(out), nvals))
+    return out.reshape(-1, 32), res
+
+
+@pytest.mark.parametrize("n,faint,fit,onlyhigh", [(700, False, False, False), (5000, False, False, False),
+                                                  (20011, True, False, False), (20011, True, False, True),
+                                                  (30000, False, True, False), (30000, True, True, False)])
+def test_tensor_sums_equal_dmma_sums(gp, ora, monkeypatch, n, faint, fit, onlyhigh):
+    tab = make_case(gp.synthetic, n, k=7, faint=faint, ora=ora)
+    off = None if fit else gp.synthetic.stefan_centres()
+    nv = (201 if fit else 103) * 32
+    a, ra = _htab(gp, monkeypatch, "dmma", tab, faint, off, nv, onlyhigh=onlyhigh)
+    b, rb = _htab(gp, monkeypatch, "tensor", tab, faint, off, nv, onlyhigh=onlyhigh)
+    assert not np.isnan(b).any()
+    err = np.abs(a - b) / np.abs(a).max(axis=0)
+    assert err.max() <= SUM_TOL, err.max()
+    assert (rb[3][:, 2] == 2).all()                       # harmonic evaluator, no fallback
+    assert np.abs(ra[1][:, 4:6] - rb[1][:, 4:6]).max() <= 2e-3
+
+
+def test_tensor_is_run_to_run_and_batch_independent(gp, ora, monkeypatch):
+    """Integer accumulation: the sums do not depend on the order of anything."""
+    tab = make_case(gp.synthetic, 30011, k=9, faint=True, ora=ora)
+    off = gp.synthetic.stefan_centres()
+    a, ra = _htab(gp, monkeypatch, "tensor", tab, True, off, 103 * 32)
+    b, rb = _htab(gp, monkeypatch, "tensor", tab, True, off, 103 * 32)
+    assert a.tobytes() == b.tobytes() and ra[0].tobytes() == rb[0].tobytes()
+
+
+def test_tensor_overflow_falls_back_to_direct(gp, ora, monkeypatch):
+    """A sample far outside the range the block sampled would wrap the fixed point: the
+    group's fits must go to the direct evaluator and still be right."""
+    tab = make_case(gp.synthetic, 20000, k=11)
+    off = gp.synthetic.stefan_centres()
+    volt = tab["volt"].copy()
+    row = 12345                                  # not one of the 128 sampled rows (multiples of n / 128)
+    assert (row * 128) % 20000 != 0
+    volt[row, 2 * 5] += 3000.0                   # diode 6 (group 2): |V| jumps by > 2^4 x the sampled maximum
+    tab2 = dict(tab, volt=volt)
+    a, ra = _htab(gp, monkeypatch, "dmma", tab2, False, off, 103 * 32)
+    b, rb = _htab(gp, monkeypatch, "tensor", tab2, False, off, 103 * 32)
+    grp = slice(4, 8)
+    assert np.isnan(b[1, grp]).all()                                   # poisoned sums of group 2
+    assert (rb[3][grp, 2] == 1).all() and (rb[3][:4, 2] == 2).all()    # direct evaluator for them only
+    # the direct evaluator agrees with the harmonic one on the other kernel to solver tolerance
+    assert np.abs(ra[1][grp, 4:6] - rb[1][grp, 4:6]).max() <= 2e-3
+    assert np.abs(ra[2][grp] - rb[2][grp]).max() <= 1e-6 * np.abs(ra[2][grp]).max()

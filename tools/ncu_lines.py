@@ -28,5 +28,5 @@ tot = sum(a[0] for a in byfile.values()); tots = sum(a[1] for a in byfile.values
 print("total warp-instr %.0f samples %.0f" % (tot, tots))
 for fn, a in sorted(byfile.items(), key=lambda x: -x[1][0]):
     print("  %-22s inst %5.1f%%  samples %5.1f%%" % (fn, 100 * a[0] / max(tot, 1), 100 * a[1] / max(tots, 1)))
-for fn, ln, src, d in sorted(rows, key=lambda x: -f(x[3], S))[:top]:
+for fn, ln, src, d in sorted(rows, key=lambda x: -f(x[3], K if len(sys.argv) > 4 else S))[:top]:
     print("%-18s %5d inst %5.2f%% smp %5.2f%% thr/inst %4.1f | %s" % (fn, ln, 100 * f(d, K) / max(tot, 1), 100 * f(d, S) / max(tots, 1), f(d, "Avg. Threads Executed"), src.strip()[:80]))
