@@ -428,6 +428,23 @@ def main():
             "peak_source": "FP64 micro-benchmark in this run (better of DFMA and mma.sync.m8n8k4.f64)",
             "objective_calls_per_fit": nfev_mean}
     fp64["frac"] = fp64["achieved_tflops"] / fp64_peak if (fp64_peak and fp64["achieved_tflops"]) else None
+    # which kernel computed the harmonic sums: the int8 tensor-core kernel takes dense tables
+    # with >= 4096 rows per fit (GPPD_HARMONICS=dmma|tensor overrides, csrc/harm_tc_kernels.cu)
+    env = os.environ.get("GPPD_HARMONICS", "")
+    tensor_mode = env[:1] == "t" or (env[:1] != "d" and (W or N) >= 4096)
+    tensor = None
+    if tensor_mode and harm_n:
+        # issued int8 work: per 32 rows four MMAs of M = 128, K = 32, N = 144 + 144 + 240 + 192
+        ops = F * N / 32.0 * 128 * 720 * 32 * 2
+        i8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
+        tensor = {"kernel": "harmonics", "instruction": "tcgen05.mma kind::i8 (48-bit fixed point, 6 x 6 byte digits)",
+                  "achieved_tops": ops / (harm_ms / harm_n * 1e-3) / 1e12, "peak_tops": i8_peak,
+                  "peak_source": "2 x the dense bf16 figure of MEASURED_PEAKS.json (int8 runs at twice the bf16 rate)"
+                                 if "bf16_tflops" in peaks else "nominal 4.5 POPS (B200_PROFILING.md fallback)",
+                  "fp64_equivalent_tflops": fp64["achieved_tflops"]}
+        tensor["frac"] = tensor["achieved_tops"] / i8_peak
+        fp64["note"] = ("harmonic sums ran on the int8 tensor cores: achieved_tflops is the FP64 work they "
+                        "replace (192 flop per diode-sample), not FP64 instructions issued")
     traffic = None   # DRAM bytes per launch of the dominant pass, from the committed ncu capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
@@ -441,10 +458,12 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_ms, "launches_timed": dom_n,
                 "pass_ms_per_step": {k: v[0] / args.steps for k, v in passes.items() if v[1]},
-                "fp64": fp64,
-                "note": "one launch of each pass covers the whole night; the dominant (harmonic) pass "
-                        "is bound by the FP64 units, not by HBM (see fp64: its 192 flop per "
-                        "diode-sample against 20 B); the demod pass is the HBM-bound one"}
+                "fp64": fp64, "tensor": tensor,
+                "harmonics_kernel": "k_harm_tc (int8 tensor cores)" if tensor_mode else "k_harm_ws (FP64 DMMA)",
+                "note": ("one launch of each pass covers the whole night; the harmonic pass does 192 FP64-equivalent "
+                         "flop per diode-sample against 20 B: on the FP64 units (k_harm_ws) it is bound by them; "
+                         "as exact fixed-point int8 MMAs (k_harm_tc) it is bound by the producers' issue rate "
+                         "(digit extraction), see DESIGN.md section 5; the demod pass is the HBM-bound one")}
 
     # ---- CPU baseline on a bounded sample -------------------------------
     cpu = None

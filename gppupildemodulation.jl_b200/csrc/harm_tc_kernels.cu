@@ -22,12 +22,15 @@
 // digit j lands in TMEM column block i + j - 2, so every block collects one power of 256
 // (2 + block for lanes 0..63, 5 + block for lanes 64..127) and four MMAs per 32 rows do
 // all 36 digit pairs (measured issue cost 46 + N / 2 cycles per MMA: ~540 cycles per 32
-// rows against ~2750 for the DMMA kernel).
+// rows against ~2750 for the DMMA kernel; the kernel as a whole runs at ~1350: the
+// producers' digit extraction -- byte permutes on the half-rate integer pipe -- and the
+// per-K-block hand-over latencies set the pace, not the tensor pipe).
 //
-// Block = (job, segment).  Warp roles: 8 V producers (thread = (row, group): stream
-// values, constant sums, digits -> MN-major operand tile), 4 E producers (lane = row:
-// the 24 harmonics by complex products of depth <= 5, digits -> operand tile), 1 MMA
-// issuer, 1 TMA loader (raw rows + basis, cp.async.bulk into an 8-deep ring).  mbarriers
+// Block = (job, segment), 20 warps (5 per sub-partition at 96 registers).  Warp roles:
+// 16 V producers in two sets that alternate K-blocks (thread = (row, group): stream values,
+// constant sums, digits -> MN-major operand tile), 2 E producers (lane = row: the 24
+// harmonics by complex products of depth <= 5, digits -> operand tile), 1 MMA issuer,
+// 1 TMA loader (raw rows + basis, cp.async.bulk into an 8-deep ring).  mbarriers
 // hand the raw ring (loader -> producers) and the operand ring (producers -> MMA ->
 // tcgen05.commit) over.  The epilogue reads the six int32 blocks from TMEM, combines them
 // in FP64 (exact up to the final roundings) and writes the same partial-sum layout as
@@ -243,16 +246,8 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
         const int i = kb * TC_KB + krow;
         const int st = st_next;
         if (FAINT && i + TC_VSETS * TC_KB < nseg) st_next = stp[(long long)(kb + TC_VSETS) * TC_KB];
-        if (!(flags & (32u << 24))) tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+        tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
         const unsigned char *rw = rw0 + rs * TC_RAW_BYTES;
-        if (flags & (16u << 24)) {
-            __syncwarp();
-            if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
-            tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
-            __syncwarp();
-            if (lane == 0) tc_arrive(b_op_full + 8 * os);
-            continue;
-        }
         const uint4 wa = *reinterpret_cast<const uint4 *>(rw);
         const uint4 wb = *reinterpret_cast<const uint4 *>(rw + 16);
         uint2 wf = *reinterpret_cast<const uint2 *>(rw + 256 - 24 * g);     // row + 256 + 8 g
@@ -266,7 +261,7 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
         double2 vv[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
-        const bool valid = i < nseg && (!FAINT || row_valid(st, flags)) && !(flags & (4u << 24));
+        const bool valid = i < nseg && (!FAINT || row_valid(st, flags));
         if (valid) {
             double2 dd[4];
 #pragma unroll
@@ -303,7 +298,7 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
 #pragma unroll
         for (int j = 0; j < TC_ND; ++j)
             *reinterpret_cast<uint2 *>(vt + ((j % 3) * 8 + (j / 3) * 4) * V_SBO) = make_uint2(dlo[j], dhi[j]);
-        if (!(flags & (2u << 24))) fence_async_smem();
+        fence_async_smem();
         __syncwarp();
         if (lane == 0) tc_arrive(b_op_full + 8 * os);
     }
@@ -423,7 +418,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         // ---- TMA loader: raw rows + basis of K-block kb into ring stage kb % TC_RS --------
         const char *volt = reinterpret_cast<const char *>(tv.volt);
         const bool dense = tv.volt_stride == 320;
-        for (int kb = 0; kb < ((flags & (32u << 24)) ? 0 : nkb); ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
             const int rs = kb % TC_RS;
             mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
             const int rows = min(TC_KB, nseg - kb * TC_KB);
@@ -442,22 +437,23 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         // ---- MMA issuer ----------------------------------------------------------------------
         constexpr uint32_t ID144 = tc_idesc(144), ID192 = tc_idesc(192), ID240 = tc_idesc(240);
         const uint32_t b_op_full = smem_u32(&S.op_full[0]);
+        const uint64_t dv0 = tc_desc(smem_u32(op_ring), V_LBO, V_SBO);
+        const uint64_t de0 = tc_desc(smem_u32(op_ring) + V_TILE, E_LBO, E_SBO);
         for (int kb = 0; kb < nkb; ++kb) {
             const int os = kb % TC_OS;
             tc_wait(b_op_full + 8 * os, (kb / TC_OS) & 1);
             tc_fence_after();
             if (tc_elect()) {
-                const uint32_t vb = smem_u32(op_ring + os * TC_OP_BYTES), eb = vb + V_TILE;
+                // descriptors of stage os: the stage's byte offset / 16 added to the address field
+                const uint64_t so = (uint64_t)((os * TC_OP_BYTES) >> 4);
+                const uint64_t av = dv0 + so, be = de0 + so;
                 const uint32_t acc = kb > 0 ? 1u : 0u;
                 // digits (2, 5) x E digits 0..2 and 3..5 first: they cover all six blocks
-                const uint64_t a2 = tc_desc(vb + 2 * 8 * V_SBO, V_LBO, V_SBO);
-                if (!(flags & (1u << 24))) {
-                tc_mma(tmem, a2, tc_desc(eb, E_LBO, E_SBO), ID144, acc);
-                tc_mma(tmem + 144, a2, tc_desc(eb + 9 * E_SBO, E_LBO, E_SBO), ID144, acc);
+                tc_mma(tmem, av + ((2 * 8 * V_SBO) >> 4), be, ID144, acc);
+                tc_mma(tmem + 144, av + ((2 * 8 * V_SBO) >> 4), be + ((9 * E_SBO) >> 4), ID144, acc);
                 // digits (1, 4) x E digits 1..5 -> blocks 0..4;  digits (0, 3) x E digits 2..5 -> blocks 0..3
-                tc_mma(tmem, tc_desc(vb + 8 * V_SBO, V_LBO, V_SBO), tc_desc(eb + 3 * E_SBO, E_LBO, E_SBO), ID240, 1u);
-                tc_mma(tmem, tc_desc(vb, V_LBO, V_SBO), tc_desc(eb + 6 * E_SBO, E_LBO, E_SBO), ID192, 1u);
-                }
+                tc_mma(tmem, av + ((8 * V_SBO) >> 4), be + ((3 * E_SBO) >> 4), ID240, 1u);
+                tc_mma(tmem, av, be + ((6 * E_SBO) >> 4), ID192, 1u);
                 tc_commit(&S.op_empty[os]);
                 if (kb == nkb - 1) tc_commit(&S.acc_full);
             }
@@ -471,7 +467,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 #pragma unroll 1
         for (int kb = e; kb < nkb; kb += TC_EW) {
             const int rs = kb % TC_RS, os = kb % TC_OS;
-            if (!(flags & (32u << 24))) tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+            tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
             const uint4 bw = *reinterpret_cast<const uint4 *>(raw_ring + rs * TC_RAW_BYTES + TC_RAW_VOLT + lane * 16);
             // basis = (sin theta, cos theta)
             double2 e1 = make_double2(__hiloint2double(bw.w, bw.z), __hiloint2double(bw.y, bw.x));
@@ -490,7 +486,6 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
             if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
             tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
             unsigned char *et = op_ring + os * TC_OP_BYTES + V_TILE + (lane >> 3) * E_LBO + (lane & 7) * 16;
-            if (!(flags & (8u << 24)))
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 // harmonics 8 a + 1 .. 8 a + 8: 16 values = one 16-byte atom row per digit
@@ -518,7 +513,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
                     for (int q = 0; q < 8; ++q) eh[q] = tc_cmul(eh[q], e8);
                 }
             }
-            if (!(flags & (2u << 24))) fence_async_smem();
+            fence_async_smem();
             __syncwarp();
             if (lane == 0) tc_arrive(b_op_full + 8 * os);
         }
@@ -638,7 +633,6 @@ void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobIn
         attr = true;
     }
     dim3 grid(njobs, P);
-    if (const char *e = getenv("GPPD_TC_DBG")) flags |= (unsigned)atoi(e) << 24;   // timing experiments
     if (flags & 2u) {
         k_harm_tc<0, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
         k_harm_tc<1, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);

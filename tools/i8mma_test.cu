@@ -48,7 +48,7 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
 }
 
 __global__ void __launch_bounds__(128) k_test(const int8_t *A, const int8_t *B, int nk, int swap, int reps,
-                                              int32_t *D, long long *cycles) {
+                                              int32_t *D, long long *cycles, int dcol = 0) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) k_test(const int8_t *A, const int8_t *B, 
             for (int kb = 0; kb < nk; ++kb) {
                 uint64_t da = make_desc(smem_u32(sa + kb * A_TILE), swap ? A_SBO : A_LBO, swap ? A_LBO : A_SBO);
                 uint64_t db = make_desc(smem_u32(sb + kb * B_TILE), swap ? B_SBO : B_LBO, swap ? B_LBO : B_SBO);
-                mma_i8(tmem, da, db, idesc, (r > 0 || kb > 0) ? 1u : 0u);
+                mma_i8(tmem + dcol, da, db, idesc, (r > 0 || kb > 0) ? 1u : 0u);
             }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&s_bar)) : "memory");
     }
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) k_test(const int8_t *A, const int8_t *B, 
     const int lane = threadIdx.x & 31;
     for (int c0 = 0; c0 < N; c0 += 16) {
         uint32_t v[16];
-        uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+        uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + c0 + dcol;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -216,6 +216,20 @@ int main(int argc, char **argv) {
         printf("swap=%d (LBO/SBO %s): mismatches 16x4 layout %lld, linear layout %lld of %d; D[0][0..3] = %d %d %d %d ref %lld %lld %lld %lld\n",
                swap, swap ? "swapped" : "as documented", bad, bad_lin, M * N, D[0], D[1], D[2], D[3], ref[0], ref[1],
                ref[2], ref[3]);
+    }
+    // accumulator at a column offset that is not a multiple of 4 / 8 / 16
+    for (int dcol : {1, 2, 3, 5}) {
+        CK(cudaMemset(dD, 0xff, 128 * N * 4));
+        k_test<<<1, 128, smem>>>(dA, dB, nk, 0, 1, dD, dC, dcol);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("dcol=%d: CUDA error %s\n", dcol, cudaGetErrorString(e)); return 1; }
+        std::vector<int32_t> D(128 * N);
+        CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+        long long bad = 0;
+        for (int m = 0; m < M; ++m)
+            for (int n = 0; n < N; ++n)
+                if (D[((m & 15) + 32 * (m >> 4)) * N + n] != ref[m * N + n]) ++bad;
+        printf("D column offset %d: mismatches %lld of %d\n", dcol, bad, M * N);
     }
     // issue rate (results overflow; only the time matters)
     for (int reps : {64, 256}) {
