@@ -249,8 +249,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     bool tensor = max_wrows >= harm_tc_min_rows();
     for (int t = 0; t < T; ++t) {
         const TableView &v = td[t].tv;
-        if (v.kind != 0 || (reinterpret_cast<unsigned long long>(v.volt) & 15ull) || (v.volt_stride & 15) ||
-            v.volt_stride < 320)
+        if (v.kind != 0 || (reinterpret_cast<unsigned long long>(v.volt) & 15ull) || v.volt_stride != 320)
             tensor = false;
     }
 

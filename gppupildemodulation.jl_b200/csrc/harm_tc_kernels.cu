@@ -15,7 +15,10 @@
 // and  sum_rows X_V X_E = sum_{i,j} 256^(i+j) sum_rows a_i b_j  is accumulated digit pair
 // by digit pair in int32.  Pairs with i + j < 5 (below 2^-45 of the result) are not all
 // formed.  The digits come for free: v 2^F + (2^52 + 2^51 + 0x808080808080) puts
-// X + 0x80..80 into the low 48 mantissa bits, whose bytes are a_i + 128.
+// X + 0x80..80 into the low 48 mantissa bits, whose bytes are a_i + 128.  (Multiplying the
+// E digits as unsigned biased bytes and removing the bias with the columns' plain sums in
+// the epilogue saves the XOR but amplifies V's rounding noise: measured 4 % faster and 7x
+// less accurate, not kept.)
 //
 // One MMA takes A = [V digit i ; V digit i + 3] (M = 128: two digits stacked along M) and
 // B = [E digit j0 | E digit j0 + 1 | ...] (N = 48 per digit): the product of digit i with
@@ -416,8 +419,9 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 
     if (warp == TC_LOAD_WARP) {
         // ---- TMA loader: raw rows + basis of K-block kb into ring stage kb % TC_RS --------
+        // (rows of 80 floats, back to back and 16-byte aligned: the dispatcher sends every
+        // other layout to the DMMA kernel)
         const char *volt = reinterpret_cast<const char *>(tv.volt);
-        const bool dense = tv.volt_stride == 320;
         for (int kb = 0; kb < nkb; ++kb) {
             const int rs = kb % TC_RS;
             mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
@@ -427,11 +431,9 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
             if (lane == 0) {
                 mbar_expect_tx(&S.raw_full[rs], (unsigned)rows * 336u);
                 bulk_g2s(dst + TC_RAW_VOLT, tb.basis + row, (unsigned)rows * 16u, &S.raw_full[rs]);
-                if (dense) bulk_g2s(dst, volt + row * 320, (unsigned)rows * 320u, &S.raw_full[rs]);
+                bulk_g2s(dst, volt + row * 320, (unsigned)rows * 320u, &S.raw_full[rs]);
             }
             __syncwarp();
-            if (!dense && lane < rows)
-                bulk_g2s(dst + lane * 320, volt + (row + lane) * tv.volt_stride, 320u, &S.raw_full[rs]);
         }
     } else if (warp == TC_MMA_WARP) {
         // ---- MMA issuer ----------------------------------------------------------------------
