@@ -462,7 +462,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
             __syncwarp();
         }
     } else if (warp >= TC_VW) {
-        // ---- E producers: lane = row, K-blocks e, e + 4, ... ---------------------------------
+        // ---- E producers: lane = row, K-blocks e, e + TC_EW, ... ------------------------------
         const int e = warp - TC_VW;
         const uint32_t b_raw_full = smem_u32(&S.raw_full[0]), b_raw_empty = smem_u32(&S.raw_empty[0]);
         const uint32_t b_op_full = smem_u32(&S.op_full[0]), b_op_empty = smem_u32(&S.op_empty[0]);
