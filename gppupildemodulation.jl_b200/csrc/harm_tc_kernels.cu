@@ -31,9 +31,10 @@
 //
 // Block = (job, segment), 20 warps (5 per sub-partition at 96 registers).  Warp roles:
 // 16 V producers in two sets that alternate K-blocks (thread = (row, group): stream values,
-// constant sums, digits -> MN-major operand tile), 2 E producers (lane = row: the 24
-// harmonics by complex products of depth <= 5, digits -> operand tile), 1 MMA issuer,
-// 1 TMA loader (raw rows + basis, cp.async.bulk into an 8-deep ring).  mbarriers
+// constant sums, digits -> MN-major operand tile), 3 E producers that take K-blocks in
+// turn (lane = row: the 24 harmonics by complex products of depth <= 5, digits -> operand
+// tile), 1 control warp: MMA issuer and TMA loader (raw rows + basis, cp.async.bulk into
+// an 8-deep ring).  mbarriers
 // hand the raw ring (loader -> producers) and the operand ring (producers -> MMA ->
 // tcgen05.commit) over.  The epilogue reads the six int32 blocks from TMEM, combines them
 // in FP64 (exact up to the final roundings) and writes the same partial-sum layout as
@@ -57,9 +58,9 @@ constexpr int TC_KB = 32;                     // rows per K-block = K of one int
 constexpr int TC_RS = 8;                      // raw ring stages
 constexpr int TC_OS = 4;                      // operand ring stages
 constexpr int TC_VSETS = 2;                   // V producer sets: set s takes K-blocks s, s + 2, ...
-constexpr int TC_VW = 8 * TC_VSETS, TC_EW = 2; // V / E producer warps (8 V warps per K-block)
-constexpr int TC_MMA_WARP = TC_VW + TC_EW, TC_LOAD_WARP = TC_MMA_WARP + 1;
-constexpr int TC_WARPS = TC_LOAD_WARP + 1;
+constexpr int TC_VW = 8 * TC_VSETS, TC_EW = 3; // V / E producer warps (8 V warps per K-block)
+constexpr int TC_MMA_WARP = TC_VW + TC_EW;    // control warp: MMA issuer + TMA loader
+constexpr int TC_WARPS = TC_MMA_WARP + 1;     // 20 warps: 5 per sub-partition at 96 registers
 constexpr int TC_THREADS = TC_WARPS * 32;
 constexpr int TC_RAW_VOLT = TC_KB * 320;
 constexpr int TC_RAW_BYTES = TC_RAW_VOLT + TC_KB * 16;         // + basis
@@ -81,6 +82,7 @@ static_assert(TC_SEG_ROWS * 3ll * 16384 < (1ll << 31), "int32 accumulators");
 // 2^52 + 2^51 + 0x808080808080: ulp 1, bytes 0..5 of (v + this) are the digits + 128
 #define TC_MAGIC 6896688841130112.0
 constexpr uint32_t TC_MAGIC_HI = 0x43388080u;  // high word of TC_MAGIC
+
 
 __device__ __forceinline__ bool tc_elect() {
     uint32_t pred;
@@ -417,12 +419,20 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     for (int q = 0; q < NACC * 4; ++q) cst[q] = 0.0;
     unsigned long long cnt = 0;
 
-    if (warp == TC_LOAD_WARP) {
-        // ---- TMA loader: raw rows + basis of K-block kb into ring stage kb % TC_RS --------
-        // (rows of 80 floats, back to back and 16-byte aligned: the dispatcher sends every
-        // other layout to the DMMA kernel)
+    if (warp == TC_MMA_WARP) {
+        // ---- control warp: MMA issuer + TMA loader -------------------------------------------
+        // The raw rows + basis of K-block kb go to ring stage kb % TC_RS (rows of 80 floats, back
+        // to back and 16-byte aligned: the dispatcher sends every other layout to the DMMA
+        // kernel).  The first TC_RS K-blocks are loaded up front; K-block k + TC_RS is loaded
+        // right after the MMAs of K-block k have been issued -- every producer of k has then
+        // released the raw stage (it does so before it arrives on the operand barrier), so
+        // the wait below never blocks and the loader cannot starve the producers.
+        constexpr uint32_t ID144 = tc_idesc(144), ID192 = tc_idesc(192), ID240 = tc_idesc(240);
+        const uint32_t b_op_full = smem_u32(&S.op_full[0]);
+        const uint64_t dv0 = tc_desc(smem_u32(op_ring), V_LBO, V_SBO);
+        const uint64_t de0 = tc_desc(smem_u32(op_ring) + V_TILE, E_LBO, E_SBO);
         const char *volt = reinterpret_cast<const char *>(tv.volt);
-        for (int kb = 0; kb < nkb; ++kb) {
+        auto load = [&](int kb) {
             const int rs = kb % TC_RS;
             mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
             const int rows = min(TC_KB, nseg - kb * TC_KB);
@@ -434,13 +444,8 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
                 bulk_g2s(dst, volt + row * 320, (unsigned)rows * 320u, &S.raw_full[rs]);
             }
             __syncwarp();
-        }
-    } else if (warp == TC_MMA_WARP) {
-        // ---- MMA issuer ----------------------------------------------------------------------
-        constexpr uint32_t ID144 = tc_idesc(144), ID192 = tc_idesc(192), ID240 = tc_idesc(240);
-        const uint32_t b_op_full = smem_u32(&S.op_full[0]);
-        const uint64_t dv0 = tc_desc(smem_u32(op_ring), V_LBO, V_SBO);
-        const uint64_t de0 = tc_desc(smem_u32(op_ring) + V_TILE, E_LBO, E_SBO);
+        };
+        for (int kb = 0; kb < min(TC_RS, nkb); ++kb) load(kb);
         for (int kb = 0; kb < nkb; ++kb) {
             const int os = kb % TC_OS;
             tc_wait(b_op_full + 8 * os, (kb / TC_OS) & 1);
@@ -460,6 +465,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
                 if (kb == nkb - 1) tc_commit(&S.acc_full);
             }
             __syncwarp();
+            if (kb + TC_RS < nkb) load(kb + TC_RS);
         }
     } else if (warp >= TC_VW) {
         // ---- E producers: lane = row, K-blocks e, e + TC_EW, ... ------------------------------
