@@ -393,6 +393,22 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 #pragma unroll
             for (int d = 0; d < 4; ++d) mx[d] = fmax(mx[d], fmax(fabs(vv[d].x), fabs(vv[d].y)));
         }
+        if (faint && r == 0) {
+            // FAINT: rows of a state that the sample missed (a state can be rare in a window
+            // and then carries a large weight 1 / var): bound |V| from the per-state table,
+            // |d| <= mean + 8 sigma, so that such rows are inside the fixed-point range
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const double amu = OFFS ? hypot(mu[d].x, mu[d].y) : 0.0;
+                for (int st = 0; st < 4; ++st) {
+                    const double2 mw = S.stats[d * 4 + st][g];
+                    if (!(mw.y > 0.0 && mw.y < 1.0e300 && mw.x >= 0.0 && mw.x < 1.0e300)) continue;
+                    const double wm = mw.y * mw.x;
+                    const double bound = KIND == 0 ? wm * (mw.x + amu + 8.0 * rsqrt(mw.y)) : wm;
+                    mx[d] = fmax(mx[d], bound);
+                }
+            }
+        }
 #pragma unroll
         for (int d = 0; d < 4; ++d)
             if (mx[d] > 0.0 && mx[d] < 1.0e300)

@@ -65,3 +65,23 @@ def test_tensor_overflow_falls_back_to_direct(gp, ora, monkeypatch):
     # the direct evaluator agrees with the harmonic one on the other kernel to solver tolerance
     assert np.abs(ra[1][grp, 4:6] - rb[1][grp, 4:6]).max() <= 2e-3
     assert np.abs(ra[2][grp] - rb[2][grp]).max() <= 1e-6 * np.abs(ra[2][grp]).max()
+
+
+@pytest.mark.parametrize("wrows", [4100, 5003, 7001])
+def test_tensor_faint_windows_with_rare_states(gp, ora, monkeypatch, wrows):
+    """Window boundaries cut state runs: a window can hold a handful of rows of a state,
+    whose weight 1 / var is then huge.  The fixed-point scale must cover them (from the
+    per-state table), not send the fits to the fallback."""
+    tab = make_case(gp.synthetic, 30011, k=13, faint=True, ora=ora)
+    off = gp.synthetic.stefan_centres()
+    dt = float(np.diff(ora.make_times(tab["time_us"][:2], tab["mjd"]))[0])
+    window = wrows * dt
+    nwin = -(-30011 // wrows)
+    a, ra = _htab(gp, monkeypatch, "dmma", tab, True, off, 103 * 32 * nwin, window=window)
+    b, rb = _htab(gp, monkeypatch, "tensor", tab, True, off, 103 * 32 * nwin, window=window)
+    assert rb[3].shape[0] == 32 * nwin and (rb[3][:, 2] == ra[3][:, 2]).all()   # same evaluator per fit
+    ok = ~np.isnan(a)
+    assert (np.isnan(b) == np.isnan(a)).all()
+    scale = np.nanmax(np.abs(a).reshape(103, -1), axis=0)
+    err = np.abs(np.where(ok, a - b, 0.0)).reshape(103, -1) / scale
+    assert np.nanmax(err) <= 10 * SUM_TOL, np.nanmax(err)
