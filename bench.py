@@ -428,10 +428,9 @@ def main():
             "peak_source": "FP64 micro-benchmark in this run (better of DFMA and mma.sync.m8n8k4.f64)",
             "objective_calls_per_fit": nfev_mean}
     fp64["frac"] = fp64["achieved_tflops"] / fp64_peak if (fp64_peak and fp64["achieved_tflops"]) else None
-    # which kernel computed the harmonic sums: the int8 tensor-core kernel takes dense tables
-    # with >= 4096 rows per fit (GPPD_HARMONICS=dmma|tensor overrides, csrc/harm_tc_kernels.cu)
-    env = os.environ.get("GPPD_HARMONICS", "")
-    tensor_mode = env[:1] == "t" or (env[:1] != "d" and (W or N) >= 4096)
+    # which kernel computed the harmonic sums: the int8 tensor-core kernel takes every dense
+    # table (GPPD_HARMONICS=dmma forces the FP64 DMMA kernel, csrc/harm_tc_kernels.cu)
+    tensor_mode = os.environ.get("GPPD_HARMONICS", "")[:1] != "d"
     tensor = None
     if tensor_mode and harm_n:
         # issued int8 work: per 32 rows four MMAs of M = 128, K = 32, N = 144 + 144 + 240 + 192

@@ -245,7 +245,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     const bool direct = method == GPPD_METHOD_DIRECT;
     // the int8 tensor-core form of the harmonic sums takes dense METROLOGY tables (rows of
     // 80 floats, 16-byte aligned); the other layouts use the FP64 DMMA kernel.
-    // GPPD_HARMONICS=dmma|tensor overrides (tensor is ignored for layouts it cannot take).
+    // GPPD_HARMONICS=dmma forces the DMMA kernel everywhere.
     bool tensor = max_wrows >= harm_tc_min_rows();
     for (int t = 0; t < T; ++t) {
         const TableView &v = td[t].tv;
