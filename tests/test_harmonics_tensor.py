@@ -85,3 +85,36 @@ def test_tensor_faint_windows_with_rare_states(gp, ora, monkeypatch, wrows):
     scale = np.nanmax(np.abs(a).reshape(103, -1), axis=0)
     err = np.abs(np.where(ok, a - b, 0.0)).reshape(103, -1) / scale
     assert np.nanmax(err) <= 10 * SUM_TOL, np.nanmax(err)
+
+
+@pytest.mark.parametrize("n", [5000, 40000])
+def test_objective_from_tensor_sums_matches_oracle(gp, ora, monkeypatch, n):
+    """The objective rebuilt (in numpy) from the tensor kernel's harmonic table,
+        sum_n conj(e_n) z_n = sum_k J_k(b) e^{-jkq} Z_k,   chi2 N = S_dd - |S_gd|^2 / S_gg,
+    against the oracle's O(N) evaluation of the reference objective (src/Modulation.jl:323-326)
+    at 1e-10, for (b, phi) over the range the solver visits."""
+    from scipy.special import jv
+    tab = make_case(gp.synthetic, n, k=17)
+    off = gp.synthetic.stefan_centres()
+    H, _ = _htab(gp, monkeypatch, "tensor", tab, False, off, 103 * 32)
+    t, z = gp.synthetic.to_complex(tab, off)
+    theta = ora.M_2PI * t                                 # fl(omega * t), like the reference
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for ch in (0, 7, 18, 31):
+        fc = np.exp(1j * np.angle(z[:, 32 + ch // 4]))
+        h = H[:, ch]
+        sdd, sgg = h[1], h[2]
+        k = np.arange(1, 25)
+        A, B, C, D = (h[7 + 4 * (k - 1) + s] for s in range(4))
+        Zp, Zm, Z0 = (A + B) + 1j * (C - D), (A - B) + 1j * (C + D), h[5] + 1j * h[6]
+        for _ in range(6):
+            b, phi = rng.uniform(0.05, 3.0), rng.uniform(-np.pi, np.pi)
+            q = (theta + phi) - theta                     # the phase quantum: uniform over the table
+            assert np.ptp(q) == 0.0
+            q = q[0]
+            S = jv(0, b) * Z0 + np.sum(jv(k, b) * (np.exp(-1j * k * q) * Zp + (-1.0) ** k * np.exp(1j * k * q) * Zm))
+            f = (sdd - abs(S) ** 2 / sgg) / n
+            fo = ora.chi2(t, z[:, ch], fc, b, phi)[0]
+            worst = max(worst, abs(f - fo) / fo)
+    assert worst <= 1e-10, worst
