@@ -118,3 +118,42 @@ def test_objective_from_tensor_sums_matches_oracle(gp, ora, monkeypatch, n):
             fo = ora.chi2(t, z[:, ch], fc, b, phi)[0]
             worst = max(worst, abs(f - fo) / fo)
     assert worst <= 1e-10, worst
+
+
+def _fit_both(gp, monkeypatch, tab, volt, off):
+    out = {}
+    for mode in ("dmma", "tensor"):
+        monkeypatch.setenv("GPPD_HARMONICS", mode)
+        out[mode] = gp.process_table(tab["time_us"], volt, tab["mjd"], offsets=off)
+    return out["dmma"], out["tensor"]
+
+
+def test_tensor_unusual_inputs(gp, ora, monkeypatch):
+    """Inputs outside the comfortable range: the tensor kernel either agrees with the FP64
+    kernel or hands the fit to the direct evaluator -- it never returns something else."""
+    tab = make_case(gp.synthetic, 9000, k=19)
+    off = gp.synthetic.stefan_centres()
+    base = tab["volt"]
+    # (1) diodes of very different amplitude in one group (per-diode scales)
+    v = base.copy()
+    v[:, 0:2] = (v[:, 0:2] - off[0].real) * 1e-4 + off[0].real
+    v[:, 2:4] *= 300.0
+    a, b = _fit_both(gp, monkeypatch, tab, v, off)
+    assert np.isfinite(b[1]).all()
+    assert np.abs(a[1][:, 4:6] - b[1][:, 4:6]).max() <= 2e-3
+    # (2) a NaN and an Inf sample: the group goes to the direct evaluator, like the FP64 path
+    #     the results are whatever the reference arithmetic gives (NaN), in both kernels
+    v = base.copy()
+    v[1234, 8] = np.nan
+    v[4321, 17] = np.inf
+    a, b = _fit_both(gp, monkeypatch, tab, v, off)
+    # the NaN sits in channel 4 (floats 8, 9: group 1), the Inf in channel 8 (floats 16, 17: group 2)
+    for ch in (4, 8):
+        assert np.isnan(a[1][ch, 4]) == np.isnan(b[1][ch, 4])
+    ok = [ch for ch in range(32) if ch // 4 not in (1, 2)]
+    assert np.abs(a[1][ok, 4:6] - b[1][ok, 4:6]).max() <= 2e-3
+    # (3) a table of zeros and a constant table: no crash, same evaluator decisions
+    for v in (np.zeros_like(base), np.full_like(base, 0.25)):
+        a, b = _fit_both(gp, monkeypatch, tab, v, off)
+        assert np.array_equal(np.isnan(a[1]), np.isnan(b[1]))
+        assert np.array_equal(np.isfinite(a[0]), np.isfinite(b[0]))
