@@ -228,8 +228,9 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
 /*
  * The centres the last GPPD_CENTER_EMPIRICAL call on pipeline slot `slot` fitted and
  * subtracted: centres [ntables][40] complex128 (ntables = 1 for the single-table entry
- * points).  Waits for the slot's stream.  A channel without a circle (fewer than 3
- * samples, or all on one line) has centre 0.
+ * points).  Waits for the slot's own stream (after a *_dev call on a caller-supplied
+ * stream the caller synchronises that stream first).  A channel without a circle (fewer
+ * than 3 samples, or all on one line) has centre 0.
  */
 int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres);
 
