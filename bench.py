@@ -339,9 +339,28 @@ def main():
     e1.record(bench_stream)
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    passes = h.pass_times(reset=True)
+    passes_overlapped = h.pass_times(reset=True)
     h.enable_timing(False)
     launches = h.launches - launches0
+    # ---- per-pass kernel times: a second region of the same K steps with ONE launch
+    # sequence per batch.  In the throughput region above the FAINT and the bright tables
+    # run as two concurrent chains (gppd_set_split_chains, default on), whose kernels
+    # share the SMs and stretch each other's event-timed durations; the roofline of a
+    # kernel needs its own duration.
+    split_default = os.environ.get("GPPD_SPLIT_CHAINS", "1")[:1] != "0"
+    passes = passes_overlapped
+    if split_default:
+        h.set_split_chains(False)
+        step_resident()
+        barrier()
+        h.enable_timing(True)
+        h.pass_times(reset=True)
+        for _ in range(args.steps):
+            step_resident()
+        barrier()
+        passes = h.pass_times(reset=True)
+        h.enable_timing(False)
+        h.set_split_chains(True)
     tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -457,6 +476,11 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": avg_ms, "launches_timed": dom_n,
                 "pass_ms_per_step": {k: v[0] / args.steps for k, v in passes.items() if v[1]},
+                "pass_timing": ("second region of the same %d steps in this run with one launch sequence per "
+                                "batch (gppd_set_split_chains(0)): in the throughput region the FAINT and the "
+                                "bright chain run concurrently and stretch each other's kernel durations"
+                                % args.steps) if split_default else "throughput region",
+                "pass_ms_per_step_overlapped": {k: v[0] / args.steps for k, v in passes_overlapped.items() if v[1]},
                 "fp64": fp64, "tensor": tensor,
                 "harmonics_kernel": "k_harm_tc (int8 tensor cores)" if tensor_mode else "k_harm_ws (FP64 DMMA)",
                 "note": ("one launch of each pass covers the whole night; the harmonic pass does 192 FP64-equivalent "

@@ -80,6 +80,7 @@ def lib():
         _i32p, _i8p]
     L.gppd_wait.argtypes = [H, C.c_int]
     L.gppd_centres.argtypes = [H, C.c_int, C.c_int64, _dp]
+    L.gppd_set_split_chains.argtypes = [H, C.c_int]
     L.gppd_debug_harmonics.argtypes = [H, C.c_int, _dp, C.c_int64]
     L.gppd_num_slots.argtypes = [H]
     L.gppd_process_table_f32_dev.argtypes = [
@@ -98,7 +99,7 @@ def lib():
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
-                 "gppd_submit_fits_rows", "gppd_centres", "gppd_debug_harmonics",
+                 "gppd_submit_fits_rows", "gppd_centres", "gppd_debug_harmonics", "gppd_set_split_chains",
                  "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",
                  "gppd_process_tables_f32_dev", "gppd_enable_timing",
                  "gppd_pass_times", "gppd_measure_fp64_peak"):
@@ -158,6 +159,10 @@ class Handle:
 
     def enable_timing(self, on: bool = True):
         check(lib().gppd_enable_timing(self._h, int(on)))
+
+    def set_split_chains(self, on: bool = True):
+        """FAINT and bright tables of a batch as two concurrent launch sequences (default on)."""
+        check(lib().gppd_set_split_chains(self._h, int(on)))
 
     def pass_times(self, reset: bool = True):
         """{pass: (total ms, launches)} measured with CUDA events on the launching stream."""

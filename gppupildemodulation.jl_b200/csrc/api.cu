@@ -109,6 +109,12 @@ struct Slot {
 struct gppd_handle_s {
     int device = 0;
     bool timing = false;
+    // FAINT and bright tables of a batch as two concurrent launch sequences (default on;
+    // GPPD_SPLIT_CHAINS=0 or gppd_set_split_chains)
+    bool split_chains = [] {
+        const char *e = getenv("GPPD_SPLIT_CHAINS");
+        return !(e && e[0] == '0');
+    }();
     Slot slots[NSLOTS];
     // Second chain of each slot: the FAINT tables of a batch run on their own
     // (high-priority) stream, so that their latency-bound passes (segmentation,
@@ -629,6 +635,12 @@ int gppd_measure_fp64_peak(gppd_handle h, double *tflops) {
     return GPPD_OK;
 }
 
+int gppd_set_split_chains(gppd_handle h, int on) {
+    if (!h) return GPPD_ERR_ARG;
+    h->split_chains = on != 0;
+    return GPPD_OK;
+}
+
 int gppd_enable_timing(gppd_handle h, int on) {
     if (!h) return GPPD_ERR_ARG;
     h->timing = on != 0;
@@ -1008,11 +1020,11 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
     // on the batching: all partial sums are over fixed row segments)
     std::vector<TableArgs> faint, bright;
     for (TableArgs &a : tabs) (a.n1 > 0 ? faint : bright).push_back(a);
-    // (opt-in, GPPD_SPLIT_CHAINS=1: measured +3 % on the 100-table night; off by default
-    // so that one launch of each pass covers the whole batch and per-pass timings stay
-    // unambiguous)
-    static const bool split = getenv("GPPD_SPLIT_CHAINS") != nullptr;
-    if (faint.empty() || bright.empty() || !split || (o.flags & GPPD_CENTER_EMPIRICAL))
+    // (the fit's latency-bound tail and the HBM-bound demodulation of one chain overlap the
+    // issue-bound harmonic pass of the other: measured +8 % on the 100-table night.  Each
+    // pass is then two launches per batch; gppd_pass_times adds their durations.
+    // GPPD_SPLIT_CHAINS=0 or gppd_set_split_chains(h, 0) keeps one launch sequence.)
+    if (faint.empty() || bright.empty() || !h->split_chains || (o.flags & GPPD_CENTER_EMPIRICAL))
         return run_batch(h, s, st, tabs, &o, nullptr, false);
     Slot &sb = h->aux[slot];
     CK(cudaEventRecord(sb.fork, st));

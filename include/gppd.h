@@ -241,6 +241,15 @@ int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres);
  */
 int gppd_debug_harmonics(gppd_handle h, int slot, double *htab, int64_t nvals);
 
+/*
+ * Batches that hold both FAINT and bright tables run as two concurrent launch sequences
+ * (the latency-bound tail of one chain's fit and its HBM-bound demodulation overlap the
+ * other chain's harmonic pass; results do not depend on it).  on = 0 keeps one launch
+ * sequence per batch, e.g. to time the passes one by one (gppd_pass_times); the default
+ * is on unless the environment has GPPD_SPLIT_CHAINS=0.
+ */
+int gppd_set_split_chains(gppd_handle h, int on);
+
 /* number of kernels this library has launched on the handle so far */
 int64_t gppd_launch_count(gppd_handle h);
 
