@@ -265,7 +265,7 @@ constexpr int FITW_WARPS = 1;   // fits per block: fits differ 4x in length (25.
                                 // calls), a block would wait for its slowest one
 
 template <bool OFFS>
-__global__ void __launch_bounds__(FITW_WARPS * 32)
+__global__ void __launch_bounds__(FITW_WARPS * 32, 22)
 k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *htab, int nfits,
                     FitOptions opt, FitResult *results, double *trace, int *fbq) {
     __shared__ FitDriverT<true> s_drv[FITW_WARPS];
