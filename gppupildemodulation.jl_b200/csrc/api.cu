@@ -567,7 +567,8 @@ int gppd_destroy(gppd_handle h) {
                           &s.offsets, &s.params, &s.chi2, &s.info, &s.trace, &s.state_out,
                           &s.state, &s.basis, &s.z, &s.y, &s.thkeys, &s.nvalid, &s.jobs,
                           &s.results, &s.spart1, &s.spart2, &s.partZ, &s.partY, &s.htab,
-                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps, &s.faintjobs, &s.fbq};
+                          &s.timers, &s.lb, &s.events, &s.flags, &s.tabs, &s.exps, &s.faintjobs, &s.fbq,
+                          &s.centres, &s.cpart};
         for (DevBuf *b : bufs) b->release();
         for (cudaEvent_t e : s.timer.ev) cudaEventDestroy(e);
     }
