@@ -6,6 +6,7 @@ header replaced (``FitsUtils.FITScopy!``, src/FitsUtils.jl:95-156;
 ``main``, src/GPPupilDemodulation.jl:356-424).  No FITS library exists in this
 image, so this module implements exactly what that needs, on plain bytes:
 
+* plain, gzipped (``.gz``) and compress'ed (``.Z``) files,
 * header parsing (standard and ``HIERARCH`` cards, CONTINUE-less strings),
 * BINTABLE layout (``NAXIS1`` = record bytes, ``TFORMn`` widths -> column offsets),
 * byte-exact pass-through of every other HDU,
@@ -125,11 +126,66 @@ def _data_bytes(h: dict) -> int:
     return n + int(h.get("PCOUNT", 0))
 
 
+def unlzw(buf: bytes) -> bytes:
+    """Decode a Unix ``compress`` (.Z) stream: LZW with 9..16-bit codes, least significant bit
+    first, code 256 = CLEAR in block mode, and the format's quirk that the encoder emits codes
+    in groups of eight, so that a change of code width (or a CLEAR) skips to the next multiple
+    of ``8 * width`` bits counted from where that width began.  CFITSIO reads such files
+    transparently; the reference lists ``fits.Z`` among its suffixes
+    (src/GPPupilDemodulation.jl:14)."""
+    if len(buf) < 3 or buf[0] != 0x1F or buf[1] != 0x9D:
+        raise ValueError("not a compress (.Z) stream")
+    maxbits, block = buf[2] & 0x1F, bool(buf[2] & 0x80)
+    if not 9 <= maxbits <= 16 or buf[2] & 0x60:
+        raise ValueError("unsupported compress (.Z) flags")
+    first_free = 257 if block else 256
+    table = [bytes([i]) for i in range(256)] + ([b""] if block else [])
+    data = buf[3:] + b"\0\0\0\0"
+    total = 8 * (len(buf) - 3)
+    out = bytearray()
+    bits, mark, pos, prev = 9, 0, 0, None
+    while True:
+        full = (1 << maxbits) if bits == maxbits else (1 << bits) - 1
+        if len(table) > full and bits < maxbits:       # the next code is one bit wider
+            group = 8 * bits
+            pos += -(pos - mark) % group
+            bits += 1
+            mark = pos
+        if pos + bits > total:
+            break
+        code = (int.from_bytes(data[pos >> 3:(pos >> 3) + 4], "little") >> (pos & 7)) & ((1 << bits) - 1)
+        pos += bits
+        if block and code == 256:                       # CLEAR: back to 9-bit codes
+            group = 8 * bits
+            pos += -(pos - mark) % group
+            del table[first_free:]
+            bits, mark, prev = 9, pos, None
+            continue
+        if prev is None:
+            if code > 255:
+                raise ValueError("corrupt compress (.Z) stream")
+            entry = table[code]
+        elif code < len(table):
+            entry = table[code]
+        elif code == len(table):
+            entry = prev + prev[:1]
+        else:
+            raise ValueError("corrupt compress (.Z) stream")
+        out += entry
+        if prev is not None and len(table) < (1 << maxbits):
+            table.append(prev + entry[:1])
+        prev = entry
+    return bytes(out)
+
+
 def read_fits(path: str) -> list:
-    """All HDUs of a (possibly gzipped) FITS file as raw bytes + parsed headers."""
+    """All HDUs of a FITS file (plain, gzipped ``.gz`` or compress'ed ``.Z``) as raw bytes +
+    parsed headers."""
     opener = gzip.open if str(path).endswith(".gz") else open
     with opener(path, "rb") as fh:
         buf = fh.read()
+    if str(path).endswith(".Z"):
+        buf = unlzw(buf)
     hdus, pos = [], 0
     while pos + BLOCK <= len(buf):
         cards, header, done = [], {}, False

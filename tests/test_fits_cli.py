@@ -115,3 +115,81 @@ def test_cli_night_end_to_end(gp, ora, tmp_path, mode):
         else:
             for k, v in hg.items():
                 assert dst[3].header[k] == v, k
+
+
+def _lzw_compress(data: bytes, maxbits: int = 16, clear_when_full: bool = False) -> bytes:
+    """compress(1)-format encoder (block mode), for the .Z tests only."""
+    body = bytearray()
+    st = dict(acc=0, nacc=0, bits=9, ingroup=0)
+
+    def emit(code):
+        st["acc"] |= code << st["nacc"]
+        st["nacc"] += st["bits"]
+        while st["nacc"] >= 8:
+            body.append(st["acc"] & 0xFF)
+            st["acc"] >>= 8
+            st["nacc"] -= 8
+        st["ingroup"] = (st["ingroup"] + 1) % 8
+
+    def pad():
+        while st["ingroup"]:
+            emit(0)
+
+    table, free = {}, 257
+    w = data[:1]
+    for i in range(1, len(data)):
+        c = data[i:i + 1]
+        if w + c in table:
+            w = w + c
+            continue
+        emit(table[w] if len(w) > 1 else w[0])
+        full = (1 << maxbits) if st["bits"] == maxbits else (1 << st["bits"]) - 1
+        if free > full and st["bits"] < maxbits:
+            pad()
+            st["bits"] += 1
+        if free < (1 << maxbits):
+            table[w + c] = free
+            free += 1
+        elif clear_when_full:
+            emit(256)
+            pad()
+            st["bits"] = 9
+            table.clear()
+            free = 257
+        w = c
+    if data:
+        emit(table[w] if len(w) > 1 else w[0])
+    while st["nacc"] > 0:
+        body.append(st["acc"] & 0xFF)
+        st["acc"] >>= 8
+        st["nacc"] -= 8
+    return bytes([0x1F, 0x9D, 0x80 | maxbits]) + bytes(body)
+
+
+def test_fits_Z_files(gp, tmp_path):
+    """`fits.Z` is one of the reference's suffixes (src/GPPupilDemodulation.jl:14; CFITSIO
+    decodes compress'ed files).  The decoder is held to streams that gzip's own `-d` accepts."""
+    import shutil
+    import subprocess
+    from gppd_b200 import fits
+    rng = np.random.default_rng(1)
+    samples = [b"", b"x", b"TOBEORNOTTOBEORTOBEORNOT" * 2000,
+               rng.integers(0, 256, 150000, dtype=np.uint8).tobytes(),      # fills the 16-bit table
+               rng.integers(0, 4, 300000, dtype=np.uint8).tobytes()]
+    for data in samples:
+        for maxbits, clear in ((16, False), (12, True), (10, False)):
+            z = _lzw_compress(data, maxbits, clear)
+            assert fits.unlzw(z) == data
+            if shutil.which("gzip"):
+                p = tmp_path / "t.Z"
+                p.write_bytes(z)
+                r = subprocess.run(["gzip", "-dc", str(p)], capture_output=True)
+                assert r.returncode == 0 and r.stdout == data       # the test encoder writes valid streams
+    with pytest.raises(ValueError):
+        fits.unlzw(b"\x1f\x8b\x08")
+    # a whole file
+    tab = gp.synthetic.make_table(300, k=5)
+    plain = gp.synthetic.make_fits(str(tmp_path / "a.fits"), tab)
+    (tmp_path / "a.fits.Z").write_bytes(_lzw_compress(open(plain, "rb").read()))
+    a, b = fits.read_fits(plain), fits.read_fits(str(tmp_path / "a.fits.Z"))
+    assert len(a) == len(b) and all(x.cards == y.cards and x.data == y.data for x, y in zip(a, b))
