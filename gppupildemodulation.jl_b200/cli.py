@@ -77,9 +77,6 @@ def _plan_file(filename, args, folder):
     """Header gating of one file (reference :358-392).  Returns a _Job or None."""
     if not os.path.isfile(filename) or not filename.endswith(SUFFIXES):
         return None
-    if filename.endswith(".Z"):
-        log.info("%s: compress(1) files are not supported here", filename)
-        return None
     hdus = fits.read_fits(filename)
     prim = hdus[0].header
     if "ESO INS PMC1 MODULATE" not in prim:

@@ -193,3 +193,22 @@ def test_fits_Z_files(gp, tmp_path):
     (tmp_path / "a.fits.Z").write_bytes(_lzw_compress(open(plain, "rb").read()))
     a, b = fits.read_fits(plain), fits.read_fits(str(tmp_path / "a.fits.Z"))
     assert len(a) == len(b) and all(x.cards == y.cards and x.data == y.data for x, y in zip(a, b))
+
+
+@pytest.mark.gpu
+def test_cli_reads_compressed_inputs(gp, ora, tmp_path):
+    """The same table as .fits, .fits.gz and .fits.Z gives the same output file."""
+    import gzip
+    from gppd_b200 import cli, fits
+    d, out = tmp_path / "in", tmp_path / "out"
+    d.mkdir()
+    tab = gp.synthetic.make_table(2500, k=6)
+    plain = gp.synthetic.make_fits(str(d / "p.fits"), tab)
+    raw = open(plain, "rb").read()
+    with gzip.open(str(d / "g.fits.gz"), "wb") as fh:
+        fh.write(raw)
+    (d / "z.fits.Z").write_bytes(_lzw_compress(raw))
+    assert cli.main(["-d", str(out), str(d / "p.fits"), str(d / "g.fits.gz"), str(d / "z.fits.Z")]) == 0
+    assert sorted(os.listdir(out)) == ["g.fits", "p.fits", "z.fits"]
+    ref = open(out / "p.fits", "rb").read()
+    assert open(out / "g.fits", "rb").read() == ref and open(out / "z.fits", "rb").read() == ref
