@@ -173,10 +173,16 @@ class NightScheduler:
                                      wrows=wrows, nwin=nwin, rb_out=rb_out, keep=(o, off, t1, t2)))
 
     def finish(self, slot):
-        """Wait for the slot's file and write its output (reference :406-412)."""
+        """Wait for the slot's file, take its records out of the slot's pinned buffer and hand
+        the assembling and writing of the output file to the writer threads (reference
+        :406-412); returns a future of the output name."""
         job, b = self.busy[slot]
         self.busy[slot] = None
         _lib.check(self.L.gppd_wait(self.h.raw, slot))
+        b = dict(b, rows_out=b["rows_out"].copy())     # the slot's staging buffer is reused
+        return self.writers.submit(self._write, job, b)
+
+    def _write(self, job, b):
         n = job.n
         fitoffsets = self.offsets is None and not self.empirical
         records = b["rows_out"].reshape(n, b["rb_out"])
@@ -210,18 +216,22 @@ class NightScheduler:
         return job.outname
 
     def run(self, jobs):
-        """Pipeline the jobs over the slots; returns the output names in input order."""
+        """Pipeline the jobs over the slots -- reader threads plan (read and gate) the next
+        files, the GPU works on up to `nslots` files, writer threads assemble and write the
+        finished ones; returns the output names in input order."""
+        from concurrent.futures import ThreadPoolExecutor
         done, slot = [], 0
-        for job in jobs:
-            if self.busy[slot] is not None:
-                done.append(self.finish(slot))
-            self.submit(slot, job)
-            slot = (slot + 1) % self.nslots
-        for k in range(self.nslots):
-            s = (slot + k) % self.nslots
-            if self.busy[s] is not None:
-                done.append(self.finish(s))
-        return done
+        with ThreadPoolExecutor(max_workers=3) as self.writers:
+            for job in jobs:
+                if self.busy[slot] is not None:
+                    done.append(self.finish(slot))
+                self.submit(slot, job)
+                slot = (slot + 1) % self.nslots
+            for k in range(self.nslots):
+                s = (slot + k) % self.nslots
+                if self.busy[s] is not None:
+                    done.append(self.finish(s))
+            return [f.result() for f in done]
 
 
 def main(argv=None) -> int:
@@ -254,10 +264,23 @@ def main(argv=None) -> int:
     sched = NightScheduler(handle, offsets, args.onlyhigh)
 
     def jobs():
-        for f in mine:
-            j = _plan_file(f, args, folder)
-            if j is not None:
-                yield j
+        # read and gate a few files ahead of the GPU (file reads release the interpreter lock)
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=2) as readers:
+            ahead = deque()
+            it = iter(mine)
+            for f in it:
+                ahead.append(readers.submit(_plan_file, f, args, folder))
+                if len(ahead) < 4:
+                    continue
+                j = ahead.popleft().result()
+                if j is not None:
+                    yield j
+            while ahead:
+                j = ahead.popleft().result()
+                if j is not None:
+                    yield j
 
     sched.run(jobs())
     return 0
