@@ -186,6 +186,7 @@ def read_fits(path: str) -> list:
         buf = fh.read()
     if str(path).endswith(".Z"):
         buf = unlzw(buf)
+    view = memoryview(buf)      # data units are views: no copy of a 30 MB table per file
     hdus, pos = [], 0
     while pos + BLOCK <= len(buf):
         cards, header, done = [], {}, False
@@ -205,7 +206,7 @@ def read_fits(path: str) -> list:
                 raise ValueError("truncated FITS header")
         nbytes = _data_bytes(header)
         padded = (nbytes + BLOCK - 1) // BLOCK * BLOCK
-        hdus.append(HDU(cards, buf[pos:pos + padded], header))
+        hdus.append(HDU(cards, view[pos:pos + padded], header))
         pos += padded
     return hdus
 
@@ -281,7 +282,7 @@ def replace_bintable(hdu: HDU, records: np.ndarray, tform_changes=None, new_colu
         _set_card(cards, k, v)
     # keep the mandatory keywords in their mandatory order: only values were edited
     # or cards appended, so the order of the original header is preserved
-    out = HDU(cards, rec.tobytes(), {})
+    out = HDU(cards, rec.reshape(-1).data, {})      # a view of the records, not another copy
     for c in cards:
         k, v = parse_card(c)
         if k is not None and k not in out.header:

@@ -21,15 +21,19 @@ for k in range(nfiles):
     os.makedirs(sub, exist_ok=True)
     gp.synthetic.make_fits(os.path.join(sub, "GRAVI_%03d.fits" % k), tab, tab["header"])
 tgen = time.time() - t0
-t0 = time.time()
-r = subprocess.run([os.path.join(ROOT, "bin", "GPPupilDemodulation"), "-r", "-d", out, d],
-                   capture_output=True, text=True)
-dt = time.time() - t0
+runs = []
+for _ in range(3):                      # the box's disk / page cache makes single runs noisy
+    shutil.rmtree(out, ignore_errors=True)
+    t0 = time.time()
+    r = subprocess.run([os.path.join(ROOT, "bin", "GPPupilDemodulation"), "-r", "-d", out, d],
+                       capture_output=True, text=True)
+    runs.append(time.time() - t0)
+dt = min(runs)
 nout = len(os.listdir(out)) if os.path.isdir(out) else 0
 res = {"workload": "night directory of %d FITS files x %d rows (30 %% FAINT), bin/GPPupilDemodulation -r" % (nfiles, rows),
        "files_written": nout, "returncode": r.returncode, "seconds": dt, "files_per_s": nout / dt,
        "diode_samples_per_s": nout * rows * 32 / dt, "input_gb": nfiles * rows * 332 / 1e9,
-       "generation_seconds": tgen, "note": "wall clock of the whole command including Python start-up, library load, file reads and writes on the box's local disk"}
+       "generation_seconds": tgen, "seconds_of_each_run": runs, "note": "wall clock of the whole command including Python start-up, library load, file reads and writes on the box's local disk"}
 print(json.dumps(res))
 if r.returncode:
     print(r.stderr[-2000:], file=sys.stderr)
