@@ -1025,7 +1025,16 @@ int gppd_process_tables_f32_dev(gppd_handle h, int slot, void *stream, int64_t n
     // issue-bound harmonic pass of the other: measured +8 % on the 100-table night.  Each
     // pass is then two launches per batch; gppd_pass_times adds their durations.
     // GPPD_SPLIT_CHAINS=0 or gppd_set_split_chains(h, 0) keeps one launch sequence.)
-    if (faint.empty() || bright.empty() || !h->split_chains || (o.flags & GPPD_CENTER_EMPIRICAL))
+    // (not for batches of very many small fits: there the one-thread-per-fit solver dominates
+    // and two concurrent launches of it are slower than one -- measured, 20 tables: 5 000-row
+    // windows (12 800 fits) 3.3 against 4.3 ms, 2 000-row windows (32 000 fits) 5.0 against 4.3)
+    long long nfits_total = 0;
+    for (const TableArgs &a : tabs) {
+        const long long w = (a.wrows <= 0 || a.wrows >= a.tv.n) ? a.tv.n : a.wrows;
+        nfits_total += (a.tv.n + w - 1) / w * NDIODE;
+    }
+    if (faint.empty() || bright.empty() || !h->split_chains || nfits_total > 16384 ||
+        (o.flags & GPPD_CENTER_EMPIRICAL))
         return run_batch(h, s, st, tabs, &o, nullptr, false);
     Slot &sb = h->aux[slot];
     CK(cudaEventRecord(sb.fork, st));
