@@ -649,13 +649,10 @@ int harm_tc_min_rows() {
 
 void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                          unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_harm_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-        cudaFuncSetAttribute(k_harm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-        cudaFuncSetAttribute(k_harm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-        attr = true;
-    }
+    // (per device: set at every launch, it costs nothing next to the launch itself)
+    cudaFuncSetAttribute(k_harm_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaFuncSetAttribute(k_harm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaFuncSetAttribute(k_harm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     dim3 grid(njobs, P);
     if (flags & 2u) {
         k_harm_tc<0, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
