@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GPPD_VERSION 100 /* 0.1.0 */
+#define GPPD_VERSION 110 /* 0.1.10: + gppd_submit_fits_rows, gppd_centres, gppd_set_split_chains, gppd_debug_harmonics, GPPD_CENTER_EMPIRICAL */
 
 /* ---- status codes ------------------------------------------------------ */
 #define GPPD_OK 0
