@@ -31,7 +31,7 @@
 //     trig((k + 4) t) = 2 cos(4 t) trig(k t) - trig((k - 4) t)      (one FMA each)
 // from the row's (cos, sin)(t .. 4t), which the producers tabulate.
 //
-// Kernel structure (k_harm_ws): one block of 8 warps per (job, group, 12 288-row
+// Kernel structure (k_harm_ws): one block of 8 warps per (job, group, 6 144-row
 // segment), two blocks per SM.  The kernel is WARP-SYNCHRONOUS: every warp owns the
 // 32-row chunks warp, warp + 8, ... of the segment and does everything for them --
 //   1. stages the raw table bytes of its next chunk with cp.async (16-byte copies: the
@@ -61,7 +61,7 @@
 
 namespace gppd {
 
-constexpr int HARM_SEG_ROWS = 12288;          // rows per segment
+constexpr int HARM_SEG_ROWS = 6144;           // rows per segment
 constexpr int MTILES = 2 * HK / 8;            // 8-row tiles of the 48 (harmonic, cos|sin) rows of C
 static_assert(2 * HK == 8 * MTILES && MTILES == 6, "lane k0 + 4j must cover k = 1..HK");
 

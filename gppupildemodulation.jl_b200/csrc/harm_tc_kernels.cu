@@ -1,7 +1,7 @@
 // harm_tc_kernels.cu -- the harmonic sums on the 5th-generation tensor cores.
 //
 // Same sums as harm_kernels.cu (reference src/Modulation.jl:137-145 rewritten with the
-// Jacobi-Anger expansion): per job and 12 288-row segment
+// Jacobi-Anger expansion): per job and 6 144-row segment
 //     C[64 x 48] = V^T[64 x rows] E[rows x 48],
 //     V[row][8 g + 2 d + {0,1}] = (x, y) of the stream value of diode d of group g,
 //     E[row][2 (k - 1) + {0,1}] = (cos, sin)(k theta_row),  k = 1..24,
@@ -53,7 +53,9 @@
 
 namespace gppd {
 
-constexpr int TC_SEG_ROWS = 12288;            // = HARM_SEG_ROWS (harm_kernels.cu)
+constexpr int TC_SEG_ROWS = 6144;             // = HARM_SEG_ROWS (harm_kernels.cu).  Shorter than the
+// night alone would want (12 288 rows: 1 % faster there): a single table then is 17 blocks
+// instead of 9, which is what the table-by-table end-to-end path needs (+6 % there)
 constexpr int TC_KB = 32;                     // rows per K-block = K of one int8 MMA
 constexpr int TC_RS = 8;                      // raw ring stages
 constexpr int TC_OS = 4;                      // operand ring stages

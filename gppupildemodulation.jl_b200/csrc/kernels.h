@@ -43,7 +43,7 @@ void launch_circle(const Launcher &L, const TableDesc *d_tabs, int ntables, long
                    double *d_part);
 
 // Jacobi-Anger harmonic sums of every fit + reduction into the harmonic table
-int harm_max_segments(long long max_rows_per_job);   // fixed 12288-row segments
+int harm_max_segments(long long max_rows_per_job);   // fixed 6144-row segments
 int stats_max_segments(long long max_rows_per_job);  // fixed 1024-row segments
 // tensor: the int8 tensor-core kernel (harm_tc_kernels.cu; dense METROLOGY tables only)
 // instead of the FP64 DMMA kernel (harm_kernels.cu; any layout)
