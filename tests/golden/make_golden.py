@@ -57,6 +57,49 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "golden_small.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
+    full = full_size_vectors(gp, oracle, make_case)
+    path = os.path.join(ROOT, "tests", "golden", "golden_1e5.npz")
+    np.savez_compressed(path, **full)
+    print(path, os.path.getsize(path), "bytes")
+
+
+FULL_ROWS = 100_000
+FULL_STRIDE = 1009          # rows of the output kept in the file
+
+
+def full_size_inputs(gp, oracle, make_case, name):
+    """BASELINE.json configs 1 / 2: one bright and one FAINT table of 1e5 rows (seeded
+    generator: the inputs are not stored, only their SHA-256)."""
+    faint = name == "faint"
+    tab = make_case(gp.synthetic, FULL_ROWS, k=43 if faint else 41, faint=faint, jitter=True, ora=oracle)
+    t, z = gp.synthetic.to_complex(tab, gp.synthetic.stefan_centres())
+    return tab, t, z
+
+
+def input_digest(tab):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(tab["time_us"]).tobytes())
+    h.update(np.ascontiguousarray(tab["volt"]).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+def full_size_vectors(gp, oracle, make_case):
+    out = {}
+    for name in ("bright", "faint"):
+        tab, t, z = full_size_inputs(gp, oracle, make_case, name)
+        o, p, l, nf = oracle.demodulateall(t, z, faintparam=tab["state"], nthreads=8, return_nfev=True)
+        out[f"{name}_sha256"] = input_digest(tab)
+        out[f"{name}_params"] = p
+        out[f"{name}_chi2"] = l
+        out[f"{name}_nfev"] = nf
+        out[f"{name}_output"] = o[::FULL_STRIDE, :32].astype(np.complex64)
+        if name == "faint":     # run-length form of the segmentation
+            st = tab["state"]
+            chg = np.flatnonzero(np.diff(st)) + 1
+            out["faint_state_starts"] = np.concatenate([[0], chg]).astype(np.int32)
+            out["faint_state_values"] = st[out["faint_state_starts"]].astype(np.int8)
+    return out
 
 
 if __name__ == "__main__":

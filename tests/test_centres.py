@@ -99,7 +99,10 @@ def test_empirical_processmetrology_vs_oracle(gp, ora):
     assert np.abs(tg["VOLT"][:, 64:].astype(np.float64) - to["VOLT"][:, 64:]).max() <= 1e-6
     keys = [k for k in ho if "SIN AMPLITUDE" in k]
     close = sum(abs(hg[k] - ho[k]) <= 1e-6 * abs(ho[k]) for k in keys)
-    assert close >= 16 and all(abs(hg[k] - ho[k]) <= 2e-2 for k in keys)
+    # (the centres themselves agree to 1e-10 of the radius only, hence 1e-6 rather than 1e-9;
+    # forked fits inside the measured envelope of the reference procedure, tests/fitref.py)
+    import fitref
+    assert close >= fitref.MIN_COINCIDE and all(abs(hg[k] - ho[k]) <= fitref.FORK_HARD for k in keys)
 
 
 @pytest.mark.gpu

@@ -14,41 +14,32 @@ stack: no Julia here, no reference tests; see oracle/gppd_oracle.h):
  (3) end to end        -- where the oracle's own trajectory coincides with the
      GPU's, parameters and demodulated output agree to 1e-9 (the north-star
      tolerance).  NEWUOA has rounding-level ties (e.g. SUM > DISTSQ right after
-     DELTA = HALF*DNORM), so a 1e-13 difference in chi2 can fork a trajectory;
-     both forks stop at rho_end = 1e-3 and then differ by ~1e-5.  For those fits
-     the test asserts agreement within the solver's own stopping tolerance.
+     DELTA = HALF*DNORM), so a 1e-15 difference in chi2 forks ~9 % of the fits
+     (measured on the oracle against itself, tests/test_fork_envelope.py).  Every
+     case must keep >= 22 of its 32 fits on the oracle's trajectory, every forked
+     fit inside the measured envelope (tests/fitref.py), and the forks of the whole
+     module are checked as a population (test_fork_population); the BASELINE-size
+     configurations (1e5 rows, bright and FAINT, `-c stefan` and `-c fit`) are run
+     against the oracle too (test_full_size_vs_oracle).
 Integer/index work (segmentation, window partition, channel map) is bit-exact.
 """
 import numpy as np
 import pytest
 
+import fitref
 from conftest import make_case
+from fitref import FORK_HARD, MIN_COINCIDE, REL_FIT, REL_OBJ
 
 pytestmark = pytest.mark.gpu
 
-REL_OBJ = 1e-10     # objective parity (1)
-REL_FIT = 1e-9      # north-star FP64 tolerance (3)
-SOLVER_TOL = 2e-3   # |delta b|, |delta phi| bound for forked trajectories (rho_end = 1e-3)
-
-
-def _valid(state, onlyhigh, ora):
-    if state is None:
-        return slice(None)
-    v = (state != ora.TRANSIENT)
-    if onlyhigh:
-        v &= (state == ora.HIGH) | (state == ora.NORMAL)
-    return v
+# fork statistics of every end-to-end comparison of this module, checked as a population
+# by test_fork_population at the end of the file (tolerances: tests/fitref.py, measured by
+# tests/test_fork_envelope.py)
+FORK_STATS = []
 
 
 def _oracle_objective(ora, t, z, state, ch, onlyhigh, fitoffsets):
-    g = ch // 4
-    v = _valid(state, onlyhigh, ora)
-    fc = np.exp(1j * np.angle(z[:, 32 + g]))[v]
-    d = z[:, ch][v]
-    w = pw = None
-    if state is not None:
-        pw, w = ora.compute_mean_var_power(state[v], d)
-    return lambda b, phi: ora.chi2(t[v], d, fc, b, phi, weight=w, power=pw, fitoffsets=fitoffsets)
+    return fitref.oracle_objective(ora, t, z, state, ch, onlyhigh, fitoffsets)
 
 
 def _replay(ora, trace, nfev, maxfun=60, xinit=None):
@@ -172,15 +163,14 @@ def test_demodulation_formula(fitcase, ora):
 def test_end_to_end_vs_oracle(fitcase, ora):
     c = fitcase
     par, op = c["par"], c["op"]
-    same = c["info"][:, 0] == c["onf"]
-    coincide = np.zeros(32, bool)
-    for ch in range(32):
-        if not same[ch]:
-            continue
-        # same trajectory <=> parameters agree far below the solver tolerance
-        coincide[ch] = (abs(par[ch, 4] - op[ch, 4]) <= REL_FIT * abs(op[ch, 4]) and
-                        abs(par[ch, 5] - op[ch, 5]) <= REL_FIT * max(1.0, abs(op[ch, 5])))
-    assert coincide.sum() >= 16, "most fits must follow the oracle's trajectory exactly"
+    # same trajectory <=> same number of objective calls and parameters equal to 1e-9;
+    # compare_fits also holds every forked fit to the measured envelope (|delta b|,
+    # |delta phi| <= FORK_HARD, relative chi2 difference <= FORK_CHI2_HARD)
+    coincide, stats = fitref.compare_fits(par, c["like"], op, c["ol"], c["info"][:, 0], c["onf"])
+    FORK_STATS.append(stats)
+    print("forks %d / 32, max |db| %.1e |dphi| %.1e dchi2 %.1e"
+          % (stats["forks"], stats["max_db"], stats["max_dphi"], stats["max_dchi2"]))
+    assert coincide.sum() >= MIN_COINCIDE, "most fits must follow the oracle's trajectory exactly"
     a, ao = par[:, 2] + 1j * par[:, 3], op[:, 2] + 1j * op[:, 3]
     sel = coincide
     assert (np.abs(a - ao)[sel] <= REL_FIT * np.abs(ao)[sel]).all()
@@ -188,16 +178,11 @@ def test_end_to_end_vs_oracle(fitcase, ora):
     scale = np.abs(c["z"][:, :32]).max(axis=0)
     err = np.abs(c["out"][:, :32] - c["oo"][:, :32]).max(axis=0) / scale
     assert (err[sel] <= REL_FIT).all()
-    # forked trajectories (rounding-level ties inside NEWUOA): both stop at
-    # rho_end = 1e-3, so they agree within the solver's stopping tolerance and
-    # reach the same chi2 to first order
+    # forked fits: the outputs differ by the phase the parameter difference makes,
+    # |delta psi| <= |delta b| + b |delta phi|
     fork = ~sel
     if fork.any():
-        assert np.abs(par[fork, 4] - op[fork, 4]).max() <= SOLVER_TOL
-        dphi = np.angle(np.exp(1j * (par[fork, 5] - op[fork, 5])))
-        assert np.abs(dphi).max() <= SOLVER_TOL
-        assert (np.abs(c["like"] - c["ol"])[fork] <= 1e-3 * c["ol"][fork]).all()
-        assert err[fork].max() <= 2 * SOLVER_TOL
+        assert err[fork].max() <= 4 * FORK_HARD
 
 
 @pytest.mark.parametrize("method", METHODS)
@@ -349,19 +334,22 @@ def test_table_whole_file(gp, ora, mode, method):
     for k in keys:
         side, tel, dio = k.split()[-3:]
         ch = gp.idx(gp.Side[side], int(tel[1]), gp.Diode[dio]) - 1
-        same = abs(hg[k] - ho[k]) <= REL_FIT * abs(ho[k])
+        kphi = k.replace("SIN AMPLITUDE", "SIN PHASE")
+        same = (abs(hg[k] - ho[k]) <= REL_FIT * abs(ho[k]) and
+                abs(fitref.dphi(hg[kphi], ho[kphi])) <= REL_FIT * max(1.0, abs(ho[kphi])))
         cols = slice(base + 2 * ch, base + 2 * ch + 2)
         scale = np.abs(vo[:, cols]).max()
         err = np.abs(vg[:, cols].astype(np.float64) - vo[:, cols]).max() / scale
         if same:
             ncoin += 1
             assert err <= 2.0 ** -22, (k, err)
-            for kk in ("AMPLITUDE ABS", "AMPLITUDE ARG", "SIN PHASE"):
+            for kk in ("AMPLITUDE ABS", "AMPLITUDE ARG"):
                 name = k.replace("SIN AMPLITUDE", kk)
                 assert abs(hg[name] - ho[name]) <= REL_FIT * max(1.0, abs(ho[name]))
         else:
-            assert abs(hg[k] - ho[k]) <= SOLVER_TOL and err <= 2 * SOLVER_TOL
-    assert ncoin >= 16
+            assert abs(hg[k] - ho[k]) <= FORK_HARD and abs(fitref.dphi(hg[kphi], ho[kphi])) <= FORK_HARD
+            assert err <= 4 * FORK_HARD
+    assert ncoin >= MIN_COINCIDE
     if faint:
         assert "STATE" not in tg   # whole-file mode writes no STATE column (:248 is window mode)
 
@@ -378,11 +366,18 @@ def test_table_windowed_faint(gp, ora, method):
     assert (wrows, nwin) == (1000, 5)
     chg = np.nonzero(np.any(np.diff(tg["B"], axis=0) != 0, axis=1))[0] + 1
     assert set(chg) <= {1000, 2000, 3000, 4000}
-    close = np.abs(tg["B"][::1000] - to["B"][::1000]) <= 1e-6 * np.abs(to["B"][::1000])
-    assert close.mean() >= 0.5
-    # forked trajectories on 2 s windows (two modulation periods, fitted centres: a
-    # flat chi2 valley) can stop far apart; most windows follow the oracle exactly
-    assert np.abs(tg["B"] - to["B"]).max() <= 0.5
+    # the four full windows (1000 rows = two modulation periods): float32 columns, so
+    # "coincide" is float32 equality of B and PHI; forks within the measured envelope
+    full = slice(0, 4000, 1000)
+    db = np.abs(tg["B"][full].astype(np.float64) - to["B"][full])
+    dp = np.abs(fitref.dphi(tg["PHI"][full].astype(np.float64), to["PHI"][full]))
+    close = (db <= 2.0 ** -22 * np.abs(to["B"][full])) & (dp <= 2.0 ** -22 * np.maximum(1.0, np.abs(to["PHI"][full])))
+    assert close.mean() >= fitref.MIN_COINCIDE_FRACTION, close.mean()
+    assert db.max() <= FORK_HARD and dp.max() <= FORK_HARD
+    # the ragged last window has 100 rows = a fifth of a modulation period: (b, phi) are
+    # not determined by the data there (the oracle against itself perturbed by 1e-15 moves
+    # b by up to 0.17 and chi2 by 1 %), so only a loose bound applies
+    assert np.abs(tg["B"][4000:] - to["B"][4000:]).max() <= 0.5
     assert np.array_equal(tg["VOLT"][:, 64:], to["VOLT"][:, 64:])
 
 
@@ -456,7 +451,7 @@ def test_full_size_properties(gp, ora, method, monkeypatch):
     vout3, p3, c3, i3, _ = gp.process_table(tab["time_us"], tab["volt"], tab["mjd"], offsets=off,
                                             method=method)
     same = np.abs(p3[:, 4] - par[:, 4]) <= REL_FIT * np.abs(par[:, 4])
-    assert same.sum() >= 24 and np.abs(p3[:, 4:6] - par[:, 4:6]).max() <= SOLVER_TOL
+    assert same.sum() >= MIN_COINCIDE and np.abs(p3[:, 4:6] - par[:, 4:6]).max() <= FORK_HARD
     assert np.abs(c3 - like).max() <= 1e-6 * np.abs(like).max()
     cols = np.repeat(same, 2)
     assert np.abs(vout3[:, :64][:, cols] - ref32[:, :64][:, cols]).max() <= 2.0 ** -22 * np.abs(ref32[:, :64]).max()
@@ -489,7 +484,7 @@ def test_ragged_sizes_table(gp, ora, n, window, keepraw):
         assert set(hg) == set(ho)
         if n >= 2000:
             nb = sum(abs(hg[k] - ho[k]) <= REL_FIT * abs(ho[k]) for k in ho if "SIN AMPLITUDE" in k)
-            assert nb >= 16
+            assert nb >= MIN_COINCIDE
     else:
         assert tg["B"].shape == to["B"].shape == (n, 32)
         wrows, nwin = gp.table_windows(tab["time_us"], tab["mjd"], window)
@@ -526,3 +521,85 @@ def test_many_small_windows(gp, ora):
         o1, p1, l1 = gp.demodulateall(t[lo:lo + w], z[lo:lo + w], raw=True)
         assert p1.tobytes() == par[win * 32:(win + 1) * 32].tobytes()
         assert np.array_equal(o1, out[lo:lo + w])
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configs 1 and 2 at their full size against the oracle
+FULL = {"bright_stefan": (False, False, 41), "bright_fit": (False, True, 42),
+        "faint_stefan": (True, False, 43), "faint_fit": (True, True, 44)}
+
+
+@pytest.mark.parametrize("mode", list(FULL))
+def test_full_size_vs_oracle(gp, ora, mode):
+    """1e5-row tables (BASELINE configs 1 / 2; `-c stefan` = subtract the centres, `-c fit`
+    = fit them): the oracle's demodulateall (reference src/Modulation.jl:344-435) against
+    BOTH boundaries of the library -- gppd_demodulate_f64 (harmonic sums on the FP64 units)
+    and the METROLOGY-table path (int8 tensor cores, int32 accumulation over 17 segments,
+    sampled fixed-point scale, float32 re-interleave)."""
+    faint, fit, k = FULL[mode]
+    n = 100_000
+    tab = make_case(gp.synthetic, n, k=k, faint=faint, jitter=True, ora=ora)
+    off = None if fit else gp.synthetic.stefan_centres()
+    t, z = gp.synthetic.to_complex(tab, off)
+    state = tab["state"]                     # CLI path: buildstates with zero delays (:144)
+    oo, op, ol, onf = ora.demodulateall(t, z, faintparam=state, fitoffsets=fit, nthreads=8,
+                                        return_nfev=True)
+    scale = np.abs(z[:, :32]).max(axis=0)
+
+    # ---- the demodulateall boundary
+    out, par, like, info, trace = gp.demodulateall(t, z, faintparam=state, fitoffsets=fit, raw=True,
+                                                   return_info=True, return_trace=True)
+    assert np.all(info[:, 2] == 2)           # harmonic evaluator, no fallback
+    for ch in (3, 20):                       # objective parity along the GPU's own trace
+        obj = _oracle_objective(ora, t, z, state, ch, False, fit)
+        for kk in range(info[ch, 0]):
+            b, phi, f = trace[ch, kk]
+            fo = obj(b, phi)[0]
+            assert abs(f - fo) <= REL_OBJ * fo, (ch, kk, f, fo)
+    coincide, stats = fitref.compare_fits(par, like, op, ol, info[:, 0], onf)
+    FORK_STATS.append(stats)
+    print("%s array path: forks %d / 32, max |db| %.1e |dphi| %.1e dchi2 %.1e"
+          % (mode, stats["forks"], stats["max_db"], stats["max_dphi"], stats["max_dchi2"]))
+    assert coincide.sum() >= MIN_COINCIDE
+    a, ao = par[:, 2] + 1j * par[:, 3], op[:, 2] + 1j * op[:, 3]
+    assert (np.abs(a - ao)[coincide] <= REL_FIT * np.abs(ao)[coincide]).all()
+    if fit:
+        cc, co = par[:, 0] + 1j * par[:, 1], op[:, 0] + 1j * op[:, 1]
+        assert (np.abs(cc - co)[coincide] <= REL_FIT * np.maximum(np.abs(co), np.abs(ao))[coincide]).all()
+    assert (np.abs(like - ol)[coincide] <= REL_FIT * ol[coincide]).all()
+    err = np.abs(out[:, :32] - oo[:, :32]).max(axis=0) / scale
+    assert (err[coincide] <= REL_FIT).all() and err.max() <= 4 * FORK_HARD
+    assert np.array_equal(out[:, 32:], z[:, 32:])
+
+    # ---- the METROLOGY-table boundary
+    fs = tab["faintstates"]
+    fs_g = gp.FaintStates(fs.timer1, fs.timer2, 1.0, 2.0) if faint else None
+    vout, p2, c2, i2, st2 = gp.process_table(tab["time_us"], tab["volt"], tab["mjd"], offsets=off,
+                                             faintparam=fs_g)
+    if faint:
+        assert np.array_equal(st2, state)    # segmentation: bit-exact
+    assert np.all(i2[:, 2] == 2)
+    coincide2, stats2 = fitref.compare_fits(p2, c2, op, ol, i2[:, 0], onf)
+    FORK_STATS.append(stats2)
+    print("%s table path: forks %d / 32, max |db| %.1e |dphi| %.1e dchi2 %.1e"
+          % (mode, stats2["forks"], stats2["max_db"], stats2["max_dphi"], stats2["max_dchi2"]))
+    assert coincide2.sum() >= MIN_COINCIDE
+    a2 = p2[:, 2] + 1j * p2[:, 3]
+    assert (np.abs(a2 - ao)[coincide2] <= REL_FIT * np.abs(ao)[coincide2]).all()
+    assert (np.abs(c2 - ol)[coincide2] <= REL_FIT * ol[coincide2]).all()
+    ref32 = np.empty((n, 80), np.float32)    # :170-171, :253
+    ref32[:, 0::2], ref32[:, 1::2] = oo.real, oo.imag
+    assert np.array_equal(vout[:, 64:], ref32[:, 64:])         # centred FC channels
+    d = np.abs(vout[:, :64].astype(np.float64) - ref32[:, :64]).reshape(n, 32, 2).max(axis=(0, 2)) / scale
+    assert (d[coincide2] <= 2.0 ** -22).all(), d[coincide2].max()
+    assert d.max() <= 4 * FORK_HARD
+
+
+def test_fork_population():
+    """All end-to-end comparisons of this module together: the fraction of fits on the
+    oracle's trajectory and the size of the forks are those of the reference procedure's
+    own ambiguity (tests/test_fork_envelope.py), not of a defect."""
+    if not FORK_STATS:
+        pytest.skip("runs after the end-to-end comparisons of this module")
+    forks, nfits = fitref.check_fork_population(FORK_STATS, "test_gpu_parity")
+    print("module total: %d forks of %d fits (%.1f %%)" % (forks, nfits, 100.0 * forks / nfits))
