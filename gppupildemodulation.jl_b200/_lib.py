@@ -20,7 +20,8 @@ TRACE_MAX = 160
 class Options(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("method", C.c_int32), ("maxfun", C.c_int32),
                 ("has_xinit", C.c_int32), ("xinit", C.c_double * 2),
-                ("rhobeg", C.c_double), ("rhoend", C.c_double)]
+                ("rhobeg", C.c_double), ("rhoend", C.c_double),
+                ("group_mask", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class GppdError(RuntimeError):
@@ -69,6 +70,9 @@ def lib():
     L.gppd_num_windows.argtypes = [C.c_int64, C.c_int64]
     L.gppd_demodulate_f64.argtypes = [H, C.c_int64, C.c_int64, _dp, _dp, _i8p,
                                       C.POINTER(Options), _dp, _dp, _dp, _i32p, _dp]
+    L.gppd_demodulate_f64_dev.argtypes = [H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.POINTER(Options), C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
     L.gppd_table_windows.argtypes = [C.c_int64, _i32p, C.c_double, C.c_double, _i64p, _i64p]
     tab = [C.c_int64, _i32p, C.c_double, _fp, _dp, _dp, C.c_int64, _dp, C.c_int64,
            C.c_double, C.POINTER(Options), _fp, _dp, _dp, _i32p, _i8p]
@@ -98,6 +102,7 @@ def lib():
     L.gppd_measure_fp64_peak.argtypes = [H, _dp]
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
+                 "gppd_demodulate_f64_dev",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
                  "gppd_submit_fits_rows", "gppd_centres", "gppd_debug_harmonics", "gppd_set_split_chains",
                  "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",

@@ -138,6 +138,9 @@ void fill_options(const gppd_options *o, FitOptions &f, int &method) {
     f.rhoend = d.rhoend > 0 ? d.rhoend : 1e-3;
     gppd_phirange(f.phi8);
     method = d.method;
+    // the group mask travels in bits 16..23 of the kernels' flag word (GROUP_MASK_SHIFT)
+    const unsigned mask = (d.group_mask & 0xffu) ? (d.group_mask & 0xffu) : 0xffu;
+    f.flags = (f.flags & 0xffffu) | (mask << GROUP_MASK_SHIFT);
 }
 
 // cudaEvent pair around one pass (only when gppd_enable_timing is on)
@@ -249,6 +252,15 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         return GPPD_ERR_ARG;
     }
     const bool direct = method == GPPD_METHOD_DIRECT;
+    const bool all_groups = ((fo.flags >> GROUP_MASK_SHIFT) & 0xffu) == 0xffu;
+    if (!all_groups && !segment_only) {
+        for (int t = 0; t < T; ++t) {
+            if (td[t].tv.kind != 1 || td[t].ov.kind != 1) {
+                g_last_error = "gppd_options.group_mask: a partial mask applies to the demodulate_f64 entry points only";
+                return GPPD_ERR_UNSUPPORTED;
+            }
+        }
+    }
     // the int8 tensor-core form of the harmonic sums takes dense METROLOGY tables (rows of
     // 80 floats, 16-byte aligned); the other layouts use the FP64 DMMA kernel.
     // GPPD_HARMONICS=dmma forces the DMMA kernel everywhere.
@@ -431,7 +443,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     DBG(stream, "demod");
     {
         PassScope ps(h, s, stream, GPPD_PASS_EXPORT);
-        launch_export(L, s.exps.as<ExportDesc>(), T, max_jobs * NDIODE, s.results.as<FitResult>());
+        launch_export(L, s.exps.as<ExportDesc>(), T, max_jobs * NDIODE, s.results.as<FitResult>(), fo.flags);
     }
     DBG(stream, "export");
     CK(cudaGetLastError());
@@ -786,6 +798,36 @@ int gppd_demodulate_f64(gppd_handle h, int64_t n, int64_t nwindow, const double 
                            cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return GPPD_OK;
+}
+
+int gppd_demodulate_f64_dev(gppd_handle h, int slot, void *stream, int64_t n, int64_t nwindow,
+                            const double *d_t, const double *d_data, const int8_t *d_state,
+                            const gppd_options *opt, double *d_out, double *d_params,
+                            double *d_chi2, int32_t *d_info) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS || !d_t || !d_data || !d_out || !d_params || !d_chi2 || n < 2) {
+        g_last_error = "demodulate_f64_dev: bad slot, null buffer or n < 2";
+        return GPPD_ERR_ARG;
+    }
+    Slot &s = h->slots[slot];
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    std::vector<TableArgs> tabs(1);
+    TableArgs &a = tabs[0];
+    memset(&a.tv, 0, sizeof a.tv);
+    memset(&a.ov, 0, sizeof a.ov);
+    a.tv.kind = 1;
+    a.tv.n = n;
+    a.tv.t = d_t;
+    a.tv.data = reinterpret_cast<const double2 *>(d_data);
+    a.ov.kind = 1;
+    a.ov.out = reinterpret_cast<double2 *>(d_out);
+    a.wrows = nwindow;
+    a.d_state_in = d_state;
+    a.d_params = d_params;
+    a.d_chi2 = d_chi2;
+    a.d_info = d_info;
+    return run_batch(h, s, st, tabs, opt, nullptr, false);
 }
 
 // ---------------------------------------------------------------------------

@@ -276,6 +276,7 @@ k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *ht
     const int fit = blockIdx.x * FITW_WARPS + warp;
     if (fit >= nfits) return;
     const int job = fit / NDIODE, ch = fit % NDIODE;
+    if (!group_on(opt.flags, ch >> 2)) return;   // gppd_options.group_mask: not this call's fit
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
     const double *H = htab + fit;
@@ -312,7 +313,15 @@ k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *ht
             tr[3 * drv.nfev + 1] = phi;
             tr[3 * drv.nfev + 2] = f;
         }
-        if (!drv.step(opt, f)) break;
+        // The 32 lanes advance ONE solver object in shared memory, every lane computing and
+        // storing the same values.  That is only sound while the warp is converged (a lane
+        // that ran ahead would read state another lane has already advanced), so the warp is
+        // re-converged around every step; inside the solver the lane-dependent code (the
+        // angle searches) ends with a __syncwarp of its own.
+        __syncwarp();
+        const bool more = drv.step(opt, f);
+        __syncwarp();
+        if (!more) break;
     }
     if (lane != 0) return;
     if (failed) {
@@ -337,7 +346,7 @@ k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, i
     fill_angle_table(s_ang);
     __syncthreads();
     const int fit = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = fit < nfits;
+    const bool live = fit < nfits && group_on(opt.flags, (fit % NDIODE) >> 2);
     const int fidx = live ? fit : 0;
     const int job = fidx / NDIODE, ch = fidx % NDIODE;
     const JobInfo ji = jobs[job];
@@ -440,6 +449,7 @@ k_fit_direct(const TableDesc *tabs, const JobInfo *jobs, int SP, const double *s
     const int fit = SCRATCH ? q : fbq[1 + q];
     __syncthreads();   // shared scratch of the previous fit is no longer in use
     const int job = fit / NDIODE, ch = fit % NDIODE;
+    if (!group_on(opt.flags, ch >> 2)) continue;   // gppd_options.group_mask (block-uniform)
     const int group = ch >> 2, fcch = fc_channel(group);
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];

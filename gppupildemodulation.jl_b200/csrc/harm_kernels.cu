@@ -146,6 +146,7 @@ k_harm_ws(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     constexpr int HP = KIND == 0 ? HP_Z : HP_Y;
     const int jg = blockIdx.x, p = blockIdx.y;
     const int job = jg >> 3, group = jg & 7;
+    if (!group_on(flags, group)) return;       // gppd_options.group_mask
     const JobInfo ji = jobs[job];
     const TableDesc tb = tabs[ji.table];
     const TableView &tv = tb.tv;

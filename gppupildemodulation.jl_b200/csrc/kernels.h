@@ -74,7 +74,7 @@ void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
 
 // FitResult -> params / chi2 / info in the caller's layout
 void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int max_fits,
-                   const FitResult *d_results);
+                   const FitResult *d_results, unsigned flags);
 
 // raw FITS binary-table records <-> dense little-endian TIME / VOLT arrays
 void launch_unpack_rows(const Launcher &L, const void *d_rows, long long n, long long row_bytes,

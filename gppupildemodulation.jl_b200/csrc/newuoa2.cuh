@@ -198,6 +198,9 @@ struct Newuoa2T {
             const double b_lo = __shfl_sync(full, v1, (sb - 1) & 31), b_hi = __shfl_sync(full, v2, (sb - 1) & 31);
             tempa = ja == 0 ? v0 : (sa <= 32 ? a_lo : a_hi);
             tempb = jb == iu + 1 ? v0 : (sb <= 32 ? b_lo : b_hi);
+            // the only lane-dependent branches of the solver are above: re-converge before
+            // the lanes go back to updating the (shared) solver state with identical values
+            __syncwarp(full);
             return;
         }
 #elif defined(NU_HOST_EMULATE_WARP)

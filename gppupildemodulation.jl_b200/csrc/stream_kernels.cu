@@ -626,6 +626,7 @@ __global__ void __launch_bounds__(DM_THREADS, 3) k_demod(const TableDesc *tabs, 
     const int rl = threadIdx.x >> 3, group = threadIdx.x & 7;
 
     if (tbg.ov.kind == 1) {  // complex128, channel-major: already unit stride along rows
+        if (!group_on(flags, group)) return;   // gppd_options.group_mask: columns left untouched
         const TableView &tv = tbg.tv;
         const OutView &ov = tbg.ov;
         const long long row_end = (tile_first + DM_TPB) * DM_ROWS < n ? (tile_first + DM_TPB) * DM_ROWS : n;
@@ -851,10 +852,11 @@ void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
 // results -> caller layout: params (c.re,c.im,a.re,a.im,b,phi) with the sign
 // normalisation of reference src/Modulation.jl:426-431, chi2, info
 // ===========================================================================
-__global__ void k_export(const ExportDesc *exps, const FitResult *results) {
+__global__ void k_export(const ExportDesc *exps, const FitResult *results, unsigned flags) {
     const ExportDesc &e = exps[blockIdx.y];
     int fl = blockIdx.x * blockDim.x + threadIdx.x;
     if (fl >= e.nfits) return;
+    if (!group_on(flags, ((e.fit0 + fl) % NDIODE) >> 2)) return;   // not fitted by this call
     FitResult r = results[e.fit0 + fl];
     double b = r.b, phi = r.phi;
     if (b < 0) {
@@ -871,8 +873,8 @@ __global__ void k_export(const ExportDesc *exps, const FitResult *results) {
 }
 
 void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int max_fits,
-                   const FitResult *d_results) {
-    k_export<<<dim3((max_fits + 127) / 128, ntables), 128, 0, L.stream>>>(d_exps, d_results);
+                   const FitResult *d_results, unsigned flags) {
+    k_export<<<dim3((max_fits + 127) / 128, ntables), 128, 0, L.stream>>>(d_exps, d_results, flags);
     *L.counter += 1;
 }
 

@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define GPPD_VERSION 110 /* 0.1.10: + gppd_submit_fits_rows, gppd_centres, gppd_set_split_chains, gppd_debug_harmonics, GPPD_CENTER_EMPIRICAL */
+#define GPPD_VERSION 120 /* 0.1.20: + gppd_options.group_mask, gppd_demodulate_f64_dev (0.1.10: gppd_submit_fits_rows,
+                            gppd_centres, gppd_set_split_chains, gppd_debug_harmonics, GPPD_CENTER_EMPIRICAL) */
 
 /* ---- status codes ------------------------------------------------------ */
 #define GPPD_OK 0
@@ -70,6 +71,16 @@ typedef struct gppd_options {
     double xinit[2];    /* demodulateall(init=[b, phi])       src/Modulation.jl:345,362 */
     double rhobeg;      /* 0 => 1.0   (src/Modulation.jl:335) */
     double rhoend;      /* 0 => 1e-3  (src/Modulation.jl:335) */
+    uint32_t group_mask; /* which of the 8 (telescope, side) groups of src/Modulation.jl:387 to
+                            process: bit g = group g = diode channels 4g..4g+3 + FC channel 32+g
+                            (g = 0..3: FT T1..T4, 4..7: SC T1..T4); 0 => all 8.  The groups are
+                            independent (:387-390), so one demodulateall call can be split over
+                            GPUs by groups with no exchange: a call with a partial mask reads
+                            and writes only the columns of its groups (the others' output
+                            columns, params, chi2 and info entries are left untouched).
+                            gppd_demodulate_f64 / gppd_demodulate_f64_dev only; the table
+                            entry points return GPPD_ERR_UNSUPPORTED for a partial mask. */
+    uint32_t reserved;  /* 0 */
 } gppd_options;
 
 /* per-fit diagnostics (optional output, 4 int32 per diode) */
@@ -131,6 +142,20 @@ int gppd_demodulate_f64(gppd_handle h, int64_t n, int64_t nwindow, const double 
                         const double *data, const int8_t *state,
                         const gppd_options *opt, double *out, double *params,
                         double *chi2, int32_t *info, double *trace);
+
+/*
+ * Device-resident variant: t, data, state, out, params, chi2, info are DEVICE pointers on
+ * the handle's GPU (same layouts as above; info may be NULL), `stream` a cudaStream_t
+ * passed as void* (NULL = the slot's own stream).  No host<->device copies and no
+ * synchronisation: the caller orders and synchronises the stream.  This is the entry
+ * point for exposures too long to stage through host memory (1e8 rows = 64 GB of
+ * complex128 per direction) and for sharding one call over GPUs with
+ * gppd_options.group_mask.  Scratch comes from pipeline slot `slot`.
+ */
+int gppd_demodulate_f64_dev(gppd_handle h, int slot, void *stream, int64_t n, int64_t nwindow,
+                            const double *d_t, const double *d_data, const int8_t *d_state,
+                            const gppd_options *opt, double *d_out, double *d_params,
+                            double *d_chi2, int32_t *d_info);
 
 /* ---- processmetrology on arrays, src/GPPupilDemodulation.jl:128-255 ----- */
 /*

@@ -1,18 +1,27 @@
 # GPPDB200.jl -- the reference-side binding of libgppd.so.
 #
-# Drop this file next to the reference's src/Modulation.jl and
-# `include("GPPDB200.jl")` from src/GPPupilDemodulation.jl (after Modulation.jl):
-# it replaces the bodies of `demodulateall` (src/Modulation.jl:344-435) and
-# `buildstates` (src/Faint.jl:21-73) by `ccall`s into the B200 library while
-# keeping their signatures, keyword arguments and return types, so that
-# `processmetrology` (src/GPPupilDemodulation.jl:161,205), `main` and
-# bin/GPPupilDemodulation work unchanged.  Error convention = the reference's
-# own FFI idiom (src/FitsUtils.jl:42-58): Cint status, error raised on the
-# Julia side.
+# `demodulateall` (reference src/Modulation.jl:344-435) and `buildstates`
+# (src/Faint.jl:21-73) as `ccall`s into the B200 library, with the reference's
+# signatures, keyword arguments and return types.  How to wire it in (INTEGRATION.md):
 #
-# NOTE: no Julia toolchain exists in the build image or on the GPU boxes, so
-# this file has never been executed; the same C ABI is exercised by the ctypes
-# host mirror (gppupildemodulation.jl_b200/api.py) in tests/.
+#   1. copy this file next to src/Modulation.jl and `include("GPPDB200.jl")` from
+#      src/GPPupilDemodulation.jl AFTER `include("Modulation.jl")` / `include("Faint.jl")`
+#      (the submodule imports the parent's types);
+#   2. the submodule's functions are `GPPDB200.demodulateall` / `GPPDB200.buildstates`:
+#      they do NOT replace `GPPupilDemodulation.demodulateall` by themselves (a name that
+#      is already bound to a function in the parent module cannot be re-declared `const`).
+#      Either change the three call sites -- `demodulateall` at
+#      src/GPPupilDemodulation.jl:161 and :205, `buildstates` at :144 -- to the qualified
+#      names, or delete the Julia bodies (src/Modulation.jl:344-435, src/Faint.jl:21-73)
+#      and add `using .GPPDB200: demodulateall, buildstates` after the include.
+#
+# Error convention = the reference's own FFI idiom (src/FitsUtils.jl:42-58): Cint
+# status, error raised on the Julia side.
+#
+# UNTESTED: no Julia toolchain exists in the build image or on the GPU boxes, so this
+# file has never been executed.  The same C ABI (same symbols, argument order and
+# buffer layouts) is exercised by the ctypes host mirror
+# (gppupildemodulation.jl_b200/api.py) in tests/.
 module GPPDB200
 
 import ..GPPupilDemodulation: MetState, FaintStates, Modulation, ModulationWithOffsets,
@@ -35,7 +44,11 @@ struct Options
     xinit::NTuple{2,Float64}
     rhobeg::Float64
     rhoend::Float64
+    group_mask::UInt32      # 0 = all 8 (telescope, side) groups
+    reserved::UInt32
 end
+Options(flags, method, maxfun, has_xinit, xinit, rhobeg, rhoend) =
+    Options(flags, method, maxfun, has_xinit, xinit, rhobeg, rhoend, UInt32(0), UInt32(0))
 
 const handle = Ref{Ptr{Cvoid}}(C_NULL)
 
@@ -58,9 +71,9 @@ end
 # buildstates(faintstates, timestamp; lag, preswitchdelay, postwitchdelay), src/Faint.jl:21
 function buildstates(faintstates::FaintStates{T,A}, timestamp::AbstractVector;
                      lag::Integer=0, preswitchdelay=0, postwitchdelay=0) where {T<:AbstractFloat,A<:AbstractVector{T}}
-    t = collect(Float64, timestamp)
-    t1 = collect(Float64, faintstates.timer1)
-    t2 = collect(Float64, faintstates.timer2)
+    t = convert(Vector{Float64}, timestamp)           # no copy for a Vector{Float64}
+    t1 = convert(Vector{Float64}, faintstates.timer1)
+    t2 = convert(Vector{Float64}, faintstates.timer2)
     st = Vector{Int8}(undef, length(t))
     gppd_assert_ok(ccall((:gppd_buildstates, libgppd), Cint,
         (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64,
@@ -81,8 +94,8 @@ function demodulateall(timestamp::AbstractVector, data::AbstractMatrix{Complex{T
                        postwitchdelay=0.3) where {T<:AbstractFloat,S<:AbstractVector{MetState}}
     n = length(timestamp)
     size(data) == (n, 40) || error("voltage and time must have the same number of lines")
-    t = collect(Float64, timestamp)
-    d = Matrix{ComplexF64}(data)                       # N x 40, column-major
+    t = convert(Vector{Float64}, timestamp)           # no copy when the types already match
+    d = convert(Matrix{ComplexF64}, data)              # N x 40, column-major (views are copied)
     state = C_NULL
     stvec = Int8[]
     if isa(faintparam, FaintStates)                    # :366-367

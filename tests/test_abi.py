@@ -50,7 +50,8 @@ def test_host_helpers(gp, ora):
 
 def test_options_struct_layout(gp):
     # must match `struct gppd_options` of include/gppd.h
-    assert C.sizeof(gp._lib.Options) == 4 * 4 + 2 * 8 + 8 + 8
+    assert C.sizeof(gp._lib.Options) == 4 * 4 + 2 * 8 + 8 + 8 + 2 * 4
+    assert gp._lib.Options.group_mask.offset == 48
     assert gp._lib.Options.xinit.offset == 16 and gp._lib.Options.rhobeg.offset == 32
 
 
