@@ -9,7 +9,7 @@ The numerics live in ``libgppd.so`` (hand-written CUDA, C ABI in
 Julia API.  There is no CPU fallback: without the built library and a B200 the
 calls raise ``GppdError``.
 """
-from . import synthetic  # noqa: F401
+from . import sharding, synthetic  # noqa: F401
 from ._lib import GppdError, Handle, build, default_handle  # noqa: F401
 from .api import (D1, D2, D3, D4, FC, FT, HIGH, LOW, M_2PI, NORMAL, OFF, SC,  # noqa: F401
                   TRANSIENT, Diode, FaintStates, MetState, ModulationNoOffsets,

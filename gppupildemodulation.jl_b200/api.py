@@ -133,8 +133,9 @@ def buildstates(faintstates: FaintStates, timestamp, lag: int = 0, preswitchdela
 
 
 def _options(onlyhigh=False, fitoffsets=False, recenter=True, keepraw=False, init="auto",
-             method="auto", maxfun=0, empirical=False) -> Options:
+             method="auto", maxfun=0, empirical=False, groups=0) -> Options:
     o = Options()
+    o.group_mask = int(groups) & 0xff
     o.flags = ((_lib.ONLYHIGH if onlyhigh else 0) | (_lib.FITOFFSETS if fitoffsets else 0) |
                (0 if recenter else _lib.NO_RECENTER) | (_lib.KEEPRAW if keepraw else 0) |
                (_lib.CENTER_EMPIRICAL if empirical else 0))
@@ -168,7 +169,7 @@ def _params_to_structs(params, fitoffsets):
 def demodulateall(timestamp, data, init="auto", recenter=True, faintparam=None,
                   onlyhigh=False, fitoffsets=False, preswitchdelay=0.01, postwitchdelay=0.3,
                   *, raw=False, nwindow=0, method="auto", maxfun=0, return_info=False,
-                  return_trace=False, handle=None):
+                  return_trace=False, handle=None, groups=0):
     """demodulateall(timestamp, data; init, recenter, faintparam, onlyhigh,
     fitoffsets, preswitchdelay, postwitchdelay) -> (output, param, likelihood)
     (src/Modulation.jl:344-435).
@@ -176,7 +177,11 @@ def demodulateall(timestamp, data, init="auto", recenter=True, faintparam=None,
     data: (N, 40) complex128.  faintparam: None | FaintStates | vector of MetState.
     Keyword-only extras (not in the reference): ``raw`` returns param as a
     (nwin*32, 6) array (c.re, c.im, a.re, a.im, b, phi); ``nwindow`` runs the
-    per-window loop of src/GPPupilDemodulation.jl:204-225 in one call.
+    per-window loop of src/GPPupilDemodulation.jl:204-225 in one call; ``groups`` is
+    ``gppd_options.group_mask`` (bit g = (telescope, side) group g of
+    src/Modulation.jl:387; 0 = all): only those groups' columns, params and chi2 entries
+    are computed, the rest of the returned arrays is unspecified -- see
+    ``sharding.gather_groups``.
     """
     h = handle or _lib.default_handle()
     t = np.ascontiguousarray(timestamp, dtype=np.float64)
@@ -193,7 +198,7 @@ def demodulateall(timestamp, data, init="auto", recenter=True, faintparam=None,
         if state.shape != (n,):
             raise ValueError("state and time must have the same number of lines")
     o = _options(onlyhigh=onlyhigh, fitoffsets=fitoffsets, recenter=recenter, init=init,
-                 method=method, maxfun=maxfun)
+                 method=method, maxfun=maxfun, groups=groups)
     nwin = int(lib().gppd_num_windows(n, int(nwindow)))
     out = np.empty((n, 40), dtype=np.complex128, order="F")
     params = np.empty((nwin * 32, 6))

@@ -30,6 +30,7 @@ import time
 import numpy as np
 
 from . import _lib, fits
+from .sharding import partition_files
 from .api import (_options, buildfaintparameters, demodulation_keys, read_stefan_file,
                   window_columns)
 
@@ -259,7 +260,7 @@ def main(argv=None) -> int:
         offsets = None
     else:
         raise SystemExit(f"unknown --center {args.center}")
-    mine = files[args.rank::max(1, args.world)]
+    mine = partition_files(files, args.rank, args.world)   # no communication between ranks
     handle = _lib.Handle(args.device)
     sched = NightScheduler(handle, offsets, args.onlyhigh)
 
