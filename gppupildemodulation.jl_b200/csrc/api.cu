@@ -276,6 +276,10 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     // longest job = grid width and stride of the partial buffers
     const int P = harm_max_segments(max_wrows);
     const int SP = stats_max_segments(max_wrows);
+    if (P > 65535 || (long long)faint_jobs.size() * SP > 0x7fffffffll) {
+        g_last_error = "job too long for one launch (more than 65 535 harmonic segments)";
+        return GPPD_ERR_ARG;
+    }
 
     // ---- scratch ------------------------------------------------------------
     if ((rc = s.tabs.ensure(sizeof(TableDesc) * (size_t)T))) return rc;

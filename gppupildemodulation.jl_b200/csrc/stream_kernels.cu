@@ -377,8 +377,10 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
             unsigned flags, int P, double *part) {
     __shared__ double s_piv[NGROUP][16];
     __shared__ double s_acc[STATS_THREADS / 32][NGROUP][STATS_VALS];
-    const int p = blockIdx.y;
-    const int job = faint_jobs[blockIdx.x];
+    // 1-D grid, block = (FAINT job, segment): a 1e8-row job has more segments than
+    // gridDim.y holds
+    const int p = (int)(blockIdx.x % (unsigned)P);
+    const int job = faint_jobs[blockIdx.x / (unsigned)P];
     const JobInfo ji = jobs[job];
     const TableDesc &tb = tabs[ji.table];
     if (!tb.state) return;
@@ -553,7 +555,7 @@ void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_j
                   const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
                   double *d_part, double *d_table) {
     if (nfaint <= 0) return;
-    dim3 grid(nfaint, P);
+    const unsigned grid = (unsigned)((long long)nfaint * P);
     k_stats_seg<<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt, flags, P,
                                                      d_part);
     const int njg = njobs * NGROUP;
