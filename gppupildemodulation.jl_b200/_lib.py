@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgppd.so")
+# GPPD_LIBRARY: another build of the same library (kernel experiments, tools/); default in-tree
+LIB_PATH = os.environ.get("GPPD_LIBRARY") or os.path.join(_HERE, "libgppd.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0

@@ -600,253 +600,371 @@ __device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned fl
                         __dadd_rn(__dmul_rn(d.y, ca), -__dmul_rn(d.x, sa)));
 }
 
-// One thread per (row, group): 4 diodes + the group's FC channel.  A block walks
-// DM_TPB consecutive tiles of DM_ROWS rows of one table.  Dense float32 tables (the
-// METROLOGY layout) are moved as whole row tiles by the TMA: cp.async.bulk
-// global -> shared into a 3-stage ring (two tiles in flight while one is being
-// worked on), results written IN PLACE over the tile and sent back shared -> global
-// by another bulk copy, so the LSU only sees the 128-bit shared-memory accesses of
-// the arithmetic.  Other layouts (strided / unaligned rows, keepraw's 144-float
-// rows) are staged with cooperative word loops through the same buffers.
-constexpr int DM_ROWS = 64;
-constexpr int DM_THREADS = 256;
-constexpr int DM_TPB = 16;                          // tiles per block
-constexpr int DM_STAGES = 3;
-constexpr int DM_STAGE_BYTES = DM_ROWS * (320 + 16); // raw rows + basis
-constexpr int DM_SMEM_OUT = DM_ROWS * 144 * 4;      // keepraw staging
-constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + DM_SMEM_OUT + 64;
+// sin and cos of the demodulation phase psi for the float32 table path: |error| < 2e-10,
+// i.e. 2^-32 -- the result is rounded to float32 (2^-24) right after, so a full-precision
+// double sincos would buy nothing.  psi = b sin(.) is a few radians at most: one-constant
+// Cody-Waite reduction by pi/2 (the quotient through the 1.5 * 2^52 rounding trick: no
+// conversion instruction, the XU pipe issues one warp instruction every 8 cycles) and the
+// leading terms of the fdlibm kernel polynomials.
+// The caller guarantees |x| < 1e4 (|psi| <= |b|: checked once per fit, not per row).
+__device__ __forceinline__ void sincos_demod(double x, double *sn, double *cs) {
+    const double t = fma(x, c_sincos[0], 6755399441055744.0);      // 1.5 * 2^52: low word = rint(x 2/pi)
+    const int k = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    const double r = fma(-fn, c_sincos[1], x);                     // |fn| pi/2_lo < 1e-12
+    const double z = r * r;
+    double ps = fma(z, c_sincos[4], c_sincos[5]);                  // S5, S4
+    ps = fma(z, ps, c_sincos[6]);
+    ps = fma(z, ps, c_sincos[7]);
+    ps = fma(z, ps, c_sincos[8]);
+    const double ks = fma(z * r, ps, r);
+    double pc = fma(z, c_sincos[11], c_sincos[12]);                // C4, C3
+    pc = fma(z, pc, c_sincos[13]);
+    pc = fma(z, pc, c_sincos[14]);
+    pc = fma(z, pc, -0.5);
+    const double kc = fma(z, pc, 1.0);
+    const bool odd = k & 1;
+    const double s0 = odd ? kc : ks, c0 = odd ? ks : kc;
+    const int sflip = (k & 2) << 30, cflip = ((k + 1) & 2) << 30;
+    *sn = __hiloint2double(__double2hiint(s0) ^ sflip, __double2loint(s0));
+    *cs = __hiloint2double(__double2hiint(c0) ^ cflip, __double2loint(c0));
+}
 
-template <bool BE>   // raw FITS byte order of the float32 tables (GPPD_BIG_ENDIAN, a batch-wide flag)
+// METROLOGY tables (float32 rows).  Every WARP runs its own pipeline over a contiguous run of
+// rows, 8 rows (one mini-tile) at a time, with no block-level synchronisation at all:
+//   cp.async.bulk global -> shared into the warp's 3-stage ring (raw rows + basis, tracked by
+//   the warp's own mbarriers), results written IN PLACE over the mini-tile, cp.async.bulk
+//   shared -> global.  While a warp waits for its bytes the other warps of the SM compute,
+//   and the LSU only sees the shared-memory accesses of the arithmetic.  (A copy-only build
+//   of this pipeline moves the night at 6.6 TB/s, the measured HBM copy rate.)
+// Thread mapping: lane = DIODE (0..31); a warp works on DM_UNROLL rows at a time.  A lane
+// reads the 8 bytes of its diode -- a warp reads 256 contiguous bytes, conflict-free -- and
+// keeps the constants of its fit (b, alpha, cos q, sin q, c, the centre) in registers for the
+// whole job.  The 8 fibre-coupler channels of the 8 rows (128 floats) pass through four per
+// lane.  Other layouts (strided / unaligned rows) and keepraw's 144-float rows are staged
+// with warp-cooperative word loops through the same buffers.
+// complex128 arrays (the demodulateall boundary) are channel-major: there the lanes run
+// along the rows (coalesced 16-byte accesses) and a warp loops over the channels.
+constexpr int DM_THREADS = 256;
+constexpr int DM_WARPS = DM_THREADS / 32;
+constexpr int DM_MT = 8;                            // rows per mini-tile
+#ifndef DM_WROWS_N
+#define DM_WROWS_N 128
+#endif
+constexpr int DM_WROWS = DM_WROWS_N;                // consecutive rows per warp (16 mini-tiles)
+constexpr int DM_BLOCK_ROWS = DM_WARPS * DM_WROWS;  // 1024 rows per block
+constexpr int DM_STAGES = 3;
+#ifndef DM_UNROLL_N
+#define DM_UNROLL_N 1
+#endif
+constexpr int DM_UNROLL = DM_UNROLL_N;              // rows a warp interleaves
+constexpr int DM_STAGE_BYTES = DM_MT * (320 + 16);  // raw rows + basis
+constexpr int DM_WARP_BYTES = DM_STAGES * DM_STAGE_BYTES;
+constexpr int DM_OUT_BYTES = DM_MT * 144 * 4;       // keepraw staging, per warp
+constexpr int DM_SMEM = DM_WARPS * DM_WARP_BYTES;
+constexpr int DM_SMEM_KEEPRAW = DM_SMEM + DM_WARPS * DM_OUT_BYTES;
+static_assert(DM_MT % DM_UNROLL == 0 && DM_WROWS % DM_MT == 0, "mini-tiles");
+
+// constants of one fit as the demodulation needs them
+struct DemodK {
+    double b, alpha, cq, sq, cre, cim;
+    int uniform;
+};
+__device__ __forceinline__ DemodK demod_constants(const FitResult *fr, bool offs) {
+    const double2 ba = __ldg(reinterpret_cast<const double2 *>(&fr->b));
+    const double2 cs = __ldg(reinterpret_cast<const double2 *>(&fr->cq));
+    DemodK k;
+    k.b = ba.x; k.alpha = ba.y; k.cq = cs.x; k.sq = cs.y;
+    k.cre = k.cim = 0.0;
+    if (offs) {
+        const double2 cc = __ldg(reinterpret_cast<const double2 *>(&fr->cre));
+        k.cre = cc.x; k.cim = cc.y;
+    }
+    k.uniform = __ldg(&fr->uniform);
+    return k;
+}
+
+// complex128, channel-major (kind 1): lanes along the rows
+__device__ void demod_arrays(const TableDesc &tbg, const FitResult *results, unsigned flags) {
+    const TableView &tv = tbg.tv;
+    const OutView &ov = tbg.ov;
+    const long long n = tv.n, wrows = tbg.wrows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long blk0 = (long long)blockIdx.x * DM_BLOCK_ROWS;
+    const long long blk1 = blk0 + DM_BLOCK_ROWS < n ? blk0 + DM_BLOCK_ROWS : n;
+    for (long long base = blk0 + warp * 32; base < blk1; base += DM_THREADS) {
+        const long long i = base + lane;
+        const bool live = i < blk1;
+        const long long ii = live ? i : blk1 - 1;
+        const double theta = row_theta(tv, ii);
+        const double2 sc = tbg.basis[ii];
+        const long long job = ii / wrows;
+        for (int group = 0; group < NGROUP; ++group) {
+            if (!group_on(flags, group)) continue;   // gppd_options.group_mask: columns left untouched
+#pragma unroll 1
+            for (int dio = 0; dio < 4; ++dio) {
+                const int ch = group * 4 + dio;
+                const FitResult *fr = results + ((long long)tbg.job0 + job) * NDIODE + ch;
+                const double2 o = demod_sample(*fr, flags, theta, sc, row_sample(tv, ii, ch));
+                if (live) ov.out[(long long)ch * n + i] = o;
+            }
+            const int fcch = fc_channel(group);
+            if (live) ov.out[(long long)fcch * n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
+        }
+    }
+}
+
+// BE: raw FITS byte order of the float32 tables (GPPD_BIG_ENDIAN, a batch-wide flag);
+// OFFS: the centres are fitted (GPPD_FITOFFSETS): out = (d - c) exp(-j psi)
+template <bool BE, bool OFFS>
 __global__ void __launch_bounds__(DM_THREADS, 3) k_demod(const TableDesc *tabs, const FitResult *results,
                                                          unsigned flags) {
     const TableDesc &tbg = tabs[blockIdx.y];
-    // table description in registers (the asm memory clobbers below would otherwise
-    // force re-reading it from global memory)
     const long long n = tbg.tv.n, wrows = tbg.wrows;
-    const long long tile_first = (long long)blockIdx.x * DM_TPB;
-    if (tile_first * DM_ROWS >= n) return;
-    const int rl = threadIdx.x >> 3, group = threadIdx.x & 7;
-
-    if (tbg.ov.kind == 1) {  // complex128, channel-major: already unit stride along rows
-        if (!group_on(flags, group)) return;   // gppd_options.group_mask: columns left untouched
-        const TableView &tv = tbg.tv;
-        const OutView &ov = tbg.ov;
-        const long long row_end = (tile_first + DM_TPB) * DM_ROWS < n ? (tile_first + DM_TPB) * DM_ROWS : n;
-        for (long long i = tile_first * DM_ROWS + rl; i < row_end; i += DM_THREADS / 8) {
-            const FitResult *fr = results + ((long long)tbg.job0 + i / wrows) * NDIODE;
-            double theta = row_theta(tv, i);
-            double2 sc = tbg.basis[i];
-            for (int dio = 0; dio < 4; ++dio) {
-                int ch = group * 4 + dio;
-                ov.out[(long long)ch * n + i] = demod_sample(fr[ch], flags, theta, sc, row_sample(tv, i, ch));
-            }
-            int fcch = fc_channel(group);
-            ov.out[(long long)fcch * n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
-        }
+    if ((long long)blockIdx.x * DM_BLOCK_ROWS >= n) return;
+    if (tbg.ov.kind == 1) {
+        demod_arrays(tbg, results, flags);
         return;
     }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wr0 = (long long)blockIdx.x * DM_BLOCK_ROWS + (long long)warp * DM_WROWS;
+    if (wr0 >= n) return;                      // (no block-level barrier below: a warp may leave)
+    const int wn = (int)((n - wr0) < DM_WROWS ? (n - wr0) : DM_WROWS);     // this warp's rows
+    const int nmt = (wn + DM_MT - 1) / DM_MT;
 
-    extern __shared__ __align__(16) unsigned char dm_smem[];
-    // [3 stages][mbarriers (64 B)][keepraw staging, only allocated with GPPD_KEEPRAW]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(dm_smem + DM_STAGES * DM_STAGE_BYTES);
-    uint32_t *s_outbuf = reinterpret_cast<uint32_t *>(dm_smem + DM_STAGES * DM_STAGE_BYTES + 64);
+    extern __shared__ __align__(128) unsigned char dm_smem[];
+    __shared__ uint64_t s_bars[DM_WARPS][DM_STAGES];
+    unsigned char *ring = dm_smem + warp * DM_WARP_BYTES;
+    uint64_t *bars = s_bars[warp];
 
     const char *volt_in = reinterpret_cast<const char *>(tbg.tv.volt);
     char *volt_out = reinterpret_cast<char *>(tbg.ov.volt);
     const long long in_stride = tbg.tv.volt_stride, out_stride = tbg.ov.volt_stride;
     const double2 *basis = tbg.basis;
     const double2 *offsets = tbg.tv.offsets;
-    constexpr bool be_in = BE, be_out = BE;
     const int keepraw = tbg.ov.keepraw;
     const int job0 = tbg.job0, njobs = tbg.njobs;
     const int ow = keepraw ? 144 : 80;   // output words per row
+    const int obase = keepraw ? 80 : 0;  // where the demodulated diodes go in an output row
     const bool bulk_in = in_stride == 320 && aligned16(volt_in);
     const bool bulk_out = out_stride == 4 * ow && aligned16(volt_out);
-    const bool offs = (flags & 2u) != 0, recenter = !(flags & 4u);
+    const bool recenter = !(flags & 4u);
+    uint32_t *s_outbuf = reinterpret_cast<uint32_t *>(dm_smem + DM_SMEM + warp * DM_OUT_BYTES);   // keepraw only
 
-    const long long ntiles_tab = (n + DM_ROWS - 1) / DM_ROWS;
-    const int T = (int)((ntiles_tab - tile_first) < DM_TPB ? (ntiles_tab - tile_first) : DM_TPB);
-    auto tile_rows = [&](int k) {
-        const long long rb = (tile_first + k) * DM_ROWS;
-        return (int)((n - rb) < DM_ROWS ? (n - rb) : DM_ROWS);
-    };
-    auto issue_load = [&](int k) {  // one thread
+    auto mt_rows = [&](int k) { return (wn - k * DM_MT) < DM_MT ? (wn - k * DM_MT) : DM_MT; };
+    auto issue_load = [&](int k) {  // lane 0
         const int st = k % DM_STAGES;
-        const long long rb = (tile_first + k) * DM_ROWS;
-        const unsigned nr = (unsigned)tile_rows(k);
-        unsigned char *stage = dm_smem + st * DM_STAGE_BYTES;
+        const long long rb = wr0 + (long long)k * DM_MT;
+        const unsigned nr = (unsigned)mt_rows(k);
+        unsigned char *stage = ring + st * DM_STAGE_BYTES;
         mbar_expect_tx(&bars[st], nr * (320u + 16u));
         bulk_g2s(stage, volt_in + rb * 320, nr * 320u, &bars[st]);
-        bulk_g2s(stage + DM_ROWS * 320, basis + rb, nr * 16u, &bars[st]);
+        bulk_g2s(stage + DM_MT * 320, basis + rb, nr * 16u, &bars[st]);
     };
     if (bulk_in) {
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             for (int st = 0; st < DM_STAGES; ++st) mbar_init(&bars[st], 1);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        __syncwarp();
+        if (lane == 0) {
             issue_load(0);
-            if (T > 1) issue_load(1);
+            if (nmt > 1) issue_load(1);
         }
     }
 
-    // Fit constants of one job (32 diodes) and the 40 centres live in shared memory: in
-    // registers they cost 68 registers per thread and a third of the occupancy.
-    // (indexed [diode of the group][group]: the 8 groups of a warp read 8 consecutive
-    // 16-byte words, one conflict-free wavefront)
-    __shared__ double2 s_ba[4][NGROUP], s_cs[4][NGROUP], s_cc[4][NGROUP];   // (b, alpha), (cq, sq), c
-    __shared__ int s_uni[4][NGROUP];
-    __shared__ double2 s_off[5][NGROUP];               // centres of the 4 diodes and the FC channel
-    long long job_cached = -1;                         // block-uniform
-    auto cache_job = [&](long long job) {              // called by all threads of the block
-        __syncthreads();                               // the previous job's readers are done
-        if (threadIdx.x < NDIODE) {
-            const FitResult &fr = results[((long long)job0 + job) * NDIODE + threadIdx.x];
-            const int g = threadIdx.x >> 2, d = threadIdx.x & 3;
-            s_ba[d][g] = make_double2(fr.b, fr.alpha);
-            s_cs[d][g] = make_double2(fr.cq, fr.sq);
-            s_cc[d][g] = offs ? make_double2(fr.cre, fr.cim) : make_double2(0.0, 0.0);
-            s_uni[d][g] = fr.uniform;
-        }
-        __syncthreads();
-        job_cached = job;
-    };
-    if (threadIdx.x < NCHAN) {
-        const int ch = threadIdx.x;
-        const int g = ch < NDIODE ? ch >> 2 : ch - NDIODE, d = ch < NDIODE ? ch & 3 : 4;
-        s_off[d][g] = offsets ? __ldg(offsets + ch) : make_double2(0.0, 0.0);
+    // this lane's diode: centre of its channel; FC pass-through: floats 4 lane .. 4 lane + 3 of the
+    // mini-tile's 8 x 16 FC floats = row lane / 4, FC channels 2 (lane % 4) and 2 (lane % 4) + 1
+    const double2 off_d = offsets ? __ldg(offsets + lane) : make_double2(0.0, 0.0);
+    const int fc_row = lane >> 2, fc_col = 64 + 4 * (lane & 3);
+    const double2 off_f0 = offsets ? __ldg(offsets + NDIODE + 2 * (lane & 3)) : make_double2(0.0, 0.0);
+    const double2 off_f1 = offsets ? __ldg(offsets + NDIODE + 2 * (lane & 3) + 1) : make_double2(0.0, 0.0);
+    DemodK K;
+    K.b = K.alpha = K.cq = K.sq = K.cre = K.cim = 0.0;
+    K.uniform = 0;
+    long long job_cached = -1;
+    if (njobs == 1) {
+        K = demod_constants(results + (long long)job0 * NDIODE + lane, OFFS);
+        job_cached = 0;
     }
-    if (njobs == 1) cache_job(0);
-    else __syncthreads();
 
 #pragma unroll 1
-    for (int k = 0; k < T; ++k) {
+    for (int k = 0; k < nmt; ++k) {
         const int st = k % DM_STAGES;
-        const long long row_base = (tile_first + k) * DM_ROWS;
-        const int nrow = tile_rows(k);
-        unsigned char *stage = dm_smem + st * DM_STAGE_BYTES;
+        const long long row_base = wr0 + (long long)k * DM_MT;
+        const int nrow = mt_rows(k);
+        unsigned char *stage = ring + st * DM_STAGE_BYTES;
         uint32_t *s_in = reinterpret_cast<uint32_t *>(stage);
-        const double2 *s_basis = reinterpret_cast<const double2 *>(stage + DM_ROWS * 320);
+        double2 *s_basis = reinterpret_cast<double2 *>(stage + DM_MT * 320);
         uint32_t *s_out = keepraw ? s_outbuf : s_in;
         if (bulk_in) {
-            if (threadIdx.x == 0 && k + 2 < T) {
-                bulk_wait_read();          // tile k-1's store has released stage (k+2) % 3
-                issue_load(k + 2);
-            }
             mbar_wait(&bars[st], (unsigned)(k / DM_STAGES) & 1u);
         } else {
-            if (bulk_out) {   // a bulk store of an earlier tile may still be reading this stage
-                if (threadIdx.x == 0) bulk_wait_read();
-                __syncthreads();
+            if (bulk_out) {   // a bulk store of an earlier mini-tile may still be reading this stage
+                if (lane == 0) bulk_wait_read();
+                __syncwarp();
             }
-            for (int w = threadIdx.x; w < nrow * 80; w += DM_THREADS) {
-                int r = w / 80, c = w - r * 80;
+            for (int w = lane; w < nrow * 80; w += 32) {
+                const int r = w / 80, c = w - r * 80;
                 s_in[w] = __ldg(reinterpret_cast<const uint32_t *>(volt_in + (row_base + r) * in_stride) + c);
             }
-            double2 *sb = reinterpret_cast<double2 *>(stage + DM_ROWS * 320);
-            for (int r = threadIdx.x; r < nrow; r += DM_THREADS) sb[r] = basis[row_base + r];
-            __syncthreads();
+            if (lane < nrow) s_basis[lane] = basis[row_base + lane];
+            __syncwarp();
         }
-        if (keepraw && k > 0) {   // the staging buffer is still being read by tile k-1's store
-            if (threadIdx.x == 0) bulk_wait_read();
-            __syncthreads();
+        if (keepraw && k > 0 && bulk_out) {   // the staging buffer is still being read by the last store
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
         }
 
-        // one job per tile (the usual case) -> its constants from shared memory
-        bool tile_one_job = true;
+        // one job per mini-tile (the usual case) -> its constants in registers
+        bool fast = recenter;
         if (njobs != 1) {
             const long long jf = row_base / wrows, jl = (row_base + nrow - 1) / wrows;
-            tile_one_job = jf == jl;
-            if (tile_one_job && jf != job_cached) cache_job(jf);
+            if (jf != jl) {
+                fast = false;
+            } else if (jf != job_cached) {
+                K = demod_constants(results + ((long long)job0 + jf) * NDIODE + lane, OFFS);
+                job_cached = jf;
+            }
+        }
+        // the fast path needs the fit's uniform phase quantum and |psi| <= |b| < 1e4 (sincos_demod);
+        // it is taken by the whole warp or not at all, so that it stays straight-line code and
+        // the DM_UNROLL rows of an iteration interleave
+        fast = fast && K.uniform && fabs(K.b) < 9.0e3;
+        const bool wfast = __all_sync(0xffffffffu, fast);
+
+        // FC pass-through first (it reads words that keepraw copies and nobody overwrites)
+        uint4 fcw = make_uint4(0u, 0u, 0u, 0u);
+        if (!keepraw && fc_row < nrow) {
+            fcw = *reinterpret_cast<const uint4 *>(s_in + fc_row * 80 + fc_col);
+            uint32_t w[4] = {fcw.x, fcw.y, fcw.z, fcw.w};
+            const double o[4] = {off_f0.x, off_f0.y, off_f1.x, off_f1.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {               // centred FC channel, :170-171
+                uint32_t a = w[j];
+                if (BE) a = bswap32(a);
+                a = __float_as_uint(__double2float_rn((double)__uint_as_float(a) - o[j]));
+                if (BE) a = bswap32(a);
+                w[j] = a;
+            }
+            fcw = make_uint4(w[0], w[1], w[2], w[3]);
         }
 
+        if (wfast) {
 #pragma unroll 1
-        for (int rr = rl; rr < nrow; rr += DM_THREADS / 8) {
-            const long long i = row_base + rr;
-            const uint4 w0 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group);
-            const uint4 w1 = *reinterpret_cast<const uint4 *>(s_in + rr * 80 + 8 * group + 4);
-            const uint2 wf = *reinterpret_cast<const uint2 *>(s_in + rr * 80 + 64 + 2 * group);
-            uint32_t raw[10] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, wf.x, wf.y};
-            uint32_t res[10];
-            const double2 sc = s_basis[rr];
+            for (int r0 = 0; r0 < nrow; r0 += DM_UNROLL) {
+                uint2 raw[DM_UNROLL], res[DM_UNROLL];
+                double2 sc[DM_UNROLL];
 #pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const int ch = d < 4 ? group * 4 + d : fc_channel(group);
-                uint32_t a = raw[2 * d], b = raw[2 * d + 1];
-                if (be_in) { a = bswap32(a); b = bswap32(b); }
-                const double2 off = s_off[d][group];
-                double vr = (double)__uint_as_float(a) - off.x;
-                double vi = (double)__uint_as_float(b) - off.y;
-                double2 o;
-                if (d == 4) {
-                    o = make_double2(vr, vi);                       // centred FC channel, :170-171
-                } else if (recenter && tile_one_job && s_uni[d][group]) {
-                    // psi = fl(fl(b sin(theta + q)) + alpha) - alpha), out = (d - c) exp(-j psi)
-                    const double2 ba = s_ba[d][group], cs = s_cs[d][group];
-                    const double sn = fma(sc.x, cs.x, sc.y * cs.y);
-                    const double gp = __dadd_rn(__dmul_rn(ba.x, sn), ba.y);
-                    const double psi = __dadd_rn(gp, -ba.y);
-                    double sp, cp;
-                    sincos_moderate(psi, &sp, &cp);
-                    if (offs) {
-                        const double2 cc = s_cc[d][group];
-                        vr -= cc.x;
-                        vi -= cc.y;
-                    }
-                    o = make_double2(fma(vr, cp, vi * sp), fma(vi, cp, -(vr * sp)));
-                } else {     // tile straddling two jobs, no uniform quantum, or recenter = false
-                    const FitResult *fr = results + ((long long)job0 + i / wrows) * NDIODE;
-                    o = demod_sample(fr[ch], flags, row_theta(tbg.tv, i), sc, make_double2(vr, vi));
+                for (int u = 0; u < DM_UNROLL; ++u) {
+                    const int rs = r0 + u < nrow ? r0 + u : r0;     // (rows past the mini-tile repeat row r0)
+                    raw[u] = *reinterpret_cast<const uint2 *>(s_in + rs * 80 + 2 * lane);
+                    sc[u] = s_basis[rs];
                 }
+#pragma unroll
+                for (int u = 0; u < DM_UNROLL; ++u) {
+                    uint32_t a = raw[u].x, b = raw[u].y;
+                    if (BE) { a = bswap32(a); b = bswap32(b); }
+                    double vr = (double)__uint_as_float(a) - off_d.x;
+                    double vi = (double)__uint_as_float(b) - off_d.y;
+                    // out = (d - c) exp(-j psi), psi = fl(fl(b sin(theta + q) + alpha) - alpha) = b sin(.)
+                    // up to 2 ulp(|psi| + |alpha|) ~ 1e-15, six orders below the float32 result
+                    const double sn = fma(sc[u].x, K.cq, sc[u].y * K.sq);
+                    const double psi = K.b * sn;
+                    double sp, cp;
+#ifdef DM_COPY_ONLY     // experiment: the pipeline without the arithmetic
+                    sp = 0.0; cp = 1.0 + psi * 1e-300;
+#else
+                    sincos_demod(psi, &sp, &cp);
+#endif
+                    if (OFFS) { vr -= K.cre; vi -= K.cim; }
+                    a = __float_as_uint(__double2float_rn(fma(vr, cp, vi * sp)));
+                    b = __float_as_uint(__double2float_rn(fma(vi, cp, -(vr * sp))));
+                    if (BE) { a = bswap32(a); b = bswap32(b); }
+                    res[u] = make_uint2(a, b);
+                }
+#pragma unroll
+                for (int u = 0; u < DM_UNROLL; ++u) {
+                    const int rr = r0 + u;
+                    if (rr >= nrow) continue;
+                    if (keepraw) {   // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
+                        const uint32_t *irow = s_in + rr * 80;
+                        uint32_t *orow = s_out + rr * 144;
+                        orow[lane] = irow[lane];
+                        orow[lane + 32] = irow[lane + 32];
+                        if (lane < 16) orow[lane + 64] = irow[lane + 64];
+                    }
+                    *reinterpret_cast<uint2 *>(s_out + rr * ow + obase + 2 * lane) = res[u];
+                }
+            }
+        } else {     // mini-tile straddling two jobs, no uniform quantum, or recenter = false: row by row
+#pragma unroll 1
+            for (int rr = 0; rr < nrow; ++rr) {
+                const uint2 raw = *reinterpret_cast<const uint2 *>(s_in + rr * 80 + 2 * lane);
+                uint32_t a = raw.x, b = raw.y;
+                if (BE) { a = bswap32(a); b = bswap32(b); }
+                const double vr = (double)__uint_as_float(a) - off_d.x;
+                const double vi = (double)__uint_as_float(b) - off_d.y;
+                const long long i = row_base + rr;
+                const FitResult *fr = results + ((long long)job0 + i / wrows) * NDIODE + lane;
+                const double2 o = demod_sample(*fr, flags, row_theta(tbg.tv, i), s_basis[rr], make_double2(vr, vi));
                 a = __float_as_uint(__double2float_rn(o.x));
                 b = __float_as_uint(__double2float_rn(o.y));
-                if (be_out) { a = bswap32(a); b = bswap32(b); }
-                res[2 * d] = a;
-                res[2 * d + 1] = b;
-            }
-            uint32_t *orow = s_out + rr * ow;
-            if (!keepraw) {
-                *reinterpret_cast<uint4 *>(orow + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
-                *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
-                *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = make_uint2(res[8], res[9]);
-            } else {  // rows 1..80 raw volts, 81..144 demodulated diodes, :163-168
-                *reinterpret_cast<uint4 *>(orow + 8 * group) = w0;
-                *reinterpret_cast<uint4 *>(orow + 8 * group + 4) = w1;
-                *reinterpret_cast<uint2 *>(orow + 64 + 2 * group) = wf;
-                *reinterpret_cast<uint4 *>(orow + 80 + 8 * group) = make_uint4(res[0], res[1], res[2], res[3]);
-                *reinterpret_cast<uint4 *>(orow + 80 + 8 * group + 4) = make_uint4(res[4], res[5], res[6], res[7]);
+                if (BE) { a = bswap32(a); b = bswap32(b); }
+                if (keepraw) {
+                    const uint32_t *irow = s_in + rr * 80;
+                    uint32_t *orow = s_out + rr * 144;
+                    orow[lane] = irow[lane];
+                    orow[lane + 32] = irow[lane + 32];
+                    if (lane < 16) orow[lane + 64] = irow[lane + 64];
+                }
+                *reinterpret_cast<uint2 *>(s_out + rr * ow + obase + 2 * lane) = make_uint2(a, b);
             }
         }
+        if (!keepraw && fc_row < nrow) *reinterpret_cast<uint4 *>(s_out + fc_row * 80 + fc_col) = fcw;
 
         if (bulk_out) {
             fence_async_smem();
-            __syncthreads();
-            if (threadIdx.x == 0) {
+            __syncwarp();
+            if (lane == 0) {
                 bulk_s2g(volt_out + row_base * (4ll * ow), s_out, (unsigned)nrow * 4u * ow);
                 bulk_commit();
             }
         } else {
-            __syncthreads();
-            for (int w = threadIdx.x; w < nrow * ow; w += DM_THREADS) {
-                int r = w / ow, c = w - r * ow;
+            __syncwarp();
+            for (int w = lane; w < nrow * ow; w += 32) {
+                const int r = w / ow, c = w - r * ow;
                 reinterpret_cast<uint32_t *>(volt_out + (row_base + r) * out_stride)[c] = s_out[w];
             }
-            __syncthreads();   // the tile / staging buffer is reused by a later iteration
+            __syncwarp();   // the stage / staging buffer is reused by a later iteration
+        }
+        // next load: stage (k + 2) % 3 was the stage of mini-tile k - 1, whose store (the group
+        // before the one just committed) must have finished reading it
+        if (bulk_in && k + 2 < nmt) {
+            if (lane == 0) {
+                if (bulk_out && !keepraw) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue_load(k + 2);
+            }
         }
     }
-    if (bulk_out && threadIdx.x == 0) bulk_wait_read();
+    if (bulk_out && lane == 0) bulk_wait_read();
 }
 
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
                   const FitResult *d_results, unsigned flags) {
-    cudaFuncSetAttribute(k_demod<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-    cudaFuncSetAttribute(k_demod<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-    const long long rows_per_block = (long long)DM_ROWS * DM_TPB;
-    // the 144-float staging buffer is only needed with keepraw (flag bit 8 = GPPD_KEEPRAW)
-    const int smem = (flags & 8u) ? DM_SMEM : DM_SMEM - DM_SMEM_OUT;
-    const dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), ntables);
-    if (flags & 16u) k_demod<true><<<grid, DM_THREADS, smem, L.stream>>>(d_tabs, d_results, flags);
-    else k_demod<false><<<grid, DM_THREADS, smem, L.stream>>>(d_tabs, d_results, flags);
+    // the 144-float staging buffers are only needed with keepraw (flag bit 8 = GPPD_KEEPRAW)
+    const int smem = (flags & 8u) ? DM_SMEM_KEEPRAW : DM_SMEM;
+    const dim3 grid((unsigned)((max_rows + DM_BLOCK_ROWS - 1) / DM_BLOCK_ROWS), ntables);
+    const bool be = (flags & 16u) != 0, offs = (flags & 2u) != 0;
+#define GPPD_LAUNCH_DEMOD(B, O)                                                                       \
+    do {                                                                                              \
+        cudaFuncSetAttribute(k_demod<B, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_KEEPRAW); \
+        k_demod<B, O><<<grid, DM_THREADS, smem, L.stream>>>(d_tabs, d_results, flags);                \
+    } while (0)
+    if (be && offs) GPPD_LAUNCH_DEMOD(true, true);
+    else if (be) GPPD_LAUNCH_DEMOD(true, false);
+    else if (offs) GPPD_LAUNCH_DEMOD(false, true);
+    else GPPD_LAUNCH_DEMOD(false, false);
+#undef GPPD_LAUNCH_DEMOD
     *L.counter += 1;
 }
 

@@ -444,7 +444,13 @@ def test_full_size_properties(gp, ora, method, monkeypatch):
     assert p2.tobytes() == par.tobytes()          # both boundaries run the same fit
     ref32 = np.empty((100_000, 80), np.float32)
     ref32[:, 0::2], ref32[:, 1::2] = out.real, out.imag
-    assert np.array_equal(vout, ref32)
+    # the table path evaluates exp(-j psi) to 1e-10 (enough for its float32 output), the array
+    # path to full double precision: the float32 values agree except where the double result
+    # sits within 1e-10 of a rounding boundary, and then by one unit in the last place
+    assert np.array_equal(vout[:, 64:], ref32[:, 64:])
+    diff = np.abs(vout[:, :64].astype(np.float64) - ref32[:, :64])
+    assert diff.max() <= 2.0 ** -23 * np.abs(ref32[:, :64]).max()
+    assert (vout[:, :64] != ref32[:, :64]).mean() < 0.02
     # default dispatch: the table's harmonic sums come from the int8 tensor-core kernel
     # (sums equal to ~1e-15, so a NEWUOA trajectory can fork at a rounding-level tie)
     monkeypatch.delenv("GPPD_HARMONICS")
