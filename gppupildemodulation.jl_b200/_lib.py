@@ -25,6 +25,14 @@ class Options(C.Structure):
                 ("group_mask", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+SEG_COPY, SEG_BYTES, SEG_RECORDS = 0, 1, 2
+
+
+class FileSegment(C.Structure):     # gppd_file_segment
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("offset", C.c_int64),
+                ("length", C.c_int64), ("bytes", C.c_void_p)]
+
+
 class GppdError(RuntimeError):
     def __init__(self, status, what, detail):
         super().__init__(f"libgppd: {what} (status {status}){': ' + detail if detail else ''}")
@@ -83,6 +91,13 @@ def lib():
         H, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, _dp,
         _dp, C.c_int64, _dp, C.c_int64, C.c_double, C.POINTER(Options), C.c_void_p, _dp, _dp,
         _i32p, _i8p]
+    L.gppd_file_submit.argtypes = [H, C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                   C.c_int64, C.c_double, _dp, _dp, C.c_int64, _dp, C.c_int64, C.c_double,
+                                   C.POINTER(Options)]
+    L.gppd_file_wait.argtypes = [H, C.c_int, _dp, _dp, _i32p, _i8p]
+    L.gppd_file_write.argtypes = [H, C.c_int, C.c_char_p, C.POINTER(FileSegment), C.c_int32, C.c_void_p,
+                                  C.c_int64]
+    L.gppd_file_drain.argtypes = [H]
     L.gppd_wait.argtypes = [H, C.c_int]
     L.gppd_centres.argtypes = [H, C.c_int, C.c_int64, _dp]
     L.gppd_set_split_chains.argtypes = [H, C.c_int]
@@ -96,6 +111,8 @@ def lib():
     L.gppd_process_tables_f32_dev.argtypes = [
         H, C.c_int, C.c_void_p, C.c_int64, _i64p, _i64p, PP, _dp, PP, C.c_void_p,
         C.POINTER(_dp), _i64p, C.POINTER(_dp), _i64p, C.POINTER(Options), PP, PP, PP, PP, PP]
+    L.gppd_debug_counters.argtypes = [H, C.POINTER(C.c_uint64), C.c_int]
+    L.gppd_debug_counters.restype = C.c_int
     L.gppd_launch_count.restype = C.c_int64
     L.gppd_launch_count.argtypes = [H]
     L.gppd_enable_timing.argtypes = [H, C.c_int]
@@ -103,7 +120,8 @@ def lib():
     L.gppd_measure_fp64_peak.argtypes = [H, _dp]
     for name in ("gppd_create", "gppd_destroy", "gppd_alloc_pinned", "gppd_free_pinned",
                  "gppd_idx", "gppd_phirange", "gppd_buildstates", "gppd_demodulate_f64",
-                 "gppd_demodulate_f64_dev",
+                 "gppd_demodulate_f64_dev", "gppd_file_submit", "gppd_file_wait", "gppd_file_write",
+                 "gppd_file_drain",
                  "gppd_table_windows", "gppd_process_table_f32", "gppd_submit_table_f32",
                  "gppd_submit_fits_rows", "gppd_centres", "gppd_debug_harmonics", "gppd_set_split_chains",
                  "gppd_wait", "gppd_num_slots", "gppd_process_table_f32_dev",

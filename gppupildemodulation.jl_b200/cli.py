@@ -15,8 +15,13 @@ pipelined over the handle's slots -- while one file's records are on the GPU the
 one is being read and uploaded and the previous one written -- and with several GPUs
 (``RANK`` / ``WORLD_SIZE`` from torchrun, or ``--rank/--world``) every rank takes every
 WORLD_SIZE-th file; there is no communication between ranks.  The METROLOGY records
-travel as raw FITS bytes (``gppd_submit_fits_rows``): byte swapping, de-interleaving,
-the fit, the demodulation and the re-packing all happen on the device.
+travel as raw FITS bytes: byte swapping, de-interleaving, the fit, the demodulation and
+the re-packing all happen on the device.  For plain ``.fits`` files Python never touches a
+record: it reads the headers, decides (gating), and hands the file to the library's
+native ingest (``gppd_file_submit`` / ``gppd_file_wait`` / ``gppd_file_write``: reader
+threads fill pinned buffers straight from the file, writer threads assemble the output);
+after the fit it only formats the new METROLOGY header.  Compressed files (``.fits.gz``,
+``fits.Z``) are decompressed here and go through ``gppd_submit_fits_rows``.
 """
 from __future__ import annotations
 
@@ -59,6 +64,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--rank", type=int, default=int(os.environ.get("RANK", "0")), help=argparse.SUPPRESS)
     p.add_argument("--world", type=int, default=int(os.environ.get("WORLD_SIZE", "1")), help=argparse.SUPPRESS)
     p.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")), help=argparse.SUPPRESS)
+    p.add_argument("--no-native", dest="no_native", action="store_true", help=argparse.SUPPRESS)
     p.add_argument("INPUT", nargs="*", default=["."],
                    help="List of all TARGET to process. In conjunction with -r TARGET can contain directories.")
     return p
@@ -67,8 +73,10 @@ def build_parser() -> argparse.ArgumentParser:
 class _Job:
     """One file in flight on one pipeline slot."""
 
-    def __init__(self, filename, outname, hdus, imet, faintparam, mjd, layout, window, keepraw):
+    def __init__(self, filename, outname, hdus, imet, faintparam, mjd, layout, window, keepraw,
+                 native=False):
         self.filename, self.outname, self.hdus, self.imet = filename, outname, hdus, imet
+        self.native = native               # plain file: records read / written by the library
         self.faintparam, self.mjd, self.window, self.keepraw = faintparam, mjd, window, keepraw
         self.row_bytes, self.n, self.cols = layout
         self.tstart = time.time()
@@ -78,7 +86,8 @@ def _plan_file(filename, args, folder):
     """Header gating of one file (reference :358-392).  Returns a _Job or None."""
     if not os.path.isfile(filename) or not filename.endswith(SUFFIXES):
         return None
-    hdus = fits.read_fits(filename)
+    native = filename.endswith(".fits") and not getattr(args, "no_native", False)
+    hdus = fits.scan_fits(filename) if native else fits.read_fits(filename)
     prim = hdus[0].header
     if "ESO INS PMC1 MODULATE" not in prim:
         log.info("no ESO INS PMC1 MODULATE keyword in %s", filename)
@@ -108,7 +117,7 @@ def _plan_file(filename, args, folder):
     fname = os.path.basename(filename).split(".fits")[0]
     outname = os.path.join(folder, fname + args.suffix + ".fits")
     return _Job(filename, outname, hdus, imet, faintparam, mjd, layout,
-                args.window if args.window != 0.0 else None, args.keepraw)
+                args.window if args.window != 0.0 else None, args.keepraw, native=native)
 
 
 class NightScheduler:
@@ -123,6 +132,7 @@ class NightScheduler:
         self.nslots = handle.num_slots
         self.busy = [None] * self.nslots       # (job, buffers) per slot
         self.pinned = [dict() for _ in range(self.nslots)]
+        self.keep = [None] * self.nslots       # per-row columns a pending native write still reads
 
     def _pinned(self, slot, key, nbytes):
         """A pinned staging buffer of the slot, grown on demand."""
@@ -137,33 +147,54 @@ class NightScheduler:
             self.pinned[slot][key] = cur
         return np.ctypeslib.as_array(C.cast(cur[0], C.POINTER(C.c_uint8)), shape=(cur[1],))[:nbytes]
 
+    def _first_times(self, job):
+        """TIME of the first two records (for the --window arithmetic, :192)."""
+        rb, toff = job.row_bytes, job.cols["TIME"][0]
+        met = job.hdus[job.imet]
+        if job.native:
+            with open(job.filename, "rb") as fh:
+                fh.seek(met.data_offset)
+                head = fh.read(2 * rb)
+        else:
+            head = bytes(met.data[:2 * rb])
+        return np.array([int.from_bytes(head[k * rb + toff:k * rb + toff + 4], "big", signed=True)
+                         for k in range(2)], dtype=np.int32)
+
     def submit(self, slot, job: _Job):
         n, rb = job.n, job.row_bytes
         rb_out = rb + (256 if job.keepraw else 0)
-        src = np.frombuffer(job.hdus[job.imet].data, dtype=np.uint8, count=n * rb)
-        rows = self._pinned(slot, "rows", n * rb)
-        rows[:] = src
-        rows_out = self._pinned(slot, "rows_out", n * rb_out)
-        # window arithmetic needs TIME[0:2]; the library reads them from the records
         wrows, nwin = n, 1
         if job.window is not None:
-            toff = job.cols["TIME"][0]
-            t01 = np.array([int.from_bytes(src[k * rb + toff:k * rb + toff + 4].tobytes(), "big", signed=True)
-                            for k in range(2)], dtype=np.int32)
+            t01 = self._first_times(job)
             w, k = C.c_int64(0), C.c_int64(0)
             _lib.check(self.L.gppd_table_windows(2, _lib.ptr(t01, _lib._i32p), job.mjd, float(job.window),
                                                  C.byref(w), C.byref(k)))
             wrows = w.value
             nwin = (n + wrows - 1) // wrows
-        params = np.empty((nwin * 32, 6))
-        chi2 = np.empty(nwin * 32)
-        state = np.empty(n, dtype=np.int8) if job.faintparam is not None else None
         o = _options(onlyhigh=self.onlyhigh, keepraw=job.keepraw, method=self.method,
                      empirical=self.empirical)
         fp = job.faintparam
         t1 = fp.timer1 if fp is not None else None
         t2 = fp.timer2 if fp is not None else None
         off = None if self.offsets is None else self.offsets.view(np.float64)
+        if job.native:
+            # the library reads the records itself, straight into its pinned staging buffers
+            met = job.hdus[job.imet]
+            _lib.check(self.L.gppd_file_submit(
+                self.h.raw, slot, os.fsencode(job.filename), met.data_offset, n, rb, job.cols["TIME"][0],
+                job.cols["VOLT"][0], job.mjd, _lib.ptr(off), _lib.ptr(t1), 0 if t1 is None else t1.size,
+                _lib.ptr(t2), 0 if t2 is None else t2.size, float(job.window or 0.0), C.byref(o)))
+            self.busy[slot] = (job, dict(wrows=wrows, nwin=nwin, rb_out=rb_out, keep=(o, off, t1, t2)))
+            return
+        src = np.frombuffer(job.hdus[job.imet].data, dtype=np.uint8, count=n * rb)
+        rows = self._pinned(slot, "rows", n * rb)
+        rows[:] = src
+        rows_out = self._pinned(slot, "rows_out", n * rb_out)
+        # the small results in pinned memory too: a download into pageable memory would make
+        # the submit call wait for the whole file
+        params = self._pinned(slot, "params", nwin * 32 * 6 * 8).view(np.float64).reshape(nwin * 32, 6)
+        chi2 = self._pinned(slot, "chi2", nwin * 32 * 8).view(np.float64)
+        state = self._pinned(slot, "state", n).view(np.int8) if job.faintparam is not None else None
         _lib.check(self.L.gppd_submit_fits_rows(
             self.h.raw, slot, n, rows.ctypes.data_as(C.c_void_p), rb, job.cols["TIME"][0],
             job.cols["VOLT"][0], job.mjd, _lib.ptr(off), _lib.ptr(t1), 0 if t1 is None else t1.size,
@@ -179,29 +210,75 @@ class NightScheduler:
         :406-412); returns a future of the output name."""
         job, b = self.busy[slot]
         self.busy[slot] = None
+        if job.native:
+            return self._finish_native(slot, job, b)
         _lib.check(self.L.gppd_wait(self.h.raw, slot))
-        b = dict(b, rows_out=b["rows_out"].copy())     # the slot's staging buffer is reused
+        # the slot's staging buffers are reused by the next file: take the results out
+        b = dict(b, rows_out=b["rows_out"].copy(), params=b["params"].copy(), chi2=b["chi2"].copy(),
+                 state=None if b["state"] is None else b["state"].copy())
         return self.writers.submit(self._write, job, b)
 
-    def _write(self, job, b):
-        n = job.n
+    def _table_edits(self, job, b, n):
+        """(header keys, new columns, extra per-row bytes or None) of the output table
+        (reference :174-189 whole-file keys, :209-249 window-mode columns)."""
         fitoffsets = self.offsets is None and not self.empirical
-        records = b["rows_out"].reshape(n, b["rb_out"])
-        keys, newcols = [], []
+        keys, newcols, extra = [], [], None
         if job.window is None:
             keys += list(demodulation_keys(b["params"], fitoffsets).items())
         else:
             cols = window_columns(b["params"], n, b["wrows"], b["nwin"], fitoffsets)
-            extra = []
+            parts = []
             for name in ("ABSA", "ARGA", "B", "PHI", "X0", "Y0"):
                 if name in cols:
-                    extra.append(cols[name].astype(">f4").view(np.uint8).reshape(n, 128))
+                    parts.append(cols[name].astype(">f4").view(np.uint8).reshape(n, 128))
                     newcols.append((name, "32E", None))
             if b["state"] is not None:      # Int8 column: FITS 'B' with TZERO = -128
-                extra.append((b["state"].astype(np.int16) + 128).astype(np.uint8).reshape(n, 1))
+                parts.append((b["state"].astype(np.int16) + 128).astype(np.uint8).reshape(n, 1))
                 newcols.append(("STATE", "1B", None))
-            records = np.concatenate([records] + extra, axis=1)
+            extra = np.ascontiguousarray(np.concatenate(parts, axis=1))
         keys.append(("PROCSOFT", "GPPupilDemodulation.jl"))
+        return keys, newcols, extra
+
+    def _finish_native(self, slot, job, b):
+        """Wait for the fit, format the new METROLOGY header and hand the writing of the
+        output file (FITScopy!, src/FitsUtils.jl:95-156) to the library's writer threads."""
+        n, nwin = job.n, b["nwin"]
+        b["params"] = np.empty((nwin * 32, 6))
+        b["chi2"] = np.empty(nwin * 32)
+        b["state"] = np.empty(n, dtype=np.int8) if job.faintparam is not None else None
+        _lib.check(self.L.gppd_file_wait(self.h.raw, slot, _lib.ptr(b["params"]), _lib.ptr(b["chi2"]), None,
+                                         _lib.ptr(b["state"], _lib._i8p)))
+        keys, newcols, extra = self._table_edits(job, b, n)
+        met = job.hdus[job.imet]
+        rb_new = b["rb_out"] + (0 if extra is None else extra.shape[1])
+        cards = fits.replace_bintable_cards(met, rb_new, n, {"VOLT": "144E"} if job.keepraw else None,
+                                            newcols, keys)
+        if b["state"] is not None and job.window is not None:
+            i = next(int(v) for k, v in map(fits.parse_card, cards) if k == "TFIELDS")
+            cards += [fits.format_card(f"TSCAL{i}", 1), fits.format_card(f"TZERO{i}", -128)]
+        head = fits.header_bytes(cards)
+        size = os.path.getsize(job.filename)
+        tail = met.data_offset + met.data_padded
+        segs = (_lib.FileSegment * 4)()
+        segs[0].kind, segs[0].offset, segs[0].length = _lib.SEG_COPY, 0, met.hdr_offset
+        segs[1].kind, segs[1].length = _lib.SEG_BYTES, len(head)
+        segs[1].bytes = C.cast(C.c_char_p(head), C.c_void_p)
+        segs[2].kind = _lib.SEG_RECORDS
+        segs[3].kind, segs[3].offset, segs[3].length = _lib.SEG_COPY, tail, max(0, size - tail)
+        _lib.check(self.L.gppd_file_write(
+            self.h.raw, slot, os.fsencode(job.outname), segs, 4,
+            None if extra is None else extra.ctypes.data_as(C.c_void_p), 0 if extra is None else extra.shape[1]))
+        self.keep[slot] = extra             # must stay valid until the slot's next submit / the drain
+        log.info("%s processed in %.3f s", job.filename, time.time() - job.tstart)
+        log.info(" %s written", job.outname)
+        return job.outname
+
+    def _write(self, job, b):
+        n = job.n
+        records = b["rows_out"].reshape(n, b["rb_out"])
+        keys, newcols, extra = self._table_edits(job, b, n)
+        if extra is not None:
+            records = np.concatenate([records, extra], axis=1)
         met = job.hdus[job.imet]
         new = fits.replace_bintable(met, records,
                                     tform_changes={"VOLT": "144E"} if job.keepraw else None,
@@ -232,7 +309,10 @@ class NightScheduler:
                 s = (slot + k) % self.nslots
                 if self.busy[s] is not None:
                     done.append(self.finish(s))
-            return [f.result() for f in done]
+            names = [f if isinstance(f, str) else f.result() for f in done]
+        _lib.check(self.L.gppd_file_drain(self.h.raw))      # the library's writer threads are done
+        self.keep = [None] * self.nslots
+        return names
 
 
 def main(argv=None) -> int:
@@ -283,7 +363,11 @@ def main(argv=None) -> int:
                 if j is not None:
                     yield j
 
-    sched.run(jobs())
+    t0 = time.time()
+    names = sched.run(jobs())
+    if os.environ.get("GPPD_CLI_TIMING"):     # tools/night_cli.py: the night without interpreter start-up
+        import json
+        print(json.dumps({"files_written": len(names), "run_seconds": time.time() - t0}), file=sys.stderr)
     return 0
 
 

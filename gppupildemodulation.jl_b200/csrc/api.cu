@@ -6,10 +6,18 @@
 //                  -> direct fit of flagged fits -> demod -> export
 // (method = direct: basis -> [stats] -> direct fit with HBM scratch -> demod -> export)
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <fcntl.h>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/gppd.h"
@@ -88,8 +96,55 @@ struct PassTimer {
     long long count[NPASS] = {0};
 };
 
+// page-locked host buffer owned by the library (native file ingest)
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return GPPD_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            g_last_error = "cudaMallocHost failed";
+            p = nullptr;
+            return GPPD_ERR_NOMEM;
+        }
+        cap = want;
+        return GPPD_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// One file in flight on a slot (gppd_file_*).  stage: 0 free, 1 queued / being read and
+// submitted, 2 results enqueued on the stream (gppd_file_wait can return), 3 being written.
+struct FileJob {
+    std::mutex m;
+    std::condition_variable cv;
+    int stage = 0;
+    bool write_pending = false;
+    int rc = GPPD_OK;
+    std::string err;
+    // the job as submitted (copied: the caller's buffers are not kept)
+    std::string in_path;
+    int64_t data_offset = 0, n = 0, row_bytes = 0, row_bytes_out = 0, time_off = 0, volt_off = 0, nfits = 0;
+    double mjd = 0.0, window_s = 0.0;
+    bool have_offsets = false, faint = false;
+    double offsets[80];
+    std::vector<double> timer1, timer2;
+    gppd_options opt;
+    PinBuf rows, rows_out, params, chi2, info, state;
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
+    FileJob file;
     // staging of caller data (host-buffer entry points)
     DevBuf time, volt, volt_out, t, data, out, state_in, offsets, rows, rows_out;
     long long htab_vals = 0;        // values in htab after the last batch (test hook)
@@ -106,9 +161,59 @@ struct Slot {
 
 }  // namespace
 
+namespace {
+// a few worker threads with a FIFO of closures (file readers / writers of one handle)
+class IoPool {
+  public:
+    void start(int nthreads, int device) {
+        std::lock_guard<std::mutex> lk(m_);
+        if (!threads_.empty()) return;
+        for (int i = 0; i < nthreads; ++i)
+            threads_.emplace_back([this, device] {
+                cudaSetDevice(device);
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                        if (q_.empty()) return;
+                        f = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    f();
+                }
+            });
+    }
+    void post(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
+    ~IoPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : threads_) t.join();
+    }
+
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+};
+}  // namespace
+
 struct gppd_handle_s {
     int device = 0;
     bool timing = false;
+    IoPool readers, writers;      // native file ingest / egress (started on first use)
+    std::mutex launch_mutex;      // run_batch plans on the host: one planner at a time
     // FAINT and bright tables of a batch as two concurrent launch sequences (default on;
     // GPPD_SPLIT_CHAINS=0 or gppd_set_split_chains)
     bool split_chains = [] {
@@ -571,6 +676,12 @@ int gppd_create(int device, gppd_handle *out) {
 int gppd_destroy(gppd_handle h) {
     if (!h) return GPPD_OK;
     cudaSetDevice(h->device);
+    gppd_file_drain(h);
+    for (int i = 0; i < NSLOTS; ++i) {
+        FileJob &f = h->slots[i].file;
+        PinBuf *pins[] = {&f.rows, &f.rows_out, &f.params, &f.chi2, &f.info, &f.state};
+        for (PinBuf *b : pins) b->release();
+    }
     for (int i = 0; i < 2 * NSLOTS; ++i) {
         Slot &s = i < NSLOTS ? h->slots[i] : h->aux[i - NSLOTS];
         if (s.stream) {
@@ -639,6 +750,16 @@ int gppd_debug_harmonics(gppd_handle h, int slot, double *htab, int64_t nvals) {
 }
 
 int64_t gppd_launch_count(gppd_handle h) { return h ? h->launches : 0; }
+
+int gppd_debug_counters(gppd_handle h, uint64_t *out16, int reset) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out16) return GPPD_ERR_ARG;
+    CK(cudaDeviceSynchronize());
+    tc_profile_read(reinterpret_cast<unsigned long long *>(out16), reset);
+    CK(cudaGetLastError());
+    return GPPD_OK;
+}
 
 int gppd_measure_fp64_peak(gppd_handle h, double *tflops) {
     int rc = check_handle(h);
@@ -923,17 +1044,20 @@ int gppd_submit_table_f32(gppd_handle h, int slot, int64_t n, const int32_t *tim
     return GPPD_OK;
 }
 
-int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, int64_t row_bytes,
-                          int64_t time_off, int64_t volt_off, double mjd, const double *offsets,
-                          const double *timer1, int64_t n1, const double *timer2, int64_t n2,
-                          double window_s, const gppd_options *opt, void *rows_out, double *params,
-                          double *chi2, int32_t *info, int8_t *state_out) {
-    int rc = check_handle(h);
-    if (rc) return rc;
-    if (slot < 0 || slot >= NSLOTS || !rows || !rows_out || !params || !chi2 || n < 2 ||
+// The record path of gppd_submit_fits_rows / gppd_file_submit: upload (unless the records are
+// already in s.rows: `rows_uploaded`), unpack, the batch, pack, download.  `first2` = the first
+// two records on the host (for the --window arithmetic, :192).
+static int submit_rows_core(gppd_handle h, int slot, int64_t n, const void *rows, bool rows_uploaded,
+                            const unsigned char *first2, int64_t row_bytes, int64_t time_off,
+                            int64_t volt_off, double mjd, const double *offsets, const double *timer1,
+                            int64_t n1, const double *timer2, int64_t n2, double window_s,
+                            const gppd_options *opt, void *rows_out, double *params, double *chi2,
+                            int32_t *info, int8_t *state_out, int64_t *nfits_out) {
+    int rc;
+    if (slot < 0 || slot >= NSLOTS || !first2 || !rows_out || !params || !chi2 || n < 2 ||
         time_off < 0 || volt_off < 0 || time_off + 4 > row_bytes || volt_off + 320 > row_bytes ||
         (time_off + 4 > volt_off && time_off < volt_off + 320)) {
-        g_last_error = "submit_fits_rows: bad slot, null buffer, n < 2 or fields outside the record";
+        g_last_error = "fits rows: bad slot, null buffer, n < 2 or fields outside the record";
         return GPPD_ERR_ARG;
     }
     gppd_options o;
@@ -946,7 +1070,7 @@ int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, 
     // TIME of the first two records (host side), for the --window arithmetic (:192)
     int32_t t01[2];
     for (int k = 0; k < 2; ++k) {
-        const unsigned char *p = reinterpret_cast<const unsigned char *>(rows) + k * row_bytes + time_off;
+        const unsigned char *p = first2 + k * row_bytes + time_off;
         t01[k] = (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]);
     }
     int64_t wrows = n, nwin = 1;
@@ -954,9 +1078,10 @@ int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, 
     if (!(window_s > 0.0)) wrows = n;
     nwin = gppd_num_windows(n, wrows);
     size_t nfits = (size_t)nwin * NDIODE;
+    if (nfits_out) *nfits_out = (int64_t)nfits;
     Slot &s = h->slots[slot];
     cudaStream_t st = s.stream;
-    CK(cudaStreamSynchronize(st));  // slot reuse: previous table of this slot must be done
+    if (!rows_uploaded) CK(cudaStreamSynchronize(st));  // slot reuse: previous table of this slot must be done
     if ((rc = s.rows.ensure((size_t)n * (size_t)row_bytes))) return rc;
     if ((rc = s.rows_out.ensure((size_t)n * (size_t)row_bytes_out))) return rc;
     if ((rc = s.time.ensure(sizeof(int32_t) * (size_t)n))) return rc;
@@ -967,7 +1092,8 @@ int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, 
     if ((rc = s.info.ensure(sizeof(int) * GPPD_INFO_STRIDE * nfits))) return rc;
     if ((rc = s.state_out.ensure((size_t)n))) return rc;
     if ((rc = s.offsets.ensure(sizeof(double) * 80))) return rc;
-    CK(cudaMemcpyAsync(s.rows.p, rows, (size_t)n * (size_t)row_bytes, cudaMemcpyHostToDevice, st));
+    if (!rows_uploaded)
+        CK(cudaMemcpyAsync(s.rows.p, rows, (size_t)n * (size_t)row_bytes, cudaMemcpyHostToDevice, st));
     if (offsets)
         CK(cudaMemcpyAsync(s.offsets.p, offsets, sizeof(double) * 80, cudaMemcpyHostToDevice, st));
     Launcher L{st, &h->launches};
@@ -999,6 +1125,336 @@ int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, 
     if (state_out && faint)
         CK(cudaMemcpyAsync(state_out, s.state_out.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     return GPPD_OK;
+}
+
+int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows, int64_t row_bytes,
+                          int64_t time_off, int64_t volt_off, double mjd, const double *offsets,
+                          const double *timer1, int64_t n1, const double *timer2, int64_t n2,
+                          double window_s, const gppd_options *opt, void *rows_out, double *params,
+                          double *chi2, int32_t *info, int8_t *state_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!rows) {
+        g_last_error = "submit_fits_rows: null buffer";
+        return GPPD_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(h->launch_mutex);
+    return submit_rows_core(h, slot, n, rows, false, reinterpret_cast<const unsigned char *>(rows), row_bytes,
+                            time_off, volt_off, mjd, offsets, timer1, n1, timer2, n2, window_s, opt, rows_out,
+                            params, chi2, info, state_out, nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// native file ingest / egress (gppd_file_*)
+namespace {
+
+constexpr size_t IO_CHUNK = 8u << 20;
+
+int io_error(const std::string &what, const std::string &path) {
+    g_last_error = what + " " + path + ": " + strerror(errno);
+    return GPPD_ERR_IO;
+}
+
+// reader thread: file -> pinned (chunk by chunk, each chunk uploaded while the next is read)
+// -> the batch -> pinned results
+int file_reader(gppd_handle h, int slot) {
+    Slot &s = h->slots[slot];
+    FileJob &f = s.file;
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const size_t bytes = (size_t)f.n * (size_t)f.row_bytes;
+    const int out_floats = (f.opt.flags & GPPD_KEEPRAW) ? 144 : 80;
+    f.row_bytes_out = f.row_bytes + 4 * (out_floats - 80);
+    // worst case number of windows is not known before TIME is read: size the small result
+    // buffers after the first chunk
+    if ((rc = f.rows.ensure(bytes))) return rc;
+    if ((rc = f.rows_out.ensure((size_t)f.n * (size_t)f.row_bytes_out))) return rc;
+    if ((rc = f.state.ensure((size_t)f.n))) return rc;
+    CK(cudaStreamSynchronize(s.stream));          // the slot's previous table is done with s.rows
+    if ((rc = s.rows.ensure(bytes))) return rc;
+    const int fd = open(f.in_path.c_str(), O_RDONLY);
+    if (fd < 0) return io_error("cannot open", f.in_path);
+#ifdef POSIX_FADV_SEQUENTIAL
+    posix_fadvise(fd, f.data_offset, (off_t)bytes, POSIX_FADV_SEQUENTIAL);
+#endif
+    size_t done = 0;
+    while (done < bytes) {
+        const size_t want = bytes - done < IO_CHUNK ? bytes - done : IO_CHUNK;
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t r = pread(fd, f.rows.as<char>() + done + got, want - got, (off_t)(f.data_offset + done + got));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) {
+                close(fd);
+                if (r == 0) errno = EIO;
+                return io_error("short read of the METROLOGY records of", f.in_path);
+            }
+            got += (size_t)r;
+        }
+        cudaError_t e = cudaMemcpyAsync(s.rows.as<char>() + done, f.rows.as<char>() + done, want,
+                                        cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) {
+            close(fd);
+            g_last_error = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e);
+            return GPPD_ERR_CUDA;
+        }
+        done += want;
+    }
+    close(fd);
+    // number of fits (windows x 32) -> the small pinned result buffers
+    int32_t t01[2];
+    for (int k = 0; k < 2; ++k) {
+        const unsigned char *p = f.rows.as<unsigned char>() + k * f.row_bytes + f.time_off;
+        t01[k] = (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]);
+    }
+    int64_t wrows = f.n, nwin = 1;
+    if ((rc = gppd_table_windows(2, t01, f.mjd, f.window_s, &wrows, &nwin))) return rc;
+    if (!(f.window_s > 0.0)) wrows = f.n;
+    nwin = gppd_num_windows(f.n, wrows);
+    f.nfits = nwin * NDIODE;
+    if ((rc = f.params.ensure(sizeof(double) * 6 * (size_t)f.nfits))) return rc;
+    if ((rc = f.chi2.ensure(sizeof(double) * (size_t)f.nfits))) return rc;
+    if ((rc = f.info.ensure(sizeof(int32_t) * GPPD_INFO_STRIDE * (size_t)f.nfits))) return rc;
+    std::lock_guard<std::mutex> lk(h->launch_mutex);
+    return submit_rows_core(h, slot, f.n, nullptr, true, f.rows.as<unsigned char>(), f.row_bytes, f.time_off,
+                            f.volt_off, f.mjd, f.have_offsets ? f.offsets : nullptr,
+                            f.faint ? f.timer1.data() : nullptr, (int64_t)f.timer1.size(),
+                            f.faint ? f.timer2.data() : nullptr, (int64_t)f.timer2.size(), f.window_s, &f.opt,
+                            f.rows_out.p, f.params.as<double>(), f.chi2.as<double>(), f.info.as<int32_t>(),
+                            f.state.as<int8_t>(), nullptr);
+}
+
+int write_all(int fd, const void *buf, size_t len, const std::string &path) {
+    const char *p = reinterpret_cast<const char *>(buf);
+    while (len) {
+        const ssize_t w = write(fd, p, len);
+        if (w < 0 && errno == EINTR) continue;
+        if (w <= 0) return io_error("cannot write", path);
+        p += w;
+        len -= (size_t)w;
+    }
+    return GPPD_OK;
+}
+
+struct OutSeg {
+    int kind;
+    int64_t offset, length;
+    std::string bytes;
+};
+
+// writer thread: the output file from its segments (FITScopy!, src/FitsUtils.jl:95-156)
+int file_writer(gppd_handle h, int slot, const std::string &out_path, const std::vector<OutSeg> &segs,
+                const unsigned char *extra, int64_t extra_row_bytes) {
+    Slot &s = h->slots[slot];
+    FileJob &f = s.file;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(s.stream));          // the output records are in pinned memory
+    const int fo = open(out_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fo < 0) return io_error("cannot create", out_path);
+    int fi = -1, rc = GPPD_OK;
+    std::vector<char> bounce;
+    for (const OutSeg &g : segs) {
+        if (g.kind == GPPD_SEG_BYTES) {
+            rc = write_all(fo, g.bytes.data(), g.bytes.size(), out_path);
+        } else if (g.kind == GPPD_SEG_COPY) {
+            if (fi < 0 && (fi = open(f.in_path.c_str(), O_RDONLY)) < 0) {
+                rc = io_error("cannot open", f.in_path);
+                break;
+            }
+            bounce.resize(IO_CHUNK);
+            int64_t done = 0;
+            while (done < g.length && rc == GPPD_OK) {
+                const size_t want = (size_t)((g.length - done) < (int64_t)IO_CHUNK ? (g.length - done) : (int64_t)IO_CHUNK);
+                const ssize_t r = pread(fi, bounce.data(), want, (off_t)(g.offset + done));
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) {
+                    if (r == 0) errno = EIO;
+                    rc = io_error("short read of", f.in_path);
+                    break;
+                }
+                rc = write_all(fo, bounce.data(), (size_t)r, out_path);
+                done += r;
+            }
+        } else if (g.kind == GPPD_SEG_RECORDS) {
+            const size_t rb = (size_t)f.row_bytes_out;
+            size_t total;
+            if (!extra || extra_row_bytes <= 0) {
+                total = (size_t)f.n * rb;
+                rc = write_all(fo, f.rows_out.p, total, out_path);
+            } else {    // records widened by the per-row columns of window mode
+                const size_t eb = (size_t)extra_row_bytes, ob = rb + eb;
+                const size_t rows_per = IO_CHUNK / ob ? IO_CHUNK / ob : 1;
+                bounce.resize(rows_per * ob);
+                total = (size_t)f.n * ob;
+                for (int64_t r0 = 0; r0 < f.n && rc == GPPD_OK; r0 += (int64_t)rows_per) {
+                    const size_t nr = (size_t)((f.n - r0) < (int64_t)rows_per ? (f.n - r0) : (int64_t)rows_per);
+                    for (size_t r = 0; r < nr; ++r) {
+                        memcpy(bounce.data() + r * ob, f.rows_out.as<char>() + ((size_t)r0 + r) * rb, rb);
+                        memcpy(bounce.data() + r * ob + rb, extra + ((size_t)r0 + r) * eb, eb);
+                    }
+                    rc = write_all(fo, bounce.data(), nr * ob, out_path);
+                }
+            }
+            const size_t pad = (2880 - total % 2880) % 2880;
+            if (rc == GPPD_OK && pad) {
+                const std::string zeros(pad, '\0');
+                rc = write_all(fo, zeros.data(), pad, out_path);
+            }
+        }
+        if (rc != GPPD_OK) break;
+    }
+    if (fi >= 0) close(fi);
+    if (close(fo) != 0 && rc == GPPD_OK) rc = io_error("cannot close", out_path);
+    return rc;
+}
+
+}  // namespace
+
+int gppd_file_submit(gppd_handle h, int slot, const char *path, int64_t data_offset, int64_t n,
+                     int64_t row_bytes, int64_t time_off, int64_t volt_off, double mjd,
+                     const double *offsets, const double *timer1, int64_t n1,
+                     const double *timer2, int64_t n2, double window_s, const gppd_options *opt) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS || !path || data_offset < 0 || n < 2 || row_bytes < 324 ||
+        n1 < 0 || n2 < 0 || n1 > MAX_TIMER || n2 > MAX_TIMER) {
+        g_last_error = "file_submit: bad slot, path, offset or table shape";
+        return GPPD_ERR_ARG;
+    }
+    h->readers.start(2, h->device);
+    h->writers.start(3, h->device);
+    FileJob &f = h->slots[slot].file;
+    {
+        std::unique_lock<std::mutex> lk(f.m);
+        f.cv.wait(lk, [&f] { return !(f.stage == 1 || f.stage == 3 || f.write_pending); });
+        f.stage = 1;
+        f.rc = GPPD_OK;
+        f.err.clear();
+        f.in_path = path;
+        f.data_offset = data_offset;
+        f.n = n;
+        f.row_bytes = row_bytes;
+        f.time_off = time_off;
+        f.volt_off = volt_off;
+        f.mjd = mjd;
+        f.window_s = window_s;
+        f.have_offsets = offsets != nullptr;
+        if (offsets) memcpy(f.offsets, offsets, sizeof f.offsets);
+        f.faint = timer1 && timer2 && n1 > 0 && n2 > 0;
+        f.timer1.assign(f.faint ? timer1 : nullptr, f.faint ? timer1 + n1 : nullptr);
+        f.timer2.assign(f.faint ? timer2 : nullptr, f.faint ? timer2 + n2 : nullptr);
+        memset(&f.opt, 0, sizeof f.opt);
+        if (opt) f.opt = *opt;
+    }
+    h->readers.post([h, slot] {
+        FileJob &f = h->slots[slot].file;
+        const int r = file_reader(h, slot);
+        std::lock_guard<std::mutex> lk(f.m);
+        f.rc = r;
+        if (r) f.err = g_last_error;
+        f.stage = 2;
+        f.cv.notify_all();
+    });
+    return GPPD_OK;
+}
+
+int gppd_file_wait(gppd_handle h, int slot, double *params, double *chi2, int32_t *info,
+                   int8_t *state_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS) return GPPD_ERR_ARG;
+    Slot &s = h->slots[slot];
+    FileJob &f = s.file;
+    {
+        std::unique_lock<std::mutex> lk(f.m);
+        if (f.stage == 0) {
+            g_last_error = "file_wait: no file was submitted on this slot";
+            return GPPD_ERR_ARG;
+        }
+        f.cv.wait(lk, [&f] { return f.stage != 1; });
+        if (f.rc) {
+            g_last_error = f.err;
+            return f.rc;
+        }
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    if (params) memcpy(params, f.params.p, sizeof(double) * 6 * (size_t)f.nfits);
+    if (chi2) memcpy(chi2, f.chi2.p, sizeof(double) * (size_t)f.nfits);
+    if (info) memcpy(info, f.info.p, sizeof(int32_t) * GPPD_INFO_STRIDE * (size_t)f.nfits);
+    if (state_out && f.faint) memcpy(state_out, f.state.p, (size_t)f.n);
+    return GPPD_OK;
+}
+
+int gppd_file_write(gppd_handle h, int slot, const char *out_path, const gppd_file_segment *segs,
+                    int32_t nsegs, const void *extra, int64_t extra_row_bytes) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (slot < 0 || slot >= NSLOTS || !out_path || !segs || nsegs < 1 || (extra && extra_row_bytes <= 0)) {
+        g_last_error = "file_write: bad slot, path or segments";
+        return GPPD_ERR_ARG;
+    }
+    FileJob &f = h->slots[slot].file;
+    std::vector<OutSeg> copy((size_t)nsegs);
+    for (int i = 0; i < nsegs; ++i) {
+        copy[i].kind = segs[i].kind;
+        copy[i].offset = segs[i].offset;
+        copy[i].length = segs[i].length;
+        if (segs[i].kind == GPPD_SEG_BYTES) {
+            if (!segs[i].bytes || segs[i].length < 0) return GPPD_ERR_ARG;
+            copy[i].bytes.assign(reinterpret_cast<const char *>(segs[i].bytes), (size_t)segs[i].length);
+        } else if (segs[i].kind != GPPD_SEG_COPY && segs[i].kind != GPPD_SEG_RECORDS) {
+            g_last_error = "file_write: unknown segment kind";
+            return GPPD_ERR_ARG;
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(f.m);
+        if (f.stage == 0 || f.stage == 3 || f.write_pending) {
+            g_last_error = "file_write: no file waiting to be written on this slot";
+            return GPPD_ERR_ARG;
+        }
+        f.write_pending = true;
+    }
+    const std::string out(out_path);
+    const unsigned char *ex = reinterpret_cast<const unsigned char *>(extra);
+    h->writers.post([h, slot, out, copy, ex, extra_row_bytes] {
+        FileJob &f = h->slots[slot].file;
+        {
+            std::unique_lock<std::mutex> lk(f.m);
+            f.cv.wait(lk, [&f] { return f.stage == 2; });
+            f.stage = 3;
+        }
+        int r = f.rc;       // a failed read / fit: nothing to write
+        std::string e = f.err;
+        if (r == GPPD_OK) {
+            r = file_writer(h, slot, out, copy, ex, extra_row_bytes);
+            if (r) e = g_last_error;
+        }
+        std::lock_guard<std::mutex> lk(f.m);
+        f.rc = r;
+        f.err = e;
+        f.stage = 0;
+        f.write_pending = false;
+        f.cv.notify_all();
+    });
+    return GPPD_OK;
+}
+
+int gppd_file_drain(gppd_handle h) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    int first = GPPD_OK;
+    for (int i = 0; i < NSLOTS; ++i) {
+        FileJob &f = h->slots[i].file;
+        std::unique_lock<std::mutex> lk(f.m);
+        f.cv.wait(lk, [&f] { return !(f.stage == 1 || f.stage == 3 || f.write_pending); });
+        if (f.rc && first == GPPD_OK) {
+            first = f.rc;
+            g_last_error = f.err;
+        }
+        f.rc = GPPD_OK;
+    }
+    return first;
 }
 
 int gppd_wait(gppd_handle h, int slot) {

@@ -57,10 +57,22 @@ constexpr int TC_SEG_ROWS = 6144;             // = HARM_SEG_ROWS (harm_kernels.c
 // night alone would want (12 288 rows: 1 % faster there): a single table then is 17 blocks
 // instead of 9, which is what the table-by-table end-to-end path needs (+6 % there)
 constexpr int TC_KB = 32;                     // rows per K-block = K of one int8 MMA
-constexpr int TC_RS = 8;                      // raw ring stages
-constexpr int TC_OS = 4;                      // operand ring stages
-constexpr int TC_VSETS = 2;                   // V producer sets: set s takes K-blocks s, s + 2, ...
-constexpr int TC_VW = 8 * TC_VSETS, TC_EW = 3; // V / E producer warps (8 V warps per K-block)
+#ifndef TC_RS_N
+#define TC_RS_N 8
+#endif
+#ifndef TC_OS_N
+#define TC_OS_N 4
+#endif
+#ifndef TC_EW_N
+#define TC_EW_N 3
+#endif
+constexpr int TC_RS = TC_RS_N;                // raw ring stages
+constexpr int TC_OS = TC_OS_N;                // operand ring stages
+#ifndef TC_VSETS_N
+#define TC_VSETS_N 2
+#endif
+constexpr int TC_VSETS = TC_VSETS_N;                   // V producer sets: set s takes K-blocks s, s + 2, ...
+constexpr int TC_VW = 8 * TC_VSETS, TC_EW = TC_EW_N; // V / E producer warps (8 V warps per K-block)
 constexpr int TC_MMA_WARP = TC_VW + TC_EW;    // control warp: MMA issuer + TMA loader
 constexpr int TC_WARPS = TC_MMA_WARP + 1;     // 20 warps: 5 per sub-partition at 96 registers
 constexpr int TC_THREADS = TC_WARPS * 32;
@@ -216,6 +228,27 @@ __device__ __forceinline__ void tc_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// TC_PROFILE (experiment builds): cycle counters summed over all blocks, read with
+// gppd_debug_counters: [0] blocks, [1] set-up, [2] main loop (control warp), [3] epilogue,
+// control warp: [4] waiting for operands, [5] issuing MMAs, [6] loading raw rows,
+// V warp 0: [7] waiting raw, [8] waiting operand stage, [9] loop total,
+// E warp 0: [10] waiting raw, [11] waiting operand stage, [12] loop total
+__device__ unsigned long long g_tc_prof[16];
+#ifdef TC_PROFILE
+#define TCP_T(x) const long long x = clock64()
+#define TCP_ADD(i, v) do { if (lane == 0) atomicAdd(&g_tc_prof[i], (unsigned long long)(v)); } while (0)
+#else
+#define TCP_T(x)
+#define TCP_ADD(i, v)
+#endif
+void tc_profile_read(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_tc_prof, z, sizeof z);
+    }
+}
+
 struct TcShared {
     uint64_t raw_full[TC_RS], raw_empty[TC_RS], op_full[TC_OS], op_empty[TC_OS], acc_full;
     double2 stats[16][NGROUP];     // [diode * 4 + state][group]: a quarter warp reads 128 contiguous bytes
@@ -253,7 +286,10 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
         const int i = kb * TC_KB + krow;
         const int st = st_next;
         if (FAINT && i + TC_VSETS * TC_KB < nseg) st_next = stp[(long long)(kb + TC_VSETS) * TC_KB];
+        TCP_T(tv0);
         tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+        TCP_T(tv1);
+        if (warp == 0) TCP_ADD(7, tv1 - tv0);
         const unsigned char *rw = rw0 + rs * TC_RAW_BYTES;
         const uint4 wa = *reinterpret_cast<const uint4 *>(rw);
         const uint4 wb = *reinterpret_cast<const uint4 *>(rw + 16);
@@ -268,7 +304,11 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
         double2 vv[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) vv[d] = make_double2(0.0, 0.0);
+#ifdef TC_SKIP_V
+        const bool valid = false;
+#else
         const bool valid = i < nseg && (!FAINT || row_valid(st, flags));
+#endif
         if (valid) {
             double2 dd[4];
 #pragma unroll
@@ -292,15 +332,22 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
             ovf |= (hi[2 * d] ^ TC_MAGIC_HI) | (hi[2 * d + 1] ^ TC_MAGIC_HI);
         }
         uint32_t dlo[TC_ND], dhi[TC_ND];
+#ifdef TC_SKIP_V
+        for (int j = 0; j < TC_ND; ++j) dlo[j] = dhi[j] = lo[0];
+#else
         {
             const uint32_t l0[4] = {lo[0], lo[1], lo[2], lo[3]}, h0[4] = {hi[0], hi[1], hi[2], hi[3]};
             const uint32_t l1[4] = {lo[4], lo[5], lo[6], lo[7]}, h1[4] = {hi[4], hi[5], hi[6], hi[7]};
             tc_digits4(l0, h0, dlo);
             tc_digits4(l1, h1, dhi);
         }
+#endif
         __syncwarp();                                   // every lane has consumed its raw bytes
         if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
+        TCP_T(tv2);
         tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
+        TCP_T(tv3);
+        if (warp == 0) TCP_ADD(8, tv3 - tv2);
         unsigned char *vt = vt0 + os * TC_OP_BYTES;
 #pragma unroll
         for (int j = 0; j < TC_ND; ++j)
@@ -326,6 +373,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     const JobInfo ji = jobs[job];
     const long long seg0 = (long long)p * TC_SEG_ROWS;
     if (seg0 >= ji.nrows) return;
+    TCP_T(tk0);
     const TableDesc tb = tabs[ji.table];
     const TableView &tv = tb.tv;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -437,36 +485,51 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     for (int q = 0; q < NACC * 4; ++q) cst[q] = 0.0;
     unsigned long long cnt = 0;
 
+    // The raw rows + basis of K-block kb go to ring stage kb % TC_RS (rows of 80 floats, back
+    // to back and 16-byte aligned: the dispatcher sends every other layout to the DMMA kernel).
+    // The control warp loads the first TC_RS K-blocks up front; after that the E producers are
+    // the loaders: the warp that starts K-block kb first loads K-block kb + TC_LEAD, whose
+    // stage the consumers of K-block kb + TC_LEAD - TC_RS = kb - TC_EW (this warp's previous
+    // K-block) released long ago, so the wait never blocks.  (The control warp used to load
+    // too: measured with cycle counters it spent 520 cycles per K-block in the two bulk
+    // copies on top of 420 issuing the MMAs and was the critical path of the whole kernel.)
+    const char *volt = reinterpret_cast<const char *>(tv.volt);
+    auto load = [&](int kb) {
+        const int rs = kb % TC_RS;
+        mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
+        const int rows = min(TC_KB, nseg - kb * TC_KB);
+        const long long row = rbase + (long long)kb * TC_KB;
+        unsigned char *dst = raw_ring + rs * TC_RAW_BYTES;
+        // two lanes, one bulk copy each (issuing one takes a few hundred cycles); the barrier's
+        // pending arrival (lane 0's expect_tx) keeps the phase open whichever copy lands first
+        if (lane == 0) {
+            mbar_expect_tx(&S.raw_full[rs], (unsigned)rows * 336u);
+            bulk_g2s(dst, volt + row * 320, (unsigned)rows * 320u, &S.raw_full[rs]);
+        } else if (lane == 1) {
+            bulk_g2s(dst + TC_RAW_VOLT, tb.basis + row, (unsigned)rows * 16u, &S.raw_full[rs]);
+        }
+        __syncwarp();
+    };
+    constexpr int TC_LEAD = TC_RS - TC_EW;
+    static_assert(TC_LEAD >= 2, "the loads must run ahead of the producers");
+
     if (warp == TC_MMA_WARP) {
-        // ---- control warp: MMA issuer + TMA loader -------------------------------------------
-        // The raw rows + basis of K-block kb go to ring stage kb % TC_RS (rows of 80 floats, back
-        // to back and 16-byte aligned: the dispatcher sends every other layout to the DMMA
-        // kernel).  The first TC_RS K-blocks are loaded up front; K-block k + TC_RS is loaded
-        // right after the MMAs of K-block k have been issued -- every producer of k has then
-        // released the raw stage (it does so before it arrives on the operand barrier), so
-        // the wait below never blocks and the loader cannot starve the producers.
+        // ---- control warp: MMA issuer (and loader of the first TC_RS K-blocks) ------------------
         constexpr uint32_t ID144 = tc_idesc(144), ID192 = tc_idesc(192), ID240 = tc_idesc(240);
         const uint32_t b_op_full = smem_u32(&S.op_full[0]);
         const uint64_t dv0 = tc_desc(smem_u32(op_ring), V_LBO, V_SBO);
         const uint64_t de0 = tc_desc(smem_u32(op_ring) + V_TILE, E_LBO, E_SBO);
-        const char *volt = reinterpret_cast<const char *>(tv.volt);
-        auto load = [&](int kb) {
-            const int rs = kb % TC_RS;
-            mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
-            const int rows = min(TC_KB, nseg - kb * TC_KB);
-            const long long row = rbase + (long long)kb * TC_KB;
-            unsigned char *dst = raw_ring + rs * TC_RAW_BYTES;
-            if (lane == 0) {
-                mbar_expect_tx(&S.raw_full[rs], (unsigned)rows * 336u);
-                bulk_g2s(dst + TC_RAW_VOLT, tb.basis + row, (unsigned)rows * 16u, &S.raw_full[rs]);
-                bulk_g2s(dst, volt + row * 320, (unsigned)rows * 320u, &S.raw_full[rs]);
-            }
-            __syncwarp();
-        };
+
+        TCP_T(tc0);
+        TCP_ADD(0, 1);
+        TCP_ADD(1, tc0 - tk0);
         for (int kb = 0; kb < min(TC_RS, nkb); ++kb) load(kb);
         for (int kb = 0; kb < nkb; ++kb) {
             const int os = kb % TC_OS;
+            TCP_T(tw0);
             tc_wait(b_op_full + 8 * os, (kb / TC_OS) & 1);
+            TCP_T(tw1);
+            TCP_ADD(4, tw1 - tw0);
             tc_fence_after();
             if (tc_elect()) {
                 // descriptors of stage os: the stage's byte offset / 16 added to the address field
@@ -483,17 +546,27 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
                 if (kb == nkb - 1) tc_commit(&S.acc_full);
             }
             __syncwarp();
-            if (kb + TC_RS < nkb) load(kb + TC_RS);
+            TCP_T(tw2);
+            TCP_ADD(5, tw2 - tw1);
         }
+        TCP_T(tc1);
+        TCP_ADD(2, tc1 - tc0);
     } else if (warp >= TC_VW) {
         // ---- E producers: lane = row, K-blocks e, e + TC_EW, ... ------------------------------
         const int e = warp - TC_VW;
         const uint32_t b_raw_full = smem_u32(&S.raw_full[0]), b_raw_empty = smem_u32(&S.raw_empty[0]);
         const uint32_t b_op_full = smem_u32(&S.op_full[0]), b_op_empty = smem_u32(&S.op_empty[0]);
 #pragma unroll 1
+        TCP_T(tel0);
         for (int kb = e; kb < nkb; kb += TC_EW) {
             const int rs = kb % TC_RS, os = kb % TC_OS;
+            TCP_T(tl0);
+            if (kb + TC_LEAD >= TC_RS && kb + TC_LEAD < nkb) load(kb + TC_LEAD);
+            TCP_T(te0);
+            if (e == 0) TCP_ADD(6, te0 - tl0);
             tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+            TCP_T(te1);
+            if (e == 0) TCP_ADD(10, te1 - te0);
             const uint4 bw = *reinterpret_cast<const uint4 *>(raw_ring + rs * TC_RAW_BYTES + TC_RAW_VOLT + lane * 16);
             // basis = (sin theta, cos theta)
             double2 e1 = make_double2(__hiloint2double(bw.w, bw.z), __hiloint2double(bw.y, bw.x));
@@ -510,10 +583,17 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
             const double2 e8 = eh[7];
             __syncwarp();
             if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
+            TCP_T(te2);
             tc_wait(b_op_empty + 8 * os, ((kb / TC_OS) & 1) ^ 1);
+            TCP_T(te3);
+            if (e == 0) TCP_ADD(11, te3 - te2);
             unsigned char *et = op_ring + os * TC_OP_BYTES + V_TILE + (lane >> 3) * E_LBO + (lane & 7) * 16;
+#ifdef TC_SKIP_E
+            for (int a = 0; a < 0; ++a) {
+#else
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
+#endif
                 // harmonics 8 a + 1 .. 8 a + 8: 16 values = one 16-byte atom row per digit
                 uint32_t dg[4][TC_ND];
 #pragma unroll
@@ -543,11 +623,17 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
             __syncwarp();
             if (lane == 0) tc_arrive(b_op_full + 8 * os);
         }
+        TCP_T(tel1);
+        if (e == 0) TCP_ADD(12, tel1 - tel0);
     } else {
+        TCP_T(tvl0);
         if (faint) tc_v_producer<KIND, OFFS, true>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
         else tc_v_producer<KIND, OFFS, false>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
+        TCP_T(tvl1);
+        if (warp == 0) TCP_ADD(9, tvl1 - tvl0);
     }
     __syncthreads();      // every producer is done with the raw ring: it now holds the reductions
+    TCP_T(tep0);
 
     double *s_red = reinterpret_cast<double *>(raw_ring);                          // [TC_VW][NGROUP][20]
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(s_red + TC_VW * NGROUP * 20);
@@ -636,6 +722,8 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     }
     tc_fence_before();
     __syncthreads();
+    TCP_T(tep1);
+    if (warp == 0) TCP_ADD(3, tep1 - tep0);
     if (warp == TC_MMA_WARP)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_TMEM_COLS));
 }

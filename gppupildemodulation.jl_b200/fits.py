@@ -103,8 +103,11 @@ def format_card(key: str, value, comment: str = "") -> str:
 @dataclass
 class HDU:
     cards: list            # raw 80-character cards (without END)
-    data: bytes            # data unit, padded to a multiple of 2880 bytes
+    data: bytes            # data unit, padded to a multiple of 2880 bytes (None: scan_fits)
     header: dict = field(default_factory=dict)
+    hdr_offset: int = -1   # scan_fits: byte offset of the header in the file
+    data_offset: int = -1  # scan_fits: byte offset of the data unit
+    data_padded: int = 0   # scan_fits: bytes of the data unit including its padding
 
     @property
     def name(self):
@@ -211,6 +214,40 @@ def read_fits(path: str) -> list:
     return hdus
 
 
+def scan_fits(path: str) -> list:
+    """The HDUs of a plain (uncompressed) FITS file WITHOUT their data: headers are read,
+    data units are skipped (``hdr_offset`` / ``data_offset`` / ``data_padded`` say where they
+    are).  What the native record path needs (``gppd_file_submit`` reads the records itself)."""
+    hdus = []
+    with open(path, "rb") as fh:
+        fh.seek(0, 2)
+        size = fh.tell()
+        pos = 0
+        while pos + BLOCK <= size:
+            start = pos
+            cards, header, done = [], {}, False
+            while not done:
+                fh.seek(pos)
+                block = fh.read(BLOCK).decode("ascii", "replace")
+                if len(block) < BLOCK:
+                    raise ValueError("truncated FITS header")
+                pos += BLOCK
+                for i in range(0, BLOCK, CARD):
+                    card = block[i:i + CARD]
+                    if card.startswith("END") and card[3:].strip() == "":
+                        done = True
+                        break
+                    cards.append(card)
+                    k, v = parse_card(card)
+                    if k is not None and k not in header:
+                        header[k] = v
+            nbytes = _data_bytes(header)
+            padded = (nbytes + BLOCK - 1) // BLOCK * BLOCK
+            hdus.append(HDU(cards, None, header, hdr_offset=start, data_offset=pos, data_padded=padded))
+            pos += padded
+    return hdus
+
+
 def _header_bytes(cards) -> bytes:
     text = "".join(c.ljust(CARD)[:CARD] for c in cards) + "END".ljust(CARD)
     text += " " * (-len(text) % BLOCK)
@@ -253,15 +290,10 @@ def _set_card(cards, key, value, comment=""):
     cards.append(new)
 
 
-def replace_bintable(hdu: HDU, records: np.ndarray, tform_changes=None, new_columns=(),
-                     new_keys=()) -> HDU:
-    """A copy of BINTABLE ``hdu`` whose records are ``records`` (uint8, rows x bytes).
-
-    tform_changes: {column name: new TFORM} for columns whose width changed in place;
-    new_columns: [(name, TFORM, unit or None)] appended after the existing ones (their
-    bytes are already at the end of ``records``); new_keys: [(keyword, value)] header
-    cards to add or replace (reference: the DEMODULATION keys and PROCSOFT,
-    src/GPPupilDemodulation.jl:174-189,252)."""
+def replace_bintable_cards(hdu: HDU, row_bytes: int, nrows: int, tform_changes=None, new_columns=(),
+                           new_keys=()) -> list:
+    """The header cards of BINTABLE ``hdu`` after its records have been replaced by ``nrows``
+    records of ``row_bytes`` bytes (see replace_bintable)."""
     cards = list(hdu.cards)
     header = dict(hdu.header)
     _, _, cols = bintable_layout(header)
@@ -274,14 +306,33 @@ def replace_bintable(hdu: HDU, records: np.ndarray, tform_changes=None, new_colu
         _set_card(cards, f"TFORM{nf}", tf)
         if unit:
             _set_card(cards, f"TUNIT{nf}", unit)
-    rec = np.ascontiguousarray(records, dtype=np.uint8)
     _set_card(cards, "TFIELDS", nf)
-    _set_card(cards, "NAXIS1", int(rec.shape[1]))
-    _set_card(cards, "NAXIS2", int(rec.shape[0]))
+    _set_card(cards, "NAXIS1", int(row_bytes))
+    _set_card(cards, "NAXIS2", int(nrows))
     for k, v in new_keys:
         _set_card(cards, k, v)
     # keep the mandatory keywords in their mandatory order: only values were edited
     # or cards appended, so the order of the original header is preserved
+    return cards
+
+
+def header_bytes(cards) -> bytes:
+    """The header unit (cards + END, padded to 2880 bytes) as it is stored in a file."""
+    return _header_bytes(cards)
+
+
+def replace_bintable(hdu: HDU, records: np.ndarray, tform_changes=None, new_columns=(),
+                     new_keys=()) -> HDU:
+    """A copy of BINTABLE ``hdu`` whose records are ``records`` (uint8, rows x bytes).
+
+    tform_changes: {column name: new TFORM} for columns whose width changed in place;
+    new_columns: [(name, TFORM, unit or None)] appended after the existing ones (their
+    bytes are already at the end of ``records``); new_keys: [(keyword, value)] header
+    cards to add or replace (reference: the DEMODULATION keys and PROCSOFT,
+    src/GPPupilDemodulation.jl:174-189,252)."""
+    rec = np.ascontiguousarray(records, dtype=np.uint8)
+    cards = replace_bintable_cards(hdu, int(rec.shape[1]), int(rec.shape[0]), tform_changes, new_columns,
+                                   new_keys)
     out = HDU(cards, rec.reshape(-1).data, {})      # a view of the records, not another copy
     for c in cards:
         k, v = parse_card(c)

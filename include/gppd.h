@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GPPD_VERSION 120 /* 0.1.20: + gppd_options.group_mask, gppd_demodulate_f64_dev (0.1.10: gppd_submit_fits_rows,
+#define GPPD_VERSION 121 /* 0.1.21: + gppd_file_* (native ingest); 0.1.20: gppd_options.group_mask, gppd_demodulate_f64_dev (0.1.10: gppd_submit_fits_rows,
                             gppd_centres, gppd_set_split_chains, gppd_debug_harmonics, GPPD_CENTER_EMPIRICAL) */
 
 /* ---- status codes ------------------------------------------------------ */
@@ -40,6 +40,7 @@ extern "C" {
 #define GPPD_ERR_NO_DEVICE 3  /* no usable sm_100 device: there is no CPU fallback */
 #define GPPD_ERR_NOMEM 4
 #define GPPD_ERR_UNSUPPORTED 5
+#define GPPD_ERR_IO 6          /* file could not be read / written; see gppd_last_error() */
 
 /* ---- option flags ------------------------------------------------------ */
 #define GPPD_ONLYHIGH 1u    /* demodulateall(onlyhigh=true)   src/Modulation.jl:348 */
@@ -217,6 +218,54 @@ int gppd_submit_fits_rows(gppd_handle h, int slot, int64_t n, const void *rows,
                           double *chi2, int32_t *info, int8_t *state_out);
 
 /*
+ * ---- native file ingest / egress, src/FitsUtils.jl:31-37,95-156 ----------------------
+ * The record path without the host language touching a byte of the table: the library
+ * reads the n METROLOGY records of a (plain, uncompressed) FITS file straight into the
+ * slot's pinned staging buffer on its own reader threads -- chunk by chunk, each chunk
+ * uploaded while the next one is being read --, runs the batch of gppd_submit_fits_rows
+ * on them, brings the output records back into pinned memory, and its writer threads
+ * assemble the output file (FITScopy!: every other HDU copied, the METROLOGY table and
+ * its header replaced).  The host language keeps what is cheap and its own: header
+ * parsing / gating (src/GPPupilDemodulation.jl:358-392) and the text of the new header.
+ *
+ *   gppd_file_submit   returns at once; the job runs on the handle's I/O threads.  It
+ *                      first waits for the slot's previous file to be written.
+ *   gppd_file_wait     blocks until the fit results are there and copies them out
+ *                      (params [nwin x 32 x 6], chi2 [nwin x 32], info / state may be NULL).
+ *   gppd_file_write    returns at once; a writer thread writes the segments in order:
+ *                        GPPD_SEG_COPY     `length` bytes of the INPUT file from `offset`
+ *                        GPPD_SEG_BYTES    `length` bytes from `bytes` (copied at call time)
+ *                        GPPD_SEG_RECORDS  the n output records (each followed by its
+ *                                          `extra_row_bytes` bytes of `extra`, if any: the
+ *                                          per-row columns of window mode, :239-249), then
+ *                                          zero padding to a multiple of 2880 bytes
+ *                      `extra` must stay valid until the slot's next gppd_file_submit or
+ *                      gppd_file_drain returns.
+ *   gppd_file_drain    waits for every pending job of the handle; returns the first error.
+ * Errors of the asynchronous parts are reported by the next wait / drain on the slot.
+ */
+#define GPPD_SEG_COPY 0
+#define GPPD_SEG_BYTES 1
+#define GPPD_SEG_RECORDS 2
+typedef struct gppd_file_segment {
+    int32_t kind;       /* GPPD_SEG_* */
+    int32_t reserved;
+    int64_t offset;     /* GPPD_SEG_COPY: byte offset in the input file */
+    int64_t length;     /* GPPD_SEG_COPY / GPPD_SEG_BYTES */
+    const void *bytes;  /* GPPD_SEG_BYTES */
+} gppd_file_segment;
+
+int gppd_file_submit(gppd_handle h, int slot, const char *path, int64_t data_offset, int64_t n,
+                     int64_t row_bytes, int64_t time_off, int64_t volt_off, double mjd,
+                     const double *offsets, const double *timer1, int64_t n1,
+                     const double *timer2, int64_t n2, double window_s, const gppd_options *opt);
+int gppd_file_wait(gppd_handle h, int slot, double *params, double *chi2, int32_t *info,
+                   int8_t *state_out);
+int gppd_file_write(gppd_handle h, int slot, const char *out_path, const gppd_file_segment *segs,
+                    int32_t nsegs, const void *extra, int64_t extra_row_bytes);
+int gppd_file_drain(gppd_handle h);
+
+/*
  * Device-resident variant (all pointers are device pointers on the handle's
  * GPU; `stream` is a cudaStream_t passed as void*, NULL = the slot's own
  * stream).  No host<->device copies, no synchronisation: the caller orders
@@ -265,6 +314,10 @@ int gppd_centres(gppd_handle h, int slot, int64_t ntables, double *centres);
  * two implementations of the sums (FP64 DMMA, int8 tensor cores) against each other.
  */
 int gppd_debug_harmonics(gppd_handle h, int slot, double *htab, int64_t nvals);
+
+/* Experiment hook: 16 cycle counters of the tensor-core harmonic kernel, non-zero only in
+ * builds with -DTC_PROFILE (csrc/harm_tc_kernels.cu says what each one is). */
+int gppd_debug_counters(gppd_handle h, uint64_t *out16, int reset);
 
 /*
  * Batches that hold both FAINT and bright tables run as two concurrent launch sequences
