@@ -298,17 +298,20 @@ class NightScheduler:
         files, the GPU works on up to `nslots` files, writer threads assemble and write the
         finished ones; returns the output names in input order."""
         from concurrent.futures import ThreadPoolExecutor
-        done, slot = [], 0
+        # Slot k is in one of two halves of the ring: up to `depth` files are on the GPU (read,
+        # uploaded, fitted, downloaded) while the `depth` files before them are being written.
+        # A slot is only re-submitted `depth` files after its write was requested, so that
+        # gppd_file_submit (which waits for the slot's previous output file) does not stall.
+        done, depth = [], max(1, self.nslots // 2)
         with ThreadPoolExecutor(max_workers=3) as self.writers:
+            i = 0
             for job in jobs:
-                if self.busy[slot] is not None:
-                    done.append(self.finish(slot))
-                self.submit(slot, job)
-                slot = (slot + 1) % self.nslots
-            for k in range(self.nslots):
-                s = (slot + k) % self.nslots
-                if self.busy[s] is not None:
-                    done.append(self.finish(s))
+                if i >= depth:
+                    done.append(self.finish((i - depth) % self.nslots))
+                self.submit(i % self.nslots, job)
+                i += 1
+            for k in range(max(0, i - depth), i):
+                done.append(self.finish(k % self.nslots))
             names = [f if isinstance(f, str) else f.result() for f in done]
         _lib.check(self.L.gppd_file_drain(self.h.raw))      # the library's writer threads are done
         self.keep = [None] * self.nslots

@@ -297,20 +297,34 @@ def replace_bintable_cards(hdu: HDU, row_bytes: int, nrows: int, tform_changes=N
     cards = list(hdu.cards)
     header = dict(hdu.header)
     _, _, cols = bintable_layout(header)
+    index = {}                      # keyword -> position of its (first) card: one parse per card
+    for i, c in enumerate(cards):
+        k = parse_card(c)[0]
+        if k is not None and k not in index:
+            index[k] = i
+
+    def put(key, value):
+        new = format_card(key, value)
+        if key in index:
+            cards[index[key]] = new
+        else:
+            index[key] = len(cards)
+            cards.append(new)
+
     for name, tf in (tform_changes or {}).items():
-        _set_card(cards, f"TFORM{cols[name][2]}", tf)
+        put(f"TFORM{cols[name][2]}", tf)
     nf = int(header["TFIELDS"])
     for name, tf, unit in new_columns:
         nf += 1
-        _set_card(cards, f"TTYPE{nf}", name)
-        _set_card(cards, f"TFORM{nf}", tf)
+        put(f"TTYPE{nf}", name)
+        put(f"TFORM{nf}", tf)
         if unit:
-            _set_card(cards, f"TUNIT{nf}", unit)
-    _set_card(cards, "TFIELDS", nf)
-    _set_card(cards, "NAXIS1", int(row_bytes))
-    _set_card(cards, "NAXIS2", int(nrows))
+            put(f"TUNIT{nf}", unit)
+    put("TFIELDS", nf)
+    put("NAXIS1", int(row_bytes))
+    put("NAXIS2", int(nrows))
     for k, v in new_keys:
-        _set_card(cards, k, v)
+        put(k, v)
     # keep the mandatory keywords in their mandatory order: only values were edited
     # or cards appended, so the order of the original header is preserved
     return cards
