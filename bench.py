@@ -83,6 +83,8 @@ class ClockSampler:
         self.nv = None
 
     def start(self):
+        if self.index is None:       # ranks other than 0 do not poll (the line reports rank 0's clocks;
+            return                   # eight processes polling NVML every 2 ms contend in the driver)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -357,7 +359,7 @@ def main():
     h.enable_timing(True)
     h.pass_times(reset=True)
     launches0 = h.launches
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if rank == 0 else None)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(bench_stream)
@@ -653,7 +655,7 @@ def stress_config(args, rank, world, local):
     n = int(args.stress_rows)
     free_b, total_b = torch.cuda.mem_get_info(dev)
     stream = torch.cuda.Stream(device=dev)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if rank == 0 else None)
     clocks.start()
     p = lambda x: C.c_void_p(x.data_ptr())
     launches0 = h.launches
@@ -814,7 +816,7 @@ def sweep_config(args, rank, world, local):
     fp64_peak = h.fp64_peak_tflops()
     T, NW = SWEEP_CHUNK_TABLES, SWEEP_TAB_WIN
     N = NW * SWEEP_W
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if rank == 0 else None)
     clocks.start()
     launches0 = h.launches
     stream = torch.cuda.Stream(device=dev)

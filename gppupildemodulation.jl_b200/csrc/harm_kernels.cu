@@ -434,7 +434,56 @@ __global__ void k_harm_reduce(const JobInfo *jobs, const double *partZ, const do
     htab[(long long)v * nfits + fit] = s;
 }
 
+// The same for very long jobs (more than HARM_LONG segments = 393 216 rows: the 1e8-row
+// exposure of BASELINE config 4 has 16 277): one WARP per (value, fit) instead of one thread,
+// which would walk the segments one dependent load after the other (measured: 2.5 ms of the
+// 1e8-row global fit).  Lane l adds the chunks l, l + 32, ... of HARM_LONG consecutive segments
+// each in index order, the lanes' sums are then added in lane order: a fixed order that depends
+// on the job's length only, so the result is deterministic and independent of the batch.
+constexpr int HARM_LONG = 64;
+__global__ void k_harm_reduce_long(const JobInfo *jobs, const double *partZ, const double *partY, int P,
+                                   int nfits, double *htab) {
+    const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nvals = partY ? HV_COUNT : HV_Y0R;
+    if (idx >= (long long)nfits * nvals) return;
+    const int v = (int)(idx / nfits), fit = (int)(idx % nfits);
+    const int job = fit / NDIODE, ch = fit % NDIODE;
+    const int jg = job * NGROUP + ch / 4, d = ch & 3;
+    const int nseg = harm_segments(jobs[job].nrows);
+    const bool zs = v < HV_Y0R;
+    const double *base = zs ? partZ + (((long long)jg * P) * 4 + d) * HP_Z + v
+                            : partY + (((long long)jg * P) * 4 + d) * HP_Y + (v - HV_Y0R);
+    const long long stride = zs ? 4ll * HP_Z : 4ll * HP_Y;
+    double s = 0.0;
+    for (int c0 = lane * HARM_LONG; c0 < nseg; c0 += 32 * HARM_LONG) {
+        const int c1 = c0 + HARM_LONG < nseg ? c0 + HARM_LONG : nseg;
+        double cs = 0.0;
+        for (int p = c0; p < c1; ++p) cs += base[(long long)p * stride];
+        s += cs;
+    }
+    double tot = 0.0;
+    for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, s, l);     // lane order
+    if (lane == 0) htab[(long long)v * nfits + fit] = tot;
+}
+
 int harm_max_segments(long long max_rows_per_job) { return harm_segments(max_rows_per_job); }
+
+// P = segments of the longest job of the batch.  A batch that holds a job of more than
+// HARM_LONG segments uses the warp-per-value kernel for all its jobs; for a job of up to
+// HARM_LONG segments (every real table) the two kernels add the same numbers in the same
+// order (one chunk on lane 0, the other lanes contribute +0.0), so a job's sums still do not
+// depend on the batch it is in.
+static void launch_harm_reduce(const Launcher &L, const JobInfo *d_jobs, const double *d_partZ,
+                               const double *d_partY, int P, int nfits, long long tot, double *d_htab) {
+    if (P > HARM_LONG)
+        k_harm_reduce_long<<<(unsigned)((tot * 32 + 255) / 256), 256, 0, L.stream>>>(d_jobs, d_partZ, d_partY, P,
+                                                                                    nfits, d_htab);
+    else
+        k_harm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(d_jobs, d_partZ, d_partY, P, nfits,
+                                                                           d_htab);
+    *L.counter += 1;
+}
 
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
@@ -445,9 +494,7 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
     const long long tot = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
     if (tensor) {
         launch_harmonics_tc(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
-        k_harm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
-            d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, d_htab);
-        *L.counter += 1;
+        launch_harm_reduce(L, d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, tot, d_htab);
         return;
     }
     cudaFuncSetAttribute(k_harm_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
@@ -462,9 +509,7 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
         k_harm_ws<0, false><<<grid, WS_THREADS, WS_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
         *L.counter += 1;
     }
-    k_harm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, L.stream>>>(
-        d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, d_htab);
-    *L.counter += 1;
+    launch_harm_reduce(L, d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, tot, d_htab);
 }
 
 }  // namespace gppd
