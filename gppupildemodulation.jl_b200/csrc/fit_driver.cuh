@@ -60,11 +60,12 @@ struct FitDriverT {
         phi = phi0;
     }
 
-    // f = chi2 at the (b, phi) handed out by the previous call.
-    // Returns true while another evaluation (at this->b, this->phi) is needed.
-    __device__ bool step(const FitOptions &o, double f) {
+    // f = chi2 at the (b, phi) handed out by the previous call.  The part of a step before
+    // the solver: returns 0 = the fit is finished, 1 = evaluate at (this->b, this->phi),
+    // 2 = the solver has to digest f first (after_solver() then finishes the step).
+    __device__ int before_solver(const FitOptions &o, double f, int &next_phase) {
         ++nfev;
-        int next_phase = DONE;
+        next_phase = DONE;
         switch (phase) {
         case SCAN:
             // argmin over the scan; Julia's argmin returns the first NaN
@@ -80,49 +81,45 @@ struct FitDriverT {
             ++k;
             if (k < 8) {
                 phi = o.phi8[k];
-                return true;
+                return 1;
             }
             x1 = 0.1;
             x2 = o.phi8[kbest];
             begin_solver(NEWUOA1, x1, x2);
-            return true;
+            return 1;
         case NEWUOA1:
             next_phase = LKL_X;
-            break;
+            return 2;
         case NEWUOA2:
             next_phase = FINAL;
-            break;
+            return 2;
         case LKL_X:
             lklval = f;
             phipi = x2 + (x2 < 0 ? PI_F64 : -PI_F64);
             phase = LKL_FLIP;
             b = x1;
             phi = phipi;
-            return true;
+            return 1;
         case LKL_FLIP:
             if (lklval > f) {  // "bad minima", strict >
                 second = 1;
                 begin_solver(NEWUOA2, x1, phipi);
-                return true;
+                return 1;
             }
             phase = FINAL;
             b = x1;
             phi = x2;
-            return true;
+            return 1;
         case FINAL:
             chi2 = f;
             phase = DONE;
-            return false;
+            return 0;
         default:
-            return false;
+            return 0;
         }
-        // ---- the one call site of the solver (phase NEWUOA1 / NEWUOA2) ----
-        // A solver that has not run yet first sets itself up and asks for its start
-        // point, which is the point f was just evaluated at: feed f straight back.
-        bool more = true;
-        const int calls = nu.phase == 0 ? 2 : 1;
-#pragma unroll 1
-        for (int c = 0; c < calls; ++c) more = nu.step(f);
+    }
+
+    __device__ void after_solver(bool more, int next_phase) {
         if (more) {
             b = nu.x[1];
             phi = nu.x[2];
@@ -134,8 +131,45 @@ struct FitDriverT {
             b = x1;
             phi = x2;
         }
+    }
+
+    // Returns true while another evaluation (at this->b, this->phi) is needed.
+    __device__ bool step(const FitOptions &o, double f) {
+        int next_phase;
+        const int r = before_solver(o, f, next_phase);
+        if (r != 2) return r == 1;
+        // ---- the one call site of the solver (phase NEWUOA1 / NEWUOA2) ----
+        // A solver that has not run yet first sets itself up and asks for its start
+        // point, which is the point f was just evaluated at: feed f straight back.
+        bool more = true;
+        const int calls = nu.phase == 0 ? 2 : 1;
+#pragma unroll 1
+        for (int c = 0; c < calls; ++c) more = nu.step(f);
+        after_solver(more, next_phase);
         return true;
     }
+
+#ifdef __CUDACC__
+    // The same step for kernels in which every lane of a warp owns a fit: ALL 32 lanes call it
+    // together (`active` = this lane has a value f for its fit), and the solvers of the warp
+    // are advanced segment by segment (Newuoa2T::step_coop), lanes at the same segment
+    // together.  A lane's arithmetic is exactly that of step().
+    __device__ bool step_coop(const FitOptions &o, double f, bool active) {
+        int next_phase = DONE;
+        const int r = active ? before_solver(o, f, next_phase) : 0;
+        const int calls = r == 2 ? (nu.phase == 0 ? 2 : 1) : 0;
+        bool more = true;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            if (!__any_sync(0xffffffffu, c < calls)) break;          // warp-uniform
+            const bool m = nu.step_coop(f, !(c < calls));
+            if (c < calls) more = m;
+        }
+        if (r != 2) return r == 1;
+        after_solver(more, next_phase);
+        return true;
+    }
+#endif
 };
 
 typedef FitDriverT<false> FitDriver;

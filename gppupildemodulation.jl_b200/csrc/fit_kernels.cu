@@ -206,8 +206,11 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
     q_powers(cq, sq, P);
     // pairwise summation in the order of the warp kernel's butterfly (xor 1, 2, 4, 8, 16):
     // lanes stream in, a 6-level carry stack merges equal-sized partial sums
+    // (fully unrolled: `lane` is a compile-time constant in every copy, so the powers of
+    // e^{jq} it needs, its slot of J[] and its place in the carry stack are all resolved by
+    // the compiler and everything stays in registers)
     double st[6][4];
-#pragma unroll 1
+#pragma unroll
     for (int lane = 0; lane < 32; ++lane) {
         double v[4] = {0.0, 0.0, 0.0, 0.0};     // the warp kernel's idle lanes contribute +0.0
         if (lane <= HK) {
@@ -216,6 +219,7 @@ __device__ __forceinline__ bool eval_harmonic(const double *H, int nfits, const 
             lane_terms<OFFS>(lane, J[lane], P, h, v[0], v[1], v[2], v[3]);
         }
         int lvl = 0;
+#pragma unroll
         for (int idx = lane; idx & 1; idx >>= 1, ++lvl) {
 #pragma unroll
             for (int c = 0; c < (OFFS ? 4 : 2); ++c) v[c] = st[lvl][c] + v[c];
@@ -338,8 +342,11 @@ k_fit_harmonic_warp(const TableDesc *tabs, const JobInfo *jobs, const double *ht
 }
 
 // ---- one thread per fit ---------------------------------------------------------
+#ifndef FITT_MINB
+#define FITT_MINB 1
+#endif
 template <bool OFFS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, FITT_MINB)
 k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, int nfits,
                FitOptions opt, FitResult *results, double *trace, int *fbq) {
     __shared__ NuSinCos s_ang[NU_ANGLES + 1];
@@ -372,8 +379,13 @@ k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, i
     double cre = 0, cim = 0, are = 0, aim = 0, f = 0;
     double *tr = (trace && live) ? trace + (long long)fit * (3 * 160) : nullptr;
     bool running = live, failed = false;
-    // lock-step loop: every fit of the warp evaluates, then advances its solver
+    // lock-step loop: every fit of the warp evaluates, then the warp advances its solvers
+    // together, segment by segment (FitDriverT::step_coop: lanes whose solvers are at the same
+    // place of the algorithm run it in one pass instead of one after the other -- measured
+    // on 1e6 fits of 512 rows: the solver part of this kernel was 73 % of its instructions
+    // with a third of the lanes active)
     while (__any_sync(0xffffffffu, running)) {
+        bool feed = false;
         if (running) {
             const double b = drv.b, phi = drv.phi;
             if (!eval_harmonic<OFFS>(H, nfits, kc, ji, b, phi, f, cre, cim, are, aim)) {
@@ -385,9 +397,11 @@ k_fit_harmonic(const TableDesc *tabs, const JobInfo *jobs, const double *htab, i
                     tr[3 * drv.nfev + 1] = phi;
                     tr[3 * drv.nfev + 2] = f;
                 }
-                running = drv.step(opt, f);
+                feed = true;
             }
         }
+        const bool more = drv.step_coop(opt, f, feed);
+        if (feed) running = more;
     }
     if (!live) return;
     if (failed) {

@@ -79,18 +79,18 @@ __device__ __forceinline__ double bessel_tiny(double b, int k) {
 
 __device__ __forceinline__ void bessel_j(double b, double *J) {
     if (fabs(b) < BESSEL_TINY) {
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k <= HK; ++k) J[k] = bessel_tiny(b, k);
         return;
     }
     const double tb = 2.0 / b;
     double jp = 0.0, jc = 1.0e-280, seven = 0.0, kd = (double)BESSEL_M;
 #define GPPD_STORE(kk, v) if ((kk) <= HK) J[kk] = (v)
-#pragma unroll 1
+#pragma unroll
     for (int k = BESSEL_M; k >= 2; k -= 2) GPPD_BESSEL_STEP2(k, kd, tb, jp, jc, seven, GPPD_STORE, GPPD_STORE)
 #undef GPPD_STORE
     const double inv = 1.0 / (jc + 2.0 * seven);   // jc = J_0
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k <= HK; ++k) J[k] *= inv;
 }
 

@@ -916,18 +916,67 @@ struct Newuoa2T {
     // Advance the solver.  On the first call `fin` is ignored; afterwards it
     // is the objective value at the point x[] returned by the previous call.
     // Returns true when x[] must be evaluated, false when finished.
-    __host__ __device__ bool step(double fin) {
-        const double half = 0.5, one = 1.0, tenth = 0.1, zero = 0.0;
-        double temp, tempq, sum, sumz, suma, sumb, bsum, dx, vquad, diff, fsave;
-        double detrat, hdiag, distsq, gqsq, gisq;
-        int ih, ip, itemp, ksave, ktemp;
+    // ------------------------------------------------------------------
+    // NEWUOB as a resumable machine of SEGMENTS (Powell's labelled blocks: 50, 70, 90/100,
+    // 120, 290, 310, after CALFUN, 410, 460, 490, 530).  advance() runs the segment `pc`
+    // points at and sets pc to the next one; step() runs segments until the solver wants an
+    // objective value (true) or has finished (false).  The arithmetic and its order are those
+    // of the straight-line version; the segmentation only exists so that the threads of a warp
+    // which each own a solver (thread-per-fit kernel) can be scheduled segment by segment
+    // (step_coop): all lanes that are at the same segment run it together, instead of every
+    // lane dragging the others through its own path from the first divergent branch on.
+    // Segment numbers grow along the usual flow of one iteration (after CALFUN -> 410 -> 460 ->
+    // 490 -> 90/100 -> 120 -> 290 -> 310): scheduling the smallest pc first lets the lanes that
+    // take a detour catch up with the others before the expensive common segments.
+    enum {
+        PC_INIT = 0, PC_L50, PC_L70, PC_AFTER, PC_L410, PC_L460, PC_L490, PC_L90, PC_L100, PC_L120,
+        PC_L290, PC_L310, PC_L530, PC_YIELD /* objective value wanted */, PC_DONE, PC_IDLE
+    };
+    int pc;
+    // values that live from the segment after CALFUN into 410 / 460
+    double s_diff, s_fsave, s_vquad;
+    int s_ksave;
 
-        if (phase == 2) return false;
-        if (phase == 1) {
+    __host__ __device__ void enter(double fin) {
+        if (phase == 2) {
+            pc = PC_DONE;
+        } else if (phase == 1) {
             fcur = fin;
-            goto AFTER_CALFUN;
+            pc = PC_AFTER;
+        } else {
+            pc = PC_INIT;
         }
+    }
 
+    __host__ __device__ bool step(double fin) {
+        enter(fin);
+        while (pc < PC_YIELD) advance();
+        return pc == PC_YIELD;
+    }
+
+#ifdef __CUDACC__
+    // All 32 lanes of a warp call this together, each with its own solver; a lane without
+    // work passes idle = true.  Returns like step().
+    __device__ bool step_coop(double fin, bool idle) {
+        if (idle) pc = PC_IDLE;
+        else enter(fin);
+        for (;;) {
+            const int cur = __reduce_min_sync(0xffffffffu, pc);
+            if (cur >= PC_YIELD) break;
+            if (pc == cur) advance();
+        }
+        return pc == PC_YIELD;
+    }
+#endif
+
+    __host__ __device__ void advance() {
+        const double half = 0.5, one = 1.0, tenth = 0.1, zero = 0.0;
+        double temp, sum, suma, sumb, bsum, dx;
+        double detrat, hdiag, distsq, gqsq, gisq;
+        int ih, itemp, ktemp;
+
+        switch (pc) {
+        case PC_INIT:
         // ---- set-up (first call) ----
         for (int j = 1; j <= N; ++j) xbase[j] = x[j];
         for (int i = 0; i < NPT * N; ++i) xpt_[i] = zero;
@@ -956,7 +1005,12 @@ struct Newuoa2T {
         fbeg = fopt = fcur = zero;
         rho = delta = diffa = diffb = diffc = xoptsq = dsq = dnorm = zero;
         ratio = crvmin = beta = alpha = dstep = zero;
-    L50:
+        s_diff = s_fsave = s_vquad = zero;
+        s_ksave = 0;
+        pc = PC_L50;
+        return;
+
+        case PC_L50:
         nfm = nf;
         nfmm = nf - N;
         ++nf;
@@ -983,8 +1037,10 @@ struct Newuoa2T {
             XPT(nf, jpt) = xjpt;
         }
         for (int j = 1; j <= N; ++j) x[j] = XPT(nf, j) + xbase[j];
-        goto L310;
-    L70:
+        pc = PC_L310;
+        return;
+
+        case PC_L70:
         fval[nf] = fcur;
         if (nf == 1) {
             fbeg = fcur;
@@ -1023,7 +1079,10 @@ struct Newuoa2T {
             ZMAT(jpt + 1, nfmm) = -recip;
             hq[ih] = (fbeg - fval[ipt + 1] - fval[jpt + 1] + fcur) / (xipt * xjpt);
         }
-        if (nf < NPT) goto L50;
+        if (nf < NPT) {
+            pc = PC_L50;
+            return;
+        }
 
         rho = rhobeg;
         delta = rho;
@@ -1036,9 +1095,15 @@ struct Newuoa2T {
             xopt[i] = XPT(kopt, i);
             xoptsq += xopt[i] * xopt[i];
         }
-    L90:
+        pc = PC_L90;
+        return;
+
+        case PC_L90:
         nfsav = nf;
-    L100:
+        pc = PC_L100;
+        return;
+
+        case PC_L100:
         knew = 0;
         trsapp(d);
         dsq = zero;
@@ -1049,12 +1114,22 @@ struct Newuoa2T {
             delta = tenth * delta;
             ratio = -1.0;
             if (delta <= 1.5 * rho) delta = rho;
-            if (nf <= nfsav + 2) goto L460;
+            if (nf <= nfsav + 2) {
+                pc = PC_L460;
+                return;
+            }
             temp = 0.125 * crvmin * rho * rho;
-            if (temp <= dmax(diffa, dmax(diffb, diffc))) goto L460;
-            goto L490;
+            if (temp <= dmax(diffa, dmax(diffb, diffc))) {
+                pc = PC_L460;
+                return;
+            }
+            pc = PC_L490;
+            return;
         }
-    L120:
+        pc = PC_L120;
+        return;
+
+        case PC_L120:
         if (dsq <= 1.0e-3 * xoptsq) shift_xbase();
         if (knew > 0) biglag(dstep);
 
@@ -1100,42 +1175,57 @@ struct Newuoa2T {
             temp = one + alpha * beta / (vlag[knew] * vlag[knew]);
             if (fabs(temp) <= 0.8) bigden();
         }
-    L290:
+        pc = PC_L290;
+        return;
+
+        case PC_L290:
         for (int i = 1; i <= N; ++i) {
             xnew[i] = xopt[i] + d[i];
             x[i] = xbase[i] + xnew[i];
         }
         ++nf;
-    L310:
+        pc = PC_L310;
+        return;
+
+        case PC_L310:
         if (nf > nftest) {
             --nf;
             status = NU_TOO_MANY_EVALUATIONS;
-            goto L530;
+            pc = PC_L530;
+            return;
         }
         phase = 1;
-        return true;  // ---- objective call ----
-    AFTER_CALFUN:
-        if (nf <= NPT) goto L70;
-        if (knew == -1) goto L530;
+        pc = PC_YIELD;  // ---- objective call ----
+        return;
 
-        vquad = zero;
+        case PC_AFTER:
+        if (nf <= NPT) {
+            pc = PC_L70;
+            return;
+        }
+        if (knew == -1) {
+            pc = PC_L530;
+            return;
+        }
+
+        s_vquad = zero;
         ih = 0;
         for (int j = 1; j <= N; ++j) {
-            vquad += d[j] * gq[j];
+            s_vquad += d[j] * gq[j];
             for (int i = 1; i <= j; ++i) {
                 ++ih;
                 temp = d[i] * xnew[j] + d[j] * xopt[i];
                 if (i == j) temp = half * temp;
-                vquad += temp * hq[ih];
+                s_vquad += temp * hq[ih];
             }
         }
-        NU_ROLLED for (int k = 1; k <= NPT; ++k) vquad += pq[k] * w[k];
-        diff = fcur - fopt - vquad;
+        NU_ROLLED for (int k = 1; k <= NPT; ++k) s_vquad += pq[k] * w[k];
+        s_diff = fcur - fopt - s_vquad;
         diffc = diffb;
         diffb = diffa;
-        diffa = fabs(diff);
+        diffa = fabs(s_diff);
         if (dnorm > rho) nfsav = nf;
-        fsave = fopt;
+        s_fsave = fopt;
         if (fcur < fopt) {
             fopt = fcur;
             xoptsq = zero;
@@ -1144,13 +1234,17 @@ struct Newuoa2T {
                 xoptsq += xopt[i] * xopt[i];
             }
         }
-        ksave = knew;
-        if (knew > 0) goto L410;
-        if (vquad >= zero) {
-            status = NU_ROUNDING_ERRORS;
-            goto L530;
+        s_ksave = knew;
+        if (knew > 0) {
+            pc = PC_L410;
+            return;
         }
-        ratio = (fcur - fsave) / vquad;
+        if (s_vquad >= zero) {
+            status = NU_ROUNDING_ERRORS;
+            pc = PC_L530;
+            return;
+        }
+        ratio = (fcur - s_fsave) / s_vquad;
         if (ratio <= tenth) {
             delta = half * dnorm;
         } else if (ratio <= 0.7) {
@@ -1163,7 +1257,7 @@ struct Newuoa2T {
         rhosq = rhosq * rhosq;
         ktemp = 0;
         detrat = zero;
-        if (fcur >= fsave) {
+        if (fcur >= s_fsave) {
             ktemp = kopt;
             detrat = one;
         }
@@ -1189,8 +1283,10 @@ struct Newuoa2T {
                 knew = k;
             }
         }
-        if (knew == 0) goto L460;
-    L410:
+        pc = knew == 0 ? PC_L460 : PC_L410;
+        return;
+
+        case PC_L410:
         update();
         fval[knew] = fcur;
         ih = 0;
@@ -1203,17 +1299,17 @@ struct Newuoa2T {
         }
         pq[knew] = zero;
         for (int j = 1; j <= NPTM; ++j) {
-            temp = diff * ZMAT(knew, j);
+            temp = s_diff * ZMAT(knew, j);
             if (j < idz) temp = -temp;
             NU_ROLLED for (int k = 1; k <= NPT; ++k) pq[k] += temp * ZMAT(k, j);
         }
         gqsq = zero;
         for (int i = 1; i <= N; ++i) {
-            gq[i] += diff * BMAT(knew, i);
+            gq[i] += s_diff * BMAT(knew, i);
             gqsq += gq[i] * gq[i];
             XPT(knew, i) = xnew[i];
         }
-        if (ksave == 0 && delta == rho) {
+        if (s_ksave == 0 && delta == rho) {
             if (fabs(ratio) > 1.0e-2) {
                 itest = 0;
             } else {
@@ -1243,11 +1339,20 @@ struct Newuoa2T {
                 }
             }
         }
-        if (fcur < fsave) kopt = knew;
-        if (fcur <= fsave + tenth * vquad) goto L100;
-        if (ksave > 0) goto L100;
+        if (fcur < s_fsave) kopt = knew;
+        if (fcur <= s_fsave + tenth * s_vquad) {
+            pc = PC_L100;
+            return;
+        }
+        if (s_ksave > 0) {
+            pc = PC_L100;
+            return;
+        }
         knew = 0;
-    L460:
+        pc = PC_L460;
+        return;
+
+        case PC_L460:
         distsq = 4.0 * delta * delta;
         NU_ROLLED for (int k = 1; k <= NPT; ++k) {
             sum = zero;
@@ -1263,11 +1368,21 @@ struct Newuoa2T {
         if (knew > 0) {
             dstep = dmax(dmin(tenth * sqrt(distsq), half * delta), rho);
             dsq = dstep * dstep;
-            goto L120;
+            pc = PC_L120;
+            return;
         }
-        if (ratio > zero) goto L100;
-        if (dmax(delta, dnorm) > rho) goto L100;
-    L490:
+        if (ratio > zero) {
+            pc = PC_L100;
+            return;
+        }
+        if (dmax(delta, dnorm) > rho) {
+            pc = PC_L100;
+            return;
+        }
+        pc = PC_L490;
+        return;
+
+        case PC_L490:
         if (rho > rhoend) {
             delta = half * rho;
             ratio = rho / rhoend;
@@ -1279,17 +1394,25 @@ struct Newuoa2T {
                 rho = tenth * rho;
             }
             delta = dmax(delta, rho);
-            goto L90;
+            pc = PC_L90;
+            return;
         }
-        if (knew == -1) goto L290;
-    L530:
+        pc = knew == -1 ? PC_L290 : PC_L530;
+        return;
+
+        case PC_L530:
         if (fopt <= fcur) {
             for (int i = 1; i <= N; ++i) x[i] = xbase[i] + xopt[i];
             fcur = fopt;
         }
         f = fcur;
         phase = 2;
-        return false;
+        pc = PC_DONE;
+        return;
+
+        default:
+            return;
+        }
     }
 
 #undef XPT
