@@ -96,6 +96,9 @@ static_assert(TC_SEG_ROWS * 3ll * 16384 < (1ll << 31), "int32 accumulators");
 // 2^52 + 2^51 + 0x808080808080: ulp 1, bytes 0..5 of (v + this) are the digits + 128
 #define TC_MAGIC 6896688841130112.0
 constexpr uint32_t TC_MAGIC_HI = 0x43388080u;  // high word of TC_MAGIC
+// the double constants of the producers' inner loops, read from constant memory: as literals
+// each use costs two uniform-register moves (the V loop carried 80 of them)
+__constant__ double c_tc[4] = {TC_MAGIC, 1.0e-280, 1.0e280, 70368744177664.0 /* 2^46 */};
 
 
 __device__ __forceinline__ bool tc_elect() {
@@ -161,7 +164,7 @@ __device__ __forceinline__ double2 tc_csqr(double2 a) {
 }
 __device__ __forceinline__ double2 tc_fc_unit(double x, double y) {
     const double h2 = fma(x, x, y * y);
-    if (h2 > 1.0e-280 && h2 < 1.0e280) {
+    if (h2 > c_tc[1] && h2 < c_tc[2]) {
         const double inv = rsqrt(h2);
         return make_double2(x * inv, y * inv);
     }
@@ -324,7 +327,7 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
         uint32_t lo[8], hi[8];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            const double tx = fma(vv[d].x, sc[d * NGROUP], TC_MAGIC), ty = fma(vv[d].y, sc[d * NGROUP], TC_MAGIC);
+            const double tx = fma(vv[d].x, sc[d * NGROUP], c_tc[0]), ty = fma(vv[d].y, sc[d * NGROUP], c_tc[0]);
             lo[2 * d] = (uint32_t)__double2loint(tx);
             hi[2 * d] = (uint32_t)__double2hiint(tx);
             lo[2 * d + 1] = (uint32_t)__double2loint(ty);
@@ -602,8 +605,8 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
                         const double2 v = eh[2 * q + s];
-                        const double tx = fma(v.x, 70368744177664.0, TC_MAGIC);   // 2^46
-                        const double ty = fma(v.y, 70368744177664.0, TC_MAGIC);
+                        const double tx = fma(v.x, c_tc[3], c_tc[0]);   // 2^46
+                        const double ty = fma(v.y, c_tc[3], c_tc[0]);
                         lo[2 * s] = (uint32_t)__double2loint(tx);
                         hi[2 * s] = (uint32_t)__double2hiint(tx);
                         lo[2 * s + 1] = (uint32_t)__double2loint(ty);
