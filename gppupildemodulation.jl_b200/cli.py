@@ -305,10 +305,19 @@ class NightScheduler:
         done, depth = [], max(1, self.nslots // 2)
         with ThreadPoolExecutor(max_workers=3) as self.writers:
             i = 0
+            self.t_plan = self.t_finish = self.t_submit = 0.0     # where the main thread's time goes
+            t0 = time.perf_counter()
             for job in jobs:
+                t1 = time.perf_counter()
                 if i >= depth:
                     done.append(self.finish((i - depth) % self.nslots))
+                t2 = time.perf_counter()
                 self.submit(i % self.nslots, job)
+                t3 = time.perf_counter()
+                self.t_plan += t1 - t0
+                self.t_finish += t2 - t1
+                self.t_submit += t3 - t2
+                t0 = t3
                 i += 1
             for k in range(max(0, i - depth), i):
                 done.append(self.finish(k % self.nslots))
@@ -370,7 +379,10 @@ def main(argv=None) -> int:
     names = sched.run(jobs())
     if os.environ.get("GPPD_CLI_TIMING"):     # tools/night_cli.py: the night without interpreter start-up
         import json
-        print(json.dumps({"files_written": len(names), "run_seconds": time.time() - t0}), file=sys.stderr)
+        print(json.dumps({"files_written": len(names), "run_seconds": time.time() - t0,
+                          "main_thread_seconds": {"waiting_for_planned_files": sched.t_plan,
+                                                  "wait_results_and_request_write": sched.t_finish,
+                                                  "submit": sched.t_submit}}), file=sys.stderr)
     return 0
 
 

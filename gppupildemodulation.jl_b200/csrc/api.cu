@@ -85,7 +85,10 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr int NSLOTS = 8;
+#ifndef GPPD_NSLOTS
+#define GPPD_NSLOTS 8
+#endif
+constexpr int NSLOTS = GPPD_NSLOTS;
 constexpr int NPASS = GPPD_NPASS;
 constexpr int MAX_TIMER = 1 << 16;
 

@@ -212,3 +212,41 @@ def test_cli_reads_compressed_inputs(gp, ora, tmp_path):
     assert sorted(os.listdir(out)) == ["g.fits", "p.fits", "z.fits"]
     ref = open(out / "p.fits", "rb").read()
     assert open(out / "g.fits", "rb").read() == ref and open(out / "z.fits", "rb").read() == ref
+
+
+@pytest.mark.gpu
+def test_native_file_path_many_files_and_errors(gp, ora, tmp_path):
+    """The native ingest (gppd_file_*): more files than pipeline slots, of different lengths and
+    modes, give the same bytes as the Python record path (--no-native); a missing input file is
+    reported by the wait / drain, not lost on the I/O threads."""
+    import ctypes as C
+    from gppd_b200 import cli, _lib
+    d, out1, out2 = tmp_path / "in", tmp_path / "native", tmp_path / "python"
+    d.mkdir()
+    from conftest import make_case
+    for k in range(19):                     # 19 files over 8 slots, ragged sizes, every third FAINT
+        faint = k % 3 == 2
+        tab = make_case(gp.synthetic, 700 + 137 * k, k=60 + k, faint=faint, ora=ora)
+        gp.synthetic.make_fits(str(d / ("f%02d.fits" % k)), tab, tab["header"])
+    for mode in ([], ["-w", "0.6", "-c", "fit"], ["-k"]):
+        for o in (out1, out2):
+            if o.exists():
+                for f in os.listdir(o):
+                    os.remove(o / f)
+        assert cli.main(mode + ["-d", str(out1)] + [str(d / f) for f in sorted(os.listdir(d))]) == 0
+        assert cli.main(mode + ["--no-native", "-d", str(out2)] + [str(d / f) for f in sorted(os.listdir(d))]) == 0
+        names = sorted(os.listdir(out1))
+        assert len(names) == 19 and names == sorted(os.listdir(out2))
+        for f in names:
+            assert open(out1 / f, "rb").read() == open(out2 / f, "rb").read(), (mode, f)
+    # error reporting of the asynchronous parts
+    L, h = _lib.lib(), gp.default_handle()
+    o = gp.api._options()
+    _lib.check(L.gppd_file_submit(h.raw, 3, os.fsencode(str(d / "missing.fits")), 2880, 100, 332, 0, 4, 59949.0,
+                                  None, None, 0, None, 0, 0.0, C.byref(o)))
+    par, chi = np.empty((32, 6)), np.empty(32)
+    rc = L.gppd_file_wait(h.raw, 3, _lib.ptr(par), _lib.ptr(chi), None, None)
+    assert rc == 6 and b"missing.fits" in L.gppd_last_error()          # GPPD_ERR_IO
+    assert L.gppd_file_drain(h.raw) == 6                                # ... and once more by the drain
+    assert L.gppd_file_drain(h.raw) == 0                                # which clears it
+    assert L.gppd_file_submit(h.raw, 99, b"x", 0, 100, 332, 0, 4, 0.0, None, None, 0, None, 0, 0.0, C.byref(o)) == 1

@@ -39,7 +39,7 @@ res = {"workload": "night directory of %d FITS files x %d rows (30 %% FAINT), bi
        "base_directory": base, "input_gb": nfiles * rows * 332 / 1e9, "generation_seconds": tgen}
 env = dict(os.environ, GPPD_CLI_TIMING="1")
 for label, extra in (("native", []), ("python_records", ["--no-native"])):
-    runs, inner = [], []
+    runs, inner, detail = [], [], None
     for _ in range(3):                      # page cache / first-touch effects make single runs noisy
         shutil.rmtree(out, ignore_errors=True)
         t0 = time.time()
@@ -49,13 +49,14 @@ for label, extra in (("native", []), ("python_records", ["--no-native"])):
         for line in r.stderr.splitlines():
             if line.startswith("{") and "run_seconds" in line:
                 inner.append(json.loads(line)["run_seconds"])
+                detail = json.loads(line).get("main_thread_seconds")
         if r.returncode:
             print(r.stderr[-2000:], file=sys.stderr)
     nout = len(os.listdir(out)) if os.path.isdir(out) else 0
     dt, di = min(runs), (min(inner) if inner else None)
     res[label] = {"files_written": nout, "returncode": r.returncode, "command_seconds": dt,
                   "command_seconds_of_each_run": runs, "night_seconds_inside_the_process": di,
-                  "files_per_s": nout / dt, "diode_samples_per_s_command": nout * rows * 32 / dt,
+                  "main_thread_seconds_last_run": detail, "files_per_s": nout / dt, "diode_samples_per_s_command": nout * rows * 32 / dt,
                   "diode_samples_per_s_night": (nout * rows * 32 / di) if di else None}
 res["note"] = ("command = wall clock of the whole command including interpreter start-up, library load and "
                "CUDA context creation; night = first file submitted to last file written, inside the process. "
