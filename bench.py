@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--config", default="night", choices=["night", "stress", "sweep"])
     ap.add_argument("--stress-rows", type=int, default=100_000_000)
     ap.add_argument("--sweep-max", type=float, default=1e7, help="largest F of the sweep (1e8: in chunks of 1e6)")
+    ap.add_argument("--fp32", action="store_true",
+                    help="night only: the OPTIONAL reduced-precision harmonic sums (GPPD_FP32); a separate "
+                         "measurement, never the headline (which is FP64)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -285,7 +288,7 @@ def main():
     chi2 = torch.empty((F, NW * 32), dtype=torch.float64, device=dev)
     info = torch.zeros((F, NW * 32, 4), dtype=torch.int32, device=dev)
     offsets = torch.tensor(gp.synthetic.stefan_centres().view(np.float64), device=dev)
-    opt = gp.api._options()
+    opt = gp.api._options(fp32=args.fp32)
     torch.cuda.synchronize()
 
     def p(tensor):
@@ -556,7 +559,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "diode-samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if not args.fp32 else "f64 fit and demodulation on float32-class harmonic sums (GPPD_FP32, optional)",
         "data": "synthetic",
         "config": night_config(F, N),
         "run_details": {"e2e_slots": S, "window_rows": W or None, "rank_pinned_to_gpu_numa_node": numa_pinned},

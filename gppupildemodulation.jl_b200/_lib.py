@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("GPPD_LIBRARY") or os.path.join(_HERE, "libgppd.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0
-ONLYHIGH, FITOFFSETS, NO_RECENTER, KEEPRAW, BIG_ENDIAN, CENTER_EMPIRICAL = 1, 2, 4, 8, 16, 32
+ONLYHIGH, FITOFFSETS, NO_RECENTER, KEEPRAW, BIG_ENDIAN, CENTER_EMPIRICAL, FP32 = 1, 2, 4, 8, 16, 32, 64
 METHOD_AUTO, METHOD_DIRECT, METHOD_HARMONIC = 0, 1, 2
 INFO_STRIDE = 4
 TRACE_MAX = 160

@@ -133,12 +133,12 @@ def buildstates(faintstates: FaintStates, timestamp, lag: int = 0, preswitchdela
 
 
 def _options(onlyhigh=False, fitoffsets=False, recenter=True, keepraw=False, init="auto",
-             method="auto", maxfun=0, empirical=False, groups=0) -> Options:
+             method="auto", maxfun=0, empirical=False, groups=0, fp32=False) -> Options:
     o = Options()
     o.group_mask = int(groups) & 0xff
     o.flags = ((_lib.ONLYHIGH if onlyhigh else 0) | (_lib.FITOFFSETS if fitoffsets else 0) |
                (0 if recenter else _lib.NO_RECENTER) | (_lib.KEEPRAW if keepraw else 0) |
-               (_lib.CENTER_EMPIRICAL if empirical else 0))
+               (_lib.CENTER_EMPIRICAL if empirical else 0) | (_lib.FP32 if fp32 else 0))
     o.method = {"auto": _lib.METHOD_AUTO, "direct": _lib.METHOD_DIRECT,
                 "harmonic": _lib.METHOD_HARMONIC}[method]
     o.maxfun = int(maxfun)
@@ -229,12 +229,13 @@ def table_windows(time_us, mjd, window):
 
 def process_table(time_us, volt, mjd, offsets=None, faintparam: FaintStates | None = None,
                   window=None, keepraw=False, onlyhigh=False, method="auto", maxfun=0,
-                  handle=None, centres_out=None):
+                  handle=None, centres_out=None, fp32=False):
     """Array-level fast path (C ABI ``gppd_process_table_f32``): returns
     (volt_out float32 (N, 80|144), params (nwin*32, 6), chi2, info, state|None).
     ``offsets``: (40,) complex128 centres, ``None`` (fit the centres) or ``True``
     (empirical circle centres, fitted on the device; ``centres_out``, a (40,)
-    complex128 array, then receives them)."""
+    complex128 array, then receives them).  ``fp32=True`` (GPPD_FP32): the optional
+    reduced-precision harmonic sums; parameters within 1e-5 of the FP64 path."""
     h = handle or _lib.default_handle()
     tu = np.ascontiguousarray(time_us, dtype=np.int32)
     v = np.ascontiguousarray(volt, dtype=np.float32)
@@ -245,7 +246,7 @@ def process_table(time_us, volt, mjd, offsets=None, faintparam: FaintStates | No
     off = None if (offsets is None or empirical) else np.ascontiguousarray(offsets, dtype=np.complex128)
     _, nwin = table_windows(tu, mjd, window)
     o = _options(onlyhigh=onlyhigh, keepraw=keepraw, method=method, maxfun=maxfun,
-                 empirical=empirical)
+                 empirical=empirical, fp32=fp32)
     vout = np.empty((n, 144 if keepraw else 80), dtype=np.float32)
     params = np.empty((nwin * 32, 6))
     chi2 = np.empty(nwin * 32)

@@ -493,7 +493,9 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
     const int nfits = njobs * NDIODE;
     const long long tot = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
     if (tensor) {
-        launch_harmonics_tc(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
+        // GPPD_FP32 (bit 6): the float32-class form of the same sums
+        if (flags & 64u) launch_harmonics_tc32(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
+        else launch_harmonics_tc(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
         launch_harm_reduce(L, d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, tot, d_htab);
         return;
     }

@@ -53,6 +53,8 @@ void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo 
                       bool tensor);
 void tc_profile_read(unsigned long long *out16, int reset);   // TC_PROFILE experiment builds
 int harm_tc_min_rows();   // shortest job the tensor kernel is used for (1; GPPD_HARMONICS=dmma: never)
+void launch_harmonics_tc32(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
+                           unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY);
 void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                          unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY);
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GPPD_VERSION 121 /* 0.1.21: + gppd_file_* (native ingest); 0.1.20: gppd_options.group_mask, gppd_demodulate_f64_dev (0.1.10: gppd_submit_fits_rows,
+#define GPPD_VERSION 122 /* 0.1.22: + GPPD_FP32; 0.1.21: + gppd_file_* (native ingest); 0.1.20: gppd_options.group_mask, gppd_demodulate_f64_dev (0.1.10: gppd_submit_fits_rows,
                             gppd_centres, gppd_set_split_chains, gppd_debug_harmonics, GPPD_CENTER_EMPIRICAL) */
 
 /* ---- status codes ------------------------------------------------------ */
@@ -56,6 +56,14 @@ extern "C" {
                                points only; their `offsets` argument is then ignored and
                                GPPD_FITOFFSETS is off.  (The reference itself throws on
                                this path: its `Circle` type is undefined.) */
+
+#define GPPD_FP32 64u /* OPTIONAL reduced precision, off by default: the harmonic sums of the fit are
+                         formed from float32 stream values and harmonics rounded to 23-bit fixed
+                         point (harm_tc32_kernels.cu) instead of 48-bit.  Times, phases, the
+                         optimiser and the demodulation stay FP64; fitted parameters agree with the
+                         FP64 path to ~1e-6 (bound tested: 1e-5, BASELINE north_star "optional FP32
+                         path").  Applies where the tensor-core harmonic kernel does (dense
+                         METROLOGY-table entry points, harmonic evaluator); ignored elsewhere. */
 
 /* which evaluator computes chi2(b, phi) inside the fit */
 #define GPPD_METHOD_AUTO 0     /* harmonic when its validity conditions hold, else direct */

@@ -29,7 +29,7 @@ def test_host_helpers(gp, ora):
     L = gp._lib.lib()
     import re
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gppd.h")).read()
-    assert L.gppd_version() == int(re.search(r"#define GPPD_VERSION (\d+)", hdr).group(1)) == 121
+    assert L.gppd_version() == int(re.search(r"#define GPPD_VERSION (\d+)", hdr).group(1)) == 122
     for side in (0, 16):
         for tel in range(1, 5):
             for dio in range(1, 6):
