@@ -31,10 +31,22 @@ namespace gppd {
 
 constexpr int T3_SEG_ROWS = 6144;             // = TC_SEG_ROWS: the partial buffers are shared
 constexpr int T3_KB = 32;                     // rows per K-block = K of one int8 MMA
-constexpr int T3_RS = 8;                      // raw ring stages
-constexpr int T3_OS = 4;                      // operand ring stages
-constexpr int T3_VSETS = 2;
-constexpr int T3_VW = 8 * T3_VSETS, T3_EW = 3;
+#ifndef T3_RS_N
+#define T3_RS_N 8
+#endif
+#ifndef T3_OS_N
+#define T3_OS_N 4
+#endif
+#ifndef T3_EW_N
+#define T3_EW_N 3
+#endif
+#ifndef T3_VSETS_N
+#define T3_VSETS_N 2
+#endif
+constexpr int T3_RS = T3_RS_N;                // raw ring stages
+constexpr int T3_OS = T3_OS_N;                // operand ring stages
+constexpr int T3_VSETS = T3_VSETS_N;
+constexpr int T3_VW = 8 * T3_VSETS, T3_EW = T3_EW_N;
 constexpr int T3_MMA_WARP = T3_VW + T3_EW;
 constexpr int T3_WARPS = T3_MMA_WARP + 1;
 constexpr int T3_THREADS = T3_WARPS * 32;
@@ -187,7 +199,11 @@ __device__ __forceinline__ void t3_v_producer(T3Shared &S, unsigned char *raw_ri
         float2 vv[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) vv[d] = make_float2(0.0f, 0.0f);
+#ifdef T3_SKIP_V
+        const bool valid = false;
+#else
         const bool valid = i < nseg && (!FAINT || row_valid(st, flags));
+#endif
         if (valid) {
             float2 dd[4];
 #pragma unroll
@@ -429,8 +445,12 @@ k_harm_tc32(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, c
             if (lane == 0) tc_arrive(b_raw_empty + 8 * rs);
             tc_wait(b_op_empty + 8 * os, ((kb / T3_OS) & 1) ^ 1);
             unsigned char *et = op_ring + os * T3_OP_BYTES + V3_TILE + (lane >> 3) * E3_LBO + (lane & 7) * 16;
+#ifdef T3_SKIP_E
+            for (int a = 0; a < 0; ++a) {
+#else
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
+#endif
                 // harmonics 8 a + 1 .. 8 a + 8: 16 values = one 16-byte atom row per digit
                 uint32_t dg[4][T3_ND];
 #pragma unroll

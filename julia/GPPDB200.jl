@@ -34,6 +34,7 @@ const GPPD_FITOFFSETS  = UInt32(2)
 const GPPD_NO_RECENTER = UInt32(4)
 const GPPD_KEEPRAW     = UInt32(8)
 const GPPD_CENTER_EMPIRICAL = UInt32(32)
+const GPPD_FP32        = UInt32(64)   # optional reduced-precision harmonic sums (off by default)
 
 # struct gppd_options (include/gppd.h)
 struct Options
@@ -146,10 +147,11 @@ function processrows!(rows_out::Vector{UInt8}, rows::Vector{UInt8}, row_bytes::I
                       time_off::Integer, volt_off::Integer, mjd::Real;
                       offsets::Union{Nothing,Bool,Vector{ComplexF64}} = nothing,
                       faintparam::Union{Nothing,FaintStates} = nothing,
-                      window::Real = 0.0, keepraw::Bool = false, onlyhigh::Bool = false, slot::Integer = 0)
+                      window::Real = 0.0, keepraw::Bool = false, onlyhigh::Bool = false, slot::Integer = 0,
+                      fp32::Bool = false)
     n = length(rows) ÷ row_bytes
     flags = (onlyhigh ? GPPD_ONLYHIGH : UInt32(0)) | (keepraw ? GPPD_KEEPRAW : UInt32(0)) |
-            (offsets === true ? GPPD_CENTER_EMPIRICAL : UInt32(0))
+            (offsets === true ? GPPD_CENTER_EMPIRICAL : UInt32(0)) | (fp32 ? GPPD_FP32 : UInt32(0))
     offsets isa Bool && (offsets = nothing)
     opt = Options(flags, 0, 0, 0, (0.0, 0.0), 0.0, 0.0)
     nwrows = Ref{Int64}(0); nwin = Ref{Int64}(1)

@@ -3,7 +3,7 @@
 # (libraries next to gppupildemodulation.jl_b200/libgppd.so, built with `make BUILD=... OUT=... EXTRA=...`)
 cd "$(dirname "$0")/.."
 for lib in "$@"; do
-  GPPD_LIBRARY=$PWD/gppupildemodulation.jl_b200/$lib python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/ab_$lib.json 2> gpurun_out/ab_$lib.err || tail -3 gpurun_out/ab_$lib.err
+  GPPD_LIBRARY=$PWD/gppupildemodulation.jl_b200/$lib python bench.py $AB_FLAGS --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/ab_$lib.json 2> gpurun_out/ab_$lib.err || tail -3 gpurun_out/ab_$lib.err
   python - "$lib" <<'PY'
 import json, sys
 lib = sys.argv[1]
