@@ -372,12 +372,13 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     // the int8 tensor-core form of the harmonic sums takes dense METROLOGY tables (rows of
     // 80 floats, 16-byte aligned); the other layouts use the FP64 DMMA kernel.
     // GPPD_HARMONICS=dmma forces the DMMA kernel everywhere.
-    bool tensor = max_wrows >= harm_tc_min_rows();
+    bool dense = true;      // every table: rows of 80 floats back to back, 16-byte aligned
     for (int t = 0; t < T; ++t) {
         const TableView &v = td[t].tv;
         if (v.kind != 0 || (reinterpret_cast<unsigned long long>(v.volt) & 15ull) || v.volt_stride != 320)
-            tensor = false;
+            dense = false;
     }
+    const bool tensor = dense && max_wrows >= harm_tc_min_rows();
 
     // partial sums are taken over FIXED row segments of each job (so that a fit's
     // result does not depend on the rest of the batch); P / SP = segments of the
@@ -517,7 +518,7 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         PassScope ps(h, s, stream, GPPD_PASS_STATS);
         launch_stats(L, d_tabs, s.jobs.as<JobInfo>(), njobs, s.faintjobs.as<int>(),
                      (int)faint_jobs.size(), s.nvalid.as<int>(), fo.flags, SP, s.spart1.as<double>(),
-                     s.spart2.as<double>());
+                     s.spart2.as<double>(), dense && !getenv("GPPD_STATS_PLAIN"));
     }
     DBG(stream, "stats");
     if (direct) {

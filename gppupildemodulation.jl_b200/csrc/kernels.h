@@ -30,7 +30,7 @@ void launch_basis(const Launcher &L, const TableDesc *d_tabs, int ntables, long 
 // d_faint_jobs: the nfaint jobs (batch job indices) whose table has states
 void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                   const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
-                  double *d_part, double *d_table);
+                  double *d_part, double *d_table, bool dense);
 
 // `--center empirical` (reference compute_offsets, src/GPPupilDemodulation.jl:105-125):
 // algebraic circle fit of each of the 40 channels of every kind-0 table whose

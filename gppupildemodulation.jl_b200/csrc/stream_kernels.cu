@@ -518,6 +518,220 @@ k_stats_seg(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, c
     }
 }
 
+// The same sums for dense tables (rows of 80 floats back to back, 16-byte aligned: every table
+// that comes through the table entry points): every WARP streams its own 128 consecutive
+// rows of the segment through a private ring of cp.async.bulk stages (4 rows each, own
+// mbarriers, no block-level barrier in the loop), like k_demod.  The loads of the next three
+// stages are in flight while a stage is reduced, and no register holds data that is not
+// being used: k_stats_seg spends 128 registers on a load batch that it cannot overlap with
+// its arithmetic (ncu: long_scoreboard the top stall, 16 warps per SM); this one fits three
+// blocks = 24 warps per SM.  The states of 32 rows are read one per lane, 32 rows ahead.  Thread = (row of the stage's half, group).
+#ifndef ST_MT_N
+#define ST_MT_N 4
+#endif
+#ifndef ST_MINB
+#define ST_MINB 3
+#endif
+constexpr int ST_MT = ST_MT_N;                              // rows per stage (4 or 8)
+constexpr int ST_WROWS = STATS_SEG_ROWS / (STATS_THREADS / 32);   // 128 rows per warp
+constexpr int ST_STAGES = 4;
+constexpr int ST_STAGE_BYTES = ST_MT * 320;
+constexpr int ST_WARP_BYTES = ST_STAGES * ST_STAGE_BYTES;
+constexpr int ST_SMEM = (STATS_THREADS / 32) * ST_WARP_BYTES;
+constexpr int ST_PER32 = 32 / ST_MT;                        // stages per 32 rows (one state prefetch)
+static_assert(ST_WROWS % 32 == 0 && (ST_MT == 4 || ST_MT == 8), "the state prefetch covers 32 rows");
+
+template <bool BE>
+__global__ void __launch_bounds__(STATS_THREADS, ST_MINB)
+k_stats_seg_bulk(const TableDesc *tabs, const JobInfo *jobs, const int *faint_jobs, const int *jobcnt,
+                 unsigned flags, int P, double *part) {
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ uint64_t s_bars[STATS_THREADS / 32][ST_STAGES];
+    __shared__ double s_piv[16][NGROUP];
+    __shared__ double s_acc[STATS_THREADS / 32][NGROUP][STATS_VALS];
+    const int p = (int)(blockIdx.x % (unsigned)P);
+    const int job = faint_jobs[blockIdx.x / (unsigned)P];
+    const JobInfo ji = jobs[job];
+    const TableDesc &tb = tabs[ji.table];
+    if (!tb.state) return;
+    const long long seg0 = (long long)p * STATS_SEG_ROWS;
+    if (seg0 >= ji.nrows) return;
+    const int nseg = (int)((ji.nrows - seg0) < STATS_SEG_ROWS ? (ji.nrows - seg0) : STATS_SEG_ROWS);
+    const TableView tv = tb.tv;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rl = lane >> 3, group = lane & 7;
+
+    // this warp's rows and the first loads, before anything else
+    const int wr0 = w * ST_WROWS;
+    const int wn = nseg - wr0 < ST_WROWS ? nseg - wr0 : ST_WROWS;          // may be <= 0
+    const int nmt = wn > 0 ? (wn + ST_MT - 1) / ST_MT : 0;
+    const long long row0 = ji.row0 + seg0 + wr0;                           // table row of the warp's first row
+    unsigned char *ring = st_smem + w * ST_WARP_BYTES;
+    uint64_t *bars = s_bars[w];
+    const char *volt = reinterpret_cast<const char *>(tv.volt);
+    auto issue_load = [&](int k) {  // lane 0
+        const unsigned nr = (unsigned)((wn - k * ST_MT) < ST_MT ? (wn - k * ST_MT) : ST_MT);
+        mbar_expect_tx(&bars[k % ST_STAGES], nr * 320u);
+        bulk_g2s(ring + (k % ST_STAGES) * ST_STAGE_BYTES, volt + (row0 + (long long)k * ST_MT) * 320, nr * 320u,
+                 &bars[k % ST_STAGES]);
+    };
+    if (lane == 0) {
+        for (int st = 0; st < ST_STAGES; ++st) mbar_init(&bars[st], 1);
+        for (int k = 0; k < ST_STAGES - 1 && k < nmt; ++k) issue_load(k);
+    }
+    const int8_t *state = tb.state + row0;
+    auto load_states = [&](int r) -> int {      // the state of the warp's row r + lane, -1 if it does not count
+        if (r + lane >= wn) return -1;
+        const int st = state[r + lane];
+        return (row_valid(st, flags) && st >= 0 && st <= 3) ? st : -1;
+    };
+    // per lane (row rl of a step): nibble j = the state of row 4 j + rl of the 32 (+ 1; 0: the row does
+    // not count), bit 3 of the nibble: the 4 rows of step j share one state.  Ten shuffles per 32 rows,
+    // away from the steps' critical path (a SHFL + VOTE per step measured ~10 % of the kernel)
+    auto pack_states = [&](int v) -> unsigned {
+        const int v1 = __shfl_xor_sync(0xffffffffu, v, 1), v2 = __shfl_xor_sync(0xffffffffu, v, 2);
+        const bool eq = (v == v1) & (v == v2);           // (no short circuit around a shuffle)
+        const unsigned uni = __ballot_sync(0xffffffffu, eq);
+        unsigned pk = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int sj = __shfl_sync(0xffffffffu, v, 4 * j + rl);
+            pk |= (unsigned)((sj + 1) | ((((uni >> (4 * j)) & 0xfu) == 0xfu) ? 8 : 0)) << (4 * j);
+        }
+        return pk;
+    };
+    unsigned st_cur = pack_states(load_states(0));
+    int st_next = load_states(32);
+
+    if (threadIdx.x < 128) {   // pivots: |d| at the job's first row of each state
+        const int g = threadIdx.x >> 4, dio = (threadIdx.x >> 2) & 3, st = threadIdx.x & 3;
+        const int first = jobcnt[JOBCNT * job + 1 + st];
+        double pv = 0.0;
+        if (first != 0x7fffffff) pv = abs_fast(row_sample(tv, ji.row0 + first, g * 4 + dio));
+        s_piv[dio * 4 + st][g] = pv;
+    }
+    for (int k = threadIdx.x; k < (STATS_THREADS / 32) * NGROUP * STATS_VALS; k += STATS_THREADS)
+        (&s_acc[0][0][0])[k] = 0.0;
+    double2 off[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) off[d] = tv.offsets ? __ldg(tv.offsets + group * 4 + d) : make_double2(0.0, 0.0);
+    __syncthreads();
+
+    int cur = -1;                 // state whose sums the registers hold (warp-uniform)
+    double a1[4], a2[4], ac = 0.0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) a1[d] = a2[d] = 0.0;
+    auto flush = [&]() {
+        if (cur < 0) return;
+        double v[9] = {ac, a1[0], a1[1], a1[2], a1[3], a2[0], a2[1], a2[2], a2[3]};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+            v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+        }
+        if (lane < NGROUP) {
+            double *acc = s_acc[w][lane];
+            acc[cur] += v[0];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                acc[4 + d * 4 + cur] += v[1 + d];
+                acc[20 + d * 4 + cur] += v[5 + d];
+            }
+        }
+        ac = 0.0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) a1[d] = a2[d] = 0.0;
+    };
+
+    // conflict-free 16-byte reads of a row's 256 diode bytes: groups 0..3 take their first
+    // half first, groups 4..7 their second (8 lanes then cover all 32 banks)
+    const int hsel = group >> 2;
+    int pst = -1;                 // state whose pivots pv[] holds
+    double pv[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int k = 0; k < nmt; ++k) {
+        if (k % ST_PER32 == 0 && k > 0) {
+            st_cur = pack_states(st_next);
+            st_next = load_states((k + ST_PER32) * ST_MT);
+        }
+        const unsigned char *stage = ring + (k % ST_STAGES) * ST_STAGE_BYTES;
+        mbar_wait(&bars[k % ST_STAGES], (unsigned)(k / ST_STAGES) & 1u);
+        float4 ra[ST_MT / 4], rb[ST_MT / 4];
+#pragma unroll
+        for (int hf = 0; hf < ST_MT / 4; ++hf) {
+            const unsigned char *q = stage + (hf * 4 + rl) * 320 + 32 * group;
+            const float4 u0 = *reinterpret_cast<const float4 *>(q + 16 * hsel);
+            const float4 u1 = *reinterpret_cast<const float4 *>(q + 16 * (1 - hsel));
+            ra[hf] = hsel ? u1 : u0;
+            rb[hf] = hsel ? u0 : u1;
+        }
+        __syncwarp();            // every lane has read the stage: it can take the load of stage k + 3
+        if (lane == 0 && k + ST_STAGES - 1 < nmt) issue_load(k + ST_STAGES - 1);
+#pragma unroll
+        for (int hf = 0; hf < ST_MT / 4; ++hf) {
+            const unsigned nib = (st_cur >> (4 * ((k % ST_PER32) * (ST_MT / 4) + hf))) & 0xfu;
+            const int st = (int)(nib & 7u) - 1;
+            double x[4] = {0.0, 0.0, 0.0, 0.0};
+            if (st >= 0) {
+                if (st != pst) {                              // (states come in long runs)
+#pragma unroll
+                    for (int dio = 0; dio < 4; ++dio) pv[dio] = s_piv[dio * 4 + st][group];
+                    pst = st;
+                }
+                float v[8] = {ra[hf].x, ra[hf].y, ra[hf].z, ra[hf].w, rb[hf].x, rb[hf].y, rb[hf].z, rb[hf].w};
+                if (BE) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(bswap32(__float_as_uint(v[q])));
+                }
+                double h2[4], ab[4];
+#pragma unroll
+                for (int dio = 0; dio < 4; ++dio) {
+                    const double2 dd = make_double2((double)v[2 * dio] - off[dio].x, (double)v[2 * dio + 1] - off[dio].y);
+                    h2[dio] = fma(dd.x, dd.x, dd.y * dd.y);
+                }
+                sqrt4(h2, ab);
+#pragma unroll
+                for (int dio = 0; dio < 4; ++dio) x[dio] = ab[dio] - pv[dio];
+            }
+            if (nib & 8u) {                                   // the usual case: one state (or no valid row)
+                const int st0 = st;
+                if (st0 >= 0) {
+                    if (st0 != cur) { flush(); cur = st0; }
+                    ac += 1.0;
+#pragma unroll
+                    for (int dio = 0; dio < 4; ++dio) {
+                        a1[dio] += x[dio];
+                        a2[dio] = fma(x[dio], x[dio], a2[dio]);
+                    }
+                }
+            } else {                                          // a run boundary inside the 4 rows
+#pragma unroll 1
+                for (int s = 0; s < 4; ++s) {
+                    if (!__any_sync(0xffffffffu, st == s)) continue;
+                    if (s != cur) { flush(); cur = s; }
+                    if (st == s) {
+                        ac += 1.0;
+#pragma unroll
+                        for (int dio = 0; dio < 4; ++dio) {
+                            a1[dio] += x[dio];
+                            a2[dio] = fma(x[dio], x[dio], a2[dio]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    flush();
+    __syncthreads();
+    for (int k = threadIdx.x; k < NGROUP * STATS_VALS; k += STATS_THREADS) {
+        const int g = k / STATS_VALS, v = k - g * STATS_VALS;
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < STATS_THREADS / 32; ++j) sum += s_acc[j][g][v];
+        part[((long long)(job * NGROUP + g) * P + p) * STATS_VALS + v] = sum;
+    }
+}
+
 // add the segments of every (job, group): one thread per (jg, diode, state)
 __global__ void k_stats_final(const TableDesc *tabs, const JobInfo *jobs, const int *jobcnt, int njg,
                               int P, const double *part, double *table) {
@@ -553,11 +767,21 @@ int stats_max_segments(long long max_rows_per_job) { return stats_segments(max_r
 
 void launch_stats(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                   const int *d_faint_jobs, int nfaint, const int *d_jobcnt, unsigned flags, int P,
-                  double *d_part, double *d_table) {
+                  double *d_part, double *d_table, bool dense) {
     if (nfaint <= 0) return;
     const unsigned grid = (unsigned)((long long)nfaint * P);
-    k_stats_seg<<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt, flags, P,
-                                                     d_part);
+    if (dense) {
+        cudaFuncSetAttribute(k_stats_seg_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
+        cudaFuncSetAttribute(k_stats_seg_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
+        if (flags & 16u)
+            k_stats_seg_bulk<true><<<grid, STATS_THREADS, ST_SMEM, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt,
+                                                                               flags, P, d_part);
+        else
+            k_stats_seg_bulk<false><<<grid, STATS_THREADS, ST_SMEM, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt,
+                                                                                flags, P, d_part);
+    } else {
+        k_stats_seg<<<grid, STATS_THREADS, 0, L.stream>>>(d_tabs, d_jobs, d_faint_jobs, d_jobcnt, flags, P, d_part);
+    }
     const int njg = njobs * NGROUP;
     k_stats_final<<<(njg * 16 + 127) / 128, 128, 0, L.stream>>>(d_tabs, d_jobs, d_jobcnt, njg, P, d_part,
                                                                d_table);
