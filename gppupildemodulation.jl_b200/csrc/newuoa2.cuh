@@ -73,6 +73,12 @@ enum { NU_SUCCESS = 0, NU_ROUNDING_ERRORS = -2, NU_TOO_MANY_EVALUATIONS = -3 };
 #else
 #define NU_COLD
 #endif
+// NU_OUTLINE (experiment builds): the three hot routines out of line too, to read their sizes
+#if defined(__CUDACC__) && defined(NU_OUTLINE)
+#define NU_HOT __noinline__
+#else
+#define NU_HOT
+#endif
 
 // The three angle searches (TRSAPP, BIGLAG, BIGDEN) always probe the same 49
 // angles 2 pi i / 50: their sines and cosines are tabulated once with nu_sincos
@@ -262,7 +268,7 @@ struct Newuoa2T {
     }
 
     // ------------------------------------------------------------------
-    __host__ __device__ void trsapp(double *step) {
+    __host__ __device__ NU_HOT void trsapp(double *step) {
         const double half = 0.5, zero = 0.0;
         const double twopi = 6.283185307179586476925;
         double dd_[N + 1], g[N + 1], hd[N + 1], hs[N + 1];
@@ -394,7 +400,7 @@ struct Newuoa2T {
 
     // ------------------------------------------------------------------
     // hcol = vlag[1..NPT], gc = vlag[NPT+1..], as in Powell's call
-    __host__ __device__ void biglag(double dlt) {
+    __host__ __device__ NU_HOT void biglag(double dlt) {
         const double half = 0.5, one = 1.0, zero = 0.0;
         const double twopi = 6.283185307179586476925;
         double *hcol = vlag, *gc = vlag + NPT;
@@ -767,7 +773,7 @@ struct Newuoa2T {
     }
 
     // ------------------------------------------------------------------
-    __host__ __device__ void update() {
+    __host__ __device__ NU_HOT void update() {
         const double one = 1.0, zero = 0.0;
         int jl = 1, iflag, ja, jb;
         double temp, tempa, tempb = 0, alph, tau, tausq, denom, scala, scalb;
