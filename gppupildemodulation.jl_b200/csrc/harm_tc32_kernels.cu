@@ -212,7 +212,7 @@ __device__ __forceinline__ void t3_v_producer(T3Shared &S, unsigned char *raw_ri
                                     (__uint_as_float(w[2 * d + 1]) - off[d * NGROUP].y) - olo[d * NGROUP].y);
             const float2 fcs = make_float2((__uint_as_float(wf.x) - off[4 * NGROUP].x) - olo[4 * NGROUP].x,
                                            (__uint_as_float(wf.y) - off[4 * NGROUP].y) - olo[4 * NGROUP].y);
-            cnt += 1ull << (16 * (st & 3));
+            if (FAINT) cnt += 1ull << (16 * (st & 3));     // (bright: every row of the segment, set by the caller)
             t3_values<KIND, OFFS, true, FAINT>(st, dd, fcs, &S.stats[0][g], vv, cst);
         }
         uint32_t m[8];
@@ -479,6 +479,8 @@ k_harm_tc32(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, c
     } else {
         if (faint) t3_v_producer<KIND, OFFS, true>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, cst, cnt);
         else t3_v_producer<KIND, OFFS, false>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, cst, cnt);
+        // bright tables: all nseg rows are valid and NORMAL; one lane per group carries the count
+        if (!faint) cnt = (warp == 0 && r4 == 0) ? (unsigned long long)nseg << (16 * (ST_NORMAL & 3)) : 0ull;
     }
     __syncthreads();      // every producer is done with the raw ring: it now holds the reductions
 

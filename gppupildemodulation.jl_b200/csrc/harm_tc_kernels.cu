@@ -263,7 +263,7 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
             }
             const double2 fcs = make_double2((double)__uint_as_float(wf.x) - off[4 * NGROUP].x,
                                              (double)__uint_as_float(wf.y) - off[4 * NGROUP].y);
-            cnt += 1ull << (16 * (st & 3));
+            if (FAINT) cnt += 1ull << (16 * (st & 3));     // (bright: every row of the segment, set by the caller)
             tc_values<KIND, OFFS, true, FAINT>(st, dd, fcs, &S.stats[0][g], mu, vv, cst);
         }
         uint32_t lo[8], hi[8];
@@ -574,6 +574,8 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         TCP_T(tvl0);
         if (faint) tc_v_producer<KIND, OFFS, true>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
         else tc_v_producer<KIND, OFFS, false>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
+        // bright tables: all nseg rows are valid and NORMAL; one lane per group carries the count
+        if (!faint) cnt = (warp == 0 && r4 == 0) ? (unsigned long long)nseg << (16 * (ST_NORMAL & 3)) : 0ull;
         TCP_T(tvl1);
         if (warp == 0) TCP_ADD(9, tvl1 - tvl0);
     }

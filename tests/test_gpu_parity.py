@@ -403,6 +403,74 @@ def test_big_endian_table_bytes(gp, ora, method="auto"):
     assert np.array_equal(vout.astype(np.float32), v0) and par.tobytes() == p0.tobytes()
 
 
+def test_big_endian_faint_table_bytes(gp, ora):
+    """The same for a FAINT table: segmentation, the statistics pass (its big-endian bulk
+    kernel) and the weighted sums all read raw FITS byte order."""
+    import ctypes as C
+    n = 5003
+    tab = make_case(gp.synthetic, n, k=6, faint=True, ora=ora)
+    off = gp.synthetic.stefan_centres()
+    fs = tab["faintstates"]
+    fs_g = gp.FaintStates(fs.timer1, fs.timer2, 1.0, 2.0)
+    v0, p0, c0, _, st0 = gp.process_table(tab["time_us"], tab["volt"], tab["mjd"], offsets=off, faintparam=fs_g)
+    L, h = gp._lib.lib(), gp.default_handle()
+    tu_be = tab["time_us"].astype(">i4")
+    v_be = tab["volt"].astype(">f4")
+    o = gp.api._options()
+    o.flags |= gp._lib.BIG_ENDIAN
+    vout = np.empty((n, 80), dtype=">f4")
+    par, chi2, st = np.empty((32, 6)), np.empty(32), np.empty(n, np.int8)
+    t1, t2 = np.ascontiguousarray(fs_g.timer1), np.ascontiguousarray(fs_g.timer2)
+    gp._lib.check(L.gppd_process_table_f32(
+        h.raw, n, tu_be.ctypes.data_as(gp._lib._i32p), tab["mjd"],
+        v_be.ctypes.data_as(gp._lib._fp), off.view(np.float64).ctypes.data_as(gp._lib._dp),
+        t1.ctypes.data_as(gp._lib._dp), t1.size, t2.ctypes.data_as(gp._lib._dp), t2.size, 0.0, C.byref(o),
+        vout.ctypes.data_as(gp._lib._fp), par.ctypes.data_as(gp._lib._dp), chi2.ctypes.data_as(gp._lib._dp),
+        None, st.ctypes.data_as(gp._lib._i8p)))
+    assert np.array_equal(st, st0) and np.array_equal(st, tab["state"])
+    assert np.array_equal(vout.astype(np.float32), v0) and par.tobytes() == p0.tobytes()
+
+
+@pytest.mark.parametrize("n,wrows", [(30011, 0), (30011, 5003), (2100, 100), (9000, 1024)])
+def test_statistics_kernels_agree(gp, ora, monkeypatch, n, wrows):
+    """The statistics pass has two kernels (dense tables: warp-private bulk pipelines; other
+    layouts: plain loads).  They add the same terms in a different order: the per-state
+    (mean, weight) tables, seen through the weighted harmonic sums, agree to rounding."""
+    from gppd_b200 import _lib
+    tab = make_case(gp.synthetic, n, k=8, faint=True, ora=ora)
+    off = gp.synthetic.stefan_centres()
+    fs = tab["faintstates"]
+    fs_g = gp.FaintStates(fs.timer1, fs.timer2, 1.0, 2.0)
+    kw = {}
+    nwin = 1
+    if wrows:
+        dt = float(np.diff(ora.make_times(tab["time_us"][:2], tab["mjd"]))[0])
+        kw["window"] = wrows * dt
+        nwin = -(-n // wrows)
+    out = {}
+    for plain in ("", "1"):
+        if plain:
+            monkeypatch.setenv("GPPD_STATS_PLAIN", "1")
+        r = gp.process_table(tab["time_us"], tab["volt"], tab["mjd"], offsets=off, faintparam=fs_g, **kw)
+        H = np.empty(103 * 32 * nwin)
+        _lib.check(_lib.lib().gppd_debug_harmonics(_lib.default_handle().raw, 0, _lib.ptr(H), H.size))
+        out[plain] = (H.reshape(103, -1), r)
+    a, b = out[""][0], out["1"][0]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    scale = np.nanmax(np.abs(a), axis=0)
+    scale[~(scale > 0)] = 1.0
+    err = np.abs(np.where(ok, a - b, 0.0)) / scale
+    assert err.max() <= 1e-11, err.max()
+    assert np.array_equal(out[""][1][4], out["1"][1][4])              # STATE
+    pa, pb = out[""][1][1], out["1"][1][1]
+    fin = np.isfinite(pa[:, 4]) & np.isfinite(pb[:, 4])
+    assert np.array_equal(np.isfinite(pa[:, 4]), np.isfinite(pb[:, 4]))
+    if wrows == 0 or wrows >= 1000:      # (a 100-row window is a fifth of a modulation period: its
+        # minimum is flat and the end point of NEWUOA follows the last bits of the sums)
+        assert np.abs(pa[fin, 4:6] - pb[fin, 4:6]).max() <= 5 * FORK_HARD
+
+
 @pytest.mark.parametrize("method", METHODS)
 def test_edge_cases(gp, ora, method):
     # minimum size, NaN propagation like the reference (a state with one sample
