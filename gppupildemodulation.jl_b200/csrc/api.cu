@@ -551,7 +551,9 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
     DBG(stream, "fit_direct");
     {
         PassScope ps(h, s, stream, GPPD_PASS_DEMOD);
-        launch_demod(L, d_tabs, T, max_rows, s.results.as<FitResult>(), fo.flags);
+        bool arrays = true;
+        for (int t = 0; t < T; ++t) arrays = arrays && td[t].tv.kind == 1 && td[t].ov.kind == 1;
+        launch_demod(L, d_tabs, T, max_rows, s.results.as<FitResult>(), fo.flags, arrays);
     }
     DBG(stream, "demod");
     {

@@ -73,7 +73,7 @@ void launch_fit_direct(const Launcher &L, const TableDesc *d_tabs, const JobInfo
 
 // demodulation + repack (reference src/Modulation.jl:417-425)
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
-                  const FitResult *d_results, unsigned flags);
+                  const FitResult *d_results, unsigned flags, bool arrays);
 
 // FitResult -> params / chi2 / info in the caller's layout
 void launch_export(const Launcher &L, const ExportDesc *d_exps, int ntables, int max_fits,

@@ -803,7 +803,7 @@ __device__ __forceinline__ double2 demod_sample(const FitResult &fr, unsigned fl
         double gp = __dadd_rn(__dmul_rn(fr.b, sn), fr.alpha);
         double psi = __dadd_rn(gp, -fr.alpha);
         double sp, cp;
-        sincos(psi, &sp, &cp);
+        sincos_moderate(psi, &sp, &cp);      // < 1 ulp; falls back to sincos() beyond 1e5
         double vr = d.x, vi = d.y;
         if (flags & 2u) { vr -= fr.cre; vi -= fr.cim; }
         // (vr + j vi) * (cp - j sp)
@@ -908,34 +908,95 @@ __device__ __forceinline__ DemodK demod_constants(const FitResult *fr, bool offs
     return k;
 }
 
-// complex128, channel-major (kind 1): lanes along the rows
-__device__ void demod_arrays(const TableDesc &tbg, const FitResult *results, unsigned flags) {
+// complex128, channel-major (kind 1): lanes along the rows (coalesced 16-byte accesses), a warp
+// takes 4 x 32 rows of the block and loops over the channels.  When its rows belong to one job
+// with a uniform phase quantum (the usual case) the constants of a fit are loaded once per
+// channel and the four rows of a lane are independent chains; psi is a few radians, so the
+// < 1 ulp sincos_moderate replaces the general-purpose sincos (a third of its instructions).
+// The other cases go sample by sample through demod_sample.
+__device__ __forceinline__ void demod_arrays_body(const TableDesc &tbg, const FitResult *results, unsigned flags) {
     const TableView &tv = tbg.tv;
     const OutView &ov = tbg.ov;
     const long long n = tv.n, wrows = tbg.wrows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long blk0 = (long long)blockIdx.x * DM_BLOCK_ROWS;
     const long long blk1 = blk0 + DM_BLOCK_ROWS < n ? blk0 + DM_BLOCK_ROWS : n;
-    for (long long base = blk0 + warp * 32; base < blk1; base += DM_THREADS) {
-        const long long i = base + lane;
-        const bool live = i < blk1;
-        const long long ii = live ? i : blk1 - 1;
-        const double theta = row_theta(tv, ii);
-        const double2 sc = tbg.basis[ii];
-        const long long job = ii / wrows;
-        for (int group = 0; group < NGROUP; ++group) {
-            if (!group_on(flags, group)) continue;   // gppd_options.group_mask: columns left untouched
-#pragma unroll 1
-            for (int dio = 0; dio < 4; ++dio) {
-                const int ch = group * 4 + dio;
-                const FitResult *fr = results + ((long long)tbg.job0 + job) * NDIODE + ch;
-                const double2 o = demod_sample(*fr, flags, theta, sc, row_sample(tv, ii, ch));
-                if (live) ov.out[(long long)ch * n + i] = o;
-            }
-            const int fcch = fc_channel(group);
-            if (live) ov.out[(long long)fcch * n + i] = row_sample(tv, i, fcch);  // output = copy(data), :353
-        }
+    constexpr int NR = DM_BLOCK_ROWS / DM_THREADS;      // rows per lane
+    long long ii[NR];
+    bool live[NR];
+    double2 sc[NR];
+    const long long first = blk0 + warp * 32;
+    if (first >= blk1) return;
+    long long last = first;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const long long i = first + (long long)j * DM_THREADS + lane;
+        live[j] = i < blk1;
+        ii[j] = live[j] ? i : blk1 - 1;
+        sc[j] = tbg.basis[ii[j]];
+        const long long wl = first + (long long)j * DM_THREADS + 31;
+        if (first + (long long)j * DM_THREADS < blk1) last = wl < blk1 ? wl : blk1 - 1;
     }
+    const long long jf = first / wrows;
+    const bool onejob = jf == last / wrows;             // warp-uniform
+    const bool recenter = !(flags & 4u), offs = (flags & 2u) != 0;
+    for (int group = 0; group < NGROUP; ++group) {
+        if (!group_on(flags, group)) continue;   // gppd_options.group_mask: columns left untouched
+#pragma unroll 1
+        for (int dio = 0; dio < 4; ++dio) {
+            const int ch = group * 4 + dio;
+            const double2 *in = tv.data + (long long)ch * n;
+            double2 *out = ov.out + (long long)ch * n;
+            bool fast = false;
+            DemodK K;
+            if (onejob && recenter) {
+                K = demod_constants(results + ((long long)tbg.job0 + jf) * NDIODE + ch, offs);
+                fast = K.uniform != 0;
+            }
+            if (fast) {
+                double2 d[NR];
+#pragma unroll
+                for (int j = 0; j < NR; ++j) d[j] = __ldg(in + ii[j]);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    // the arithmetic of demod_sample (reference :417-425) with the fit's constants
+                    const double sn = fma(sc[j].x, K.cq, sc[j].y * K.sq);
+                    const double gp = __dadd_rn(__dmul_rn(K.b, sn), K.alpha);
+                    const double psi = __dadd_rn(gp, -K.alpha);
+                    double sp, cp;
+                    sincos_moderate(psi, &sp, &cp);
+                    double vr = d[j].x, vi = d[j].y;
+                    if (offs) { vr -= K.cre; vi -= K.cim; }
+                    const double2 o = make_double2(__dadd_rn(__dmul_rn(vr, cp), __dmul_rn(vi, sp)),
+                                                   __dadd_rn(__dmul_rn(vi, cp), -__dmul_rn(vr, sp)));
+                    if (live[j]) out[ii[j]] = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const FitResult *fr = results + ((long long)tbg.job0 + ii[j] / wrows) * NDIODE + ch;
+                    const double2 o = demod_sample(*fr, flags, row_theta(tv, ii[j]), sc[j], row_sample(tv, ii[j], ch));
+                    if (live[j]) out[ii[j]] = o;
+                }
+            }
+        }
+        const int fcch = fc_channel(group);
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+            if (live[j]) ov.out[(long long)fcch * n + ii[j]] = __ldg(tv.data + (long long)fcch * n + ii[j]);  // output = copy(data), :353
+    }
+}
+
+// a batch of complex128 arrays (the f64 entry points) has its own kernel and register budget;
+// k_demod keeps an out-of-line copy for a table of that kind inside a mixed batch
+__device__ __noinline__ void demod_arrays(const TableDesc &tbg, const FitResult *results, unsigned flags) {
+    demod_arrays_body(tbg, results, flags);
+}
+__global__ void __launch_bounds__(DM_THREADS, 3) k_demod_arrays(const TableDesc *tabs, const FitResult *results,
+                                                                unsigned flags) {
+    const TableDesc &tbg = tabs[blockIdx.y];
+    if ((long long)blockIdx.x * DM_BLOCK_ROWS >= tbg.tv.n) return;
+    demod_arrays_body(tbg, results, flags);
 }
 
 // BE: raw FITS byte order of the float32 tables (GPPD_BIG_ENDIAN, a batch-wide flag);
@@ -1174,10 +1235,15 @@ __global__ void __launch_bounds__(DM_THREADS, 3) k_demod(const TableDesc *tabs, 
 }
 
 void launch_demod(const Launcher &L, const TableDesc *d_tabs, int ntables, long long max_rows,
-                  const FitResult *d_results, unsigned flags) {
+                  const FitResult *d_results, unsigned flags, bool arrays) {
     // the 144-float staging buffers are only needed with keepraw (flag bit 8 = GPPD_KEEPRAW)
     const int smem = (flags & 8u) ? DM_SMEM_KEEPRAW : DM_SMEM;
     const dim3 grid((unsigned)((max_rows + DM_BLOCK_ROWS - 1) / DM_BLOCK_ROWS), ntables);
+    if (arrays) {          // every table of the batch is a set of complex128 arrays
+        k_demod_arrays<<<grid, DM_THREADS, 0, L.stream>>>(d_tabs, d_results, flags);
+        *L.counter += 1;
+        return;
+    }
     const bool be = (flags & 16u) != 0, offs = (flags & 2u) != 0;
 #define GPPD_LAUNCH_DEMOD(B, O)                                                                       \
     do {                                                                                              \
