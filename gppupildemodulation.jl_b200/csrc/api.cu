@@ -20,6 +20,8 @@
 #include <unistd.h>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap and its enums only: the encoder is fetched through the runtime
+
 #include "../../include/gppd.h"
 #include "kernels.h"
 
@@ -157,7 +159,7 @@ struct Slot {
     // batch scratch
     DevBuf state, basis, z, y, thkeys, nvalid, jobs, results;
     DevBuf spart1, spart2, partZ, partY, htab;
-    DevBuf timers, lb, events, flags, tabs, exps, faintjobs, fbq;
+    DevBuf timers, lb, events, flags, tabs, exps, faintjobs, fbq, tmaps;
     PassTimer timer;
     cudaEvent_t fork = nullptr, join = nullptr;   // aux slots: hand-over to / from the main stream
 };
@@ -249,6 +251,33 @@ void fill_options(const gppd_options *o, FitOptions &f, int &method) {
     // the group mask travels in bits 16..23 of the kernels' flag word (GROUP_MASK_SHIFT)
     const unsigned mask = (d.group_mask & 0xffu) ? (d.group_mask & 0xffu) : 0xffu;
     f.flags = (f.flags & 0xffffu) | (mask << GROUP_MASK_SHIFT);
+}
+
+// CUtensorMap of one table of complex128 arrays, data[40][n] double2 seen as [40][2 n] doubles,
+// box = 128 doubles (64 rows) x 40 channels.  cuTensorMapEncodeTiled is a driver entry point: it
+// is fetched through the runtime, so that the library does not link libcuda.
+static bool encode_array_map(CUtensorMap *out, const double2 *data, long long n) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_fn>(p);
+        else
+            cudaGetLastError();
+    });
+    if (!fn || n < 1 || 2 * (unsigned long long)n > 0x7fffffffull) return false;   // (int32 box coordinates)
+    const cuuint64_t dims[2] = {2ull * (cuuint64_t)n, 40};
+    const cuuint64_t strides[1] = {16ull * (cuuint64_t)n};        // bytes between channels
+    const cuuint32_t box[2] = {128, 40}, estr[2] = {1, 1};       // 64 rows x 40 channels (harm_tc_kernels.cu: TC_ARR_ROWS)
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double2 *>(data), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // cudaEvent pair around one pass (only when gppd_enable_timing is on)
@@ -378,7 +407,31 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         if (v.kind != 0 || (reinterpret_cast<unsigned long long>(v.volt) & 15ull) || v.volt_stride != 320)
             dense = false;
     }
-    const bool tensor = dense && max_wrows >= harm_tc_min_rows();
+    // ... and complex128 arrays (the demodulateall boundary), channel-major and 16-byte aligned
+    bool arrays16 = true;
+    for (int t = 0; t < T; ++t) {
+        const TableView &v = td[t].tv;
+        if (v.kind != 1 || (reinterpret_cast<unsigned long long>(v.data) & 15ull)) arrays16 = false;
+    }
+    // (a block of the tensor kernel serves all 8 groups: with a partial group mask of fewer than
+    // TENSOR_MIN_GROUPS groups the per-group DMMA kernel does less work)
+    const int ngroups_on = __builtin_popcount((fo.flags >> GROUP_MASK_SHIFT) & 0xffu);
+    const char *tmg = getenv("GPPD_TENSOR_MIN_GROUPS");
+    const int min_groups = tmg ? atoi(tmg) : 4;
+    int tensor = max_wrows < harm_tc_min_rows() ? 0 : (dense ? 1 : (arrays16 && ngroups_on >= min_groups ? 2 : 0));
+    if (tensor == 2) {
+        // one 2-D TMA descriptor per table: the kernel fetches 64 rows of all 40 channels with ONE
+        // request (40 separate bulk copies per 32 rows measured 1 500 cycles of the SM's TMA unit)
+        std::vector<CUtensorMap> tm((size_t)T);
+        bool ok = s.tmaps.ensure(sizeof(CUtensorMap) * (size_t)T) == GPPD_OK;
+        for (int t = 0; t < T && ok; ++t) ok = encode_array_map(&tm[t], td[t].tv.data, td[t].tv.n);
+        if (ok) {
+            CK(cudaMemcpyAsync(s.tmaps.p, tm.data(), sizeof(CUtensorMap) * (size_t)T, cudaMemcpyHostToDevice, stream));
+            for (int t = 0; t < T; ++t) td[t].tmap = s.tmaps.as<CUtensorMap>() + t;
+        } else {
+            tensor = 0;         // (no encoder in this driver: the FP64 DMMA kernel)
+        }
+    }
 
     // partial sums are taken over FIXED row segments of each job (so that a fit's
     // result does not depend on the rest of the batch); P / SP = segments of the

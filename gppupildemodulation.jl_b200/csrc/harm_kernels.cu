@@ -488,14 +488,16 @@ static void launch_harm_reduce(const Launcher &L, const JobInfo *d_jobs, const d
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab,
-                      bool tensor) {
+                      int tensor) {
     const bool offs = (flags & 2u) != 0;
     const int nfits = njobs * NDIODE;
     const long long tot = (long long)nfits * (offs ? HV_COUNT : HV_Y0R);
     if (tensor) {
         // GPPD_FP32 (bit 6): the float32-class form of the same sums
-        if (flags & 64u) launch_harmonics_tc32(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
-        else launch_harmonics_tc(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
+        if ((flags & 64u) && tensor == 1)
+            launch_harmonics_tc32(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY);
+        else
+            launch_harmonics_tc(L, d_tabs, d_jobs, njobs, flags, P, d_spart2, d_partZ, d_partY, tensor == 2);
         launch_harm_reduce(L, d_jobs, d_partZ, offs ? d_partY : nullptr, P, nfits, tot, d_htab);
         return;
     }

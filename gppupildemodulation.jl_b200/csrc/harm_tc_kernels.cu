@@ -91,7 +91,18 @@ constexpr int TC_SMEM = TC_RS * TC_RAW_BYTES + TC_OS * TC_OP_BYTES + 128;
 constexpr int TC_TMEM_COLS = 512;             // 6 blocks x 48 columns used
 constexpr int TC_EBITS = 46;                  // E = X 2^-46
 constexpr int TC_VBITS = 43;                  // sampled max |V| -> below 2^43
-static_assert(TC_SMEM <= 227 * 1024, "shared memory");
+// complex128 arrays (kind 1, the demodulateall boundary): a raw stage holds 32 rows of the 40
+// channel-major channels, [channel][row] double2, + the basis: twice the bytes of a table stage
+// and spans TWO K-blocks (64 rows): the SM's TMA unit spends ~40 cycles per box row (channel)
+// whatever its length -- 32-row boxes (512-byte rows) cost 1 600 cycles per K-block, more than
+// the arithmetic; 64-row boxes halve that.
+constexpr int TC_RS_ARR = 3;                  // stages of the array ring
+constexpr int TC_SPS_ARR = 2;                 // K-blocks per stage
+constexpr int TC_ARR_ROWS = TC_SPS_ARR * TC_KB;
+constexpr int TC_RAW_ARR_DATA = NCHAN * TC_ARR_ROWS * 16;
+constexpr int TC_RAW_ARR_BYTES = TC_RAW_ARR_DATA + TC_ARR_ROWS * 16;
+constexpr int TC_SMEM_ARR = TC_RS_ARR * TC_RAW_ARR_BYTES + TC_OS * TC_OP_BYTES + 128;
+static_assert(TC_SMEM <= 227 * 1024 && TC_SMEM_ARR + 5 * 1024 <= 227 * 1024, "shared memory");
 static_assert(TC_SEG_ROWS * 3ll * 16384 < (1ll << 31), "int32 accumulators");
 
 // 2^52 + 2^51 + 0x808080808080: ulp 1, bytes 0..5 of (v + this) are the digits + 128
@@ -206,14 +217,22 @@ struct TcShared {
     uint32_t tmem;
 };
 
-// V producer: thread = (row 4 wv + r4 of the K-block, group g), K-blocks vset, vset + 2, ...
-template <int KIND, bool OFFS, bool FAINT>
+// V producer: thread = (row of the K-block, group g), K-blocks vset, vset + 2, ...
+// Tables (rows of 80 floats): row 4 wv + lane / 8, group lane % 8 -- a quarter warp reads the
+// 256 contiguous bytes of a row.  Arrays (ARR, [channel][row] double2 stages): row
+// 8 (wv / 2) + lane % 8, group 4 (wv % 2) + lane / 8 -- a quarter warp reads 8 consecutive
+// rows of one channel.  Either way the 8-byte digit stores of a half warp are contiguous.
+template <int KIND, bool OFFS, bool FAINT, bool ARR>
 __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ring, unsigned char *op_ring,
                                               const TableDesc &tb, unsigned flags, long long rbase, int nseg,
                                               int nkb, int warp, int lane, const double2 (&mu)[4], double *cst,
                                               unsigned long long &cnt) {
-    const int r4 = lane >> 3, g = lane & 7;
-    const int vset = warp >> 3, krow = 4 * (warp & 7) + r4;
+    constexpr int RS = ARR ? TC_RS_ARR : TC_RS;
+    constexpr int SPS = ARR ? TC_SPS_ARR : 1;           // K-blocks per raw stage
+    constexpr int RAW_BYTES = ARR ? TC_RAW_ARR_BYTES : TC_RAW_BYTES;
+    const int wv = warp & 7;
+    const int g = ARR ? 4 * (wv & 1) + (lane >> 3) : lane & 7;
+    const int vset = warp >> 3, krow = ARR ? 8 * (wv >> 1) + (lane & 7) : 4 * wv + (lane >> 3);
     const uint32_t b_raw_full = smem_u32(&S.raw_full[0]), b_raw_empty = smem_u32(&S.raw_empty[0]);
     const uint32_t b_op_full = smem_u32(&S.op_full[0]), b_op_empty = smem_u32(&S.op_empty[0]);
     const int8_t *stp = FAINT ? tb.state + rbase + krow : nullptr;
@@ -223,28 +242,37 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
     const bool be = tb.tv.big_endian != 0;
     const double2 *off = &S.voff[0][g];                 // off[d * NGROUP]
     const double *sc = &S.vscale[0][g];
-    const unsigned char *rw0 = raw_ring + krow * 320 + 32 * g;
+    const unsigned char *rw0 = ARR ? raw_ring + krow * 16 : raw_ring + krow * 320 + 32 * g;
     unsigned char *vt0 = op_ring + (g >> 1) * V_SBO + (krow >> 3) * V_LBO + (krow & 7) * 16 + 8 * (g & 1);
 #pragma unroll 1
     for (int kb = vset; kb < nkb; kb += TC_VSETS) {
-        const int rs = kb % TC_RS, os = kb % TC_OS;
+        const int rs = (kb / SPS) % RS, os = kb % TC_OS;
         const int i = kb * TC_KB + krow;
         const int st = st_next;
         if (FAINT && i + TC_VSETS * TC_KB < nseg) st_next = stp[(long long)(kb + TC_VSETS) * TC_KB];
         TCP_T(tv0);
-        tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+        tc_wait(b_raw_full + 8 * rs, ((kb / SPS) / RS) & 1);
         TCP_T(tv1);
         if (warp == 0) TCP_ADD(7, tv1 - tv0);
-        const unsigned char *rw = rw0 + rs * TC_RAW_BYTES;
-        const uint4 wa = *reinterpret_cast<const uint4 *>(rw);
-        const uint4 wb = *reinterpret_cast<const uint4 *>(rw + 16);
-        uint2 wf = *reinterpret_cast<const uint2 *>(rw + 256 - 24 * g);     // row + 256 + 8 g
-        uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        if (be) {
+        const unsigned char *rw = rw0 + rs * RAW_BYTES + (kb % SPS) * (TC_KB * 16);
+        uint32_t w[8];
+        uint2 wf;
+        double2 da[5];
+        if (ARR) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
-            wf.x = bswap32(wf.x);
-            wf.y = bswap32(wf.y);
+            for (int d = 0; d < 4; ++d) da[d] = *reinterpret_cast<const double2 *>(rw + (4 * g + d) * (TC_ARR_ROWS * 16));
+            da[4] = *reinterpret_cast<const double2 *>(rw + (NDIODE + g) * (TC_ARR_ROWS * 16));
+        } else {
+            const uint4 wa = *reinterpret_cast<const uint4 *>(rw);
+            const uint4 wb = *reinterpret_cast<const uint4 *>(rw + 16);
+            wf = *reinterpret_cast<const uint2 *>(rw + 256 - 24 * g);     // row + 256 + 8 g
+            w[0] = wa.x; w[1] = wa.y; w[2] = wa.z; w[3] = wa.w; w[4] = wb.x; w[5] = wb.y; w[6] = wb.z; w[7] = wb.w;
+            if (be) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = bswap32(w[k]);
+                wf.x = bswap32(wf.x);
+                wf.y = bswap32(wf.y);
+            }
         }
         double2 vv[4];
 #pragma unroll
@@ -252,17 +280,24 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
 #ifdef TC_SKIP_V
         const bool valid = false;
 #else
-        const bool valid = i < nseg && (!FAINT || row_valid(st, flags));
+        // (arrays: gppd_options.group_mask -- a masked group's columns travel with the box but are not used)
+        const bool valid = i < nseg && (!FAINT || row_valid(st, flags)) && (!ARR || group_on(flags, g));
 #endif
         if (valid) {
-            double2 dd[4];
+            double2 dd[4], fcs;
+            if (ARR) {                  // (the arrays carry no centres: they are subtracted upstream)
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - off[d * NGROUP].x,
-                                     (double)__uint_as_float(w[2 * d + 1]) - off[d * NGROUP].y);
+                for (int d = 0; d < 4; ++d) dd[d] = da[d];
+                fcs = da[4];
+            } else {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    dd[d] = make_double2((double)__uint_as_float(w[2 * d]) - off[d * NGROUP].x,
+                                         (double)__uint_as_float(w[2 * d + 1]) - off[d * NGROUP].y);
+                }
+                fcs = make_double2((double)__uint_as_float(wf.x) - off[4 * NGROUP].x,
+                                   (double)__uint_as_float(wf.y) - off[4 * NGROUP].y);
             }
-            const double2 fcs = make_double2((double)__uint_as_float(wf.x) - off[4 * NGROUP].x,
-                                             (double)__uint_as_float(wf.y) - off[4 * NGROUP].y);
             if (FAINT) cnt += 1ull << (16 * (st & 3));     // (bright: every row of the segment, set by the caller)
             tc_values<KIND, OFFS, true, FAINT>(st, dd, fcs, &S.stats[0][g], mu, vv, cst);
         }
@@ -304,7 +339,7 @@ __device__ __forceinline__ void tc_v_producer(TcShared &S, unsigned char *raw_ri
     if (ovf & 0xffff0000u) S.ovf[g] = 1;
 }
 
-template <int KIND, bool OFFS>
+template <int KIND, bool OFFS, bool ARR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, const double *stats,
           double *partial) {
@@ -327,14 +362,18 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     const bool faint = tb.state != nullptr;
     const long long rbase = ji.row0 + seg0;           // first table row of the segment
 
+    constexpr int RS = ARR ? TC_RS_ARR : TC_RS;
+    constexpr int SPS = ARR ? TC_SPS_ARR : 1;                           // K-blocks per raw stage
+    constexpr int RAW_BYTES = ARR ? TC_RAW_ARR_BYTES : TC_RAW_BYTES;
+    constexpr int RAW_BASIS = ARR ? TC_RAW_ARR_DATA : TC_RAW_VOLT;      // where a stage's basis starts
     unsigned char *raw_ring = tc_smem;
-    unsigned char *op_ring = tc_smem + TC_RS * TC_RAW_BYTES;
+    unsigned char *op_ring = tc_smem + RS * RAW_BYTES;
 
     // ---- set-up: barriers, TMEM, tables, per-diode scales ------------------------------
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_RS; ++i) {
+        for (int i = 0; i < RS; ++i) {
             mbar_init(&S.raw_full[i], 1);
-            mbar_init(&S.raw_empty[i], 8 + 1);        // 8 V warps + 1 E warp per K-block
+            mbar_init(&S.raw_empty[i], (8 + 1) * SPS); // 8 V warps + 1 E warp per K-block
         }
         for (int i = 0; i < TC_OS; ++i) {
             mbar_init(&S.op_full[i], 8 + 1);
@@ -363,18 +402,26 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     tc_fence_after();
     const uint32_t tmem = S.tmem;
 
-    const int r4 = lane >> 3, g = lane & 7;
+    const int r4 = lane >> 3, g = lane & 7;       // (row, group) of the scale sampling and of a table's V producers
+    // group of this thread as a V producer, and whether it is the lane that reports its group's sums
+    const int gv = ARR ? 4 * (warp & 1) + (lane >> 3) : g;
+    const bool vlead = ARR ? (lane & 7) == 0 : r4 == 0;
     double2 mu[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d)
-        mu[d] = (OFFS && warp < TC_VW) ? row_sample(tv, ji.row0, g * 4 + d) : make_double2(0.0, 0.0);
+        mu[d] = (OFFS && warp < TC_VW && (!ARR || group_on(flags, gv))) ? row_sample(tv, ji.row0, gv * 4 + d)
+                                                                         : make_double2(0.0, 0.0);
 
     if (warp < 8) {
         // 128 rows spread over the segment: the largest |V| component of each diode
         double mx[4] = {0.0, 0.0, 0.0, 0.0};
         const int r = threadIdx.x >> 3;
+        double2 mus[4];                               // mu of the sampled group (= mu for tables)
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            mus[d] = (ARR && OFFS) ? (group_on(flags, g) ? row_sample(tv, ji.row0, g * 4 + d) : make_double2(0.0, 0.0)) : mu[d];
 #pragma unroll 1
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < (ARR && !group_on(flags, g) ? 0 : 4); ++it) {
             const int i = (int)(((long long)(it * 32 + r) * nseg) >> 7);
             const long long row = rbase + i;
             const int st = faint ? tb.state[row] : ST_NORMAL;
@@ -383,8 +430,8 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 #pragma unroll
             for (int d = 0; d < 4; ++d) dd[d] = row_sample(tv, row, g * 4 + d);
             const double2 fcs = row_sample(tv, row, fc_channel(g));
-            if (faint) tc_values<KIND, OFFS, false, true>(st, dd, fcs, &S.stats[0][g], mu, vv, nullptr);
-            else tc_values<KIND, OFFS, false, false>(st, dd, fcs, &S.stats[0][g], mu, vv, nullptr);
+            if (faint) tc_values<KIND, OFFS, false, true>(st, dd, fcs, &S.stats[0][g], mus, vv, nullptr);
+            else tc_values<KIND, OFFS, false, false>(st, dd, fcs, &S.stats[0][g], mus, vv, nullptr);
 #pragma unroll
             for (int d = 0; d < 4; ++d) mx[d] = fmax(mx[d], fmax(fabs(vv[d].x), fabs(vv[d].y)));
         }
@@ -394,7 +441,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
             // |d| <= mean + 8 sigma, so that such rows are inside the fixed-point range
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                const double amu = OFFS ? hypot(mu[d].x, mu[d].y) : 0.0;
+                const double amu = OFFS ? hypot(mus[d].x, mus[d].y) : 0.0;
                 for (int st = 0; st < 4; ++st) {
                     const double2 mw = S.stats[d * 4 + st][g];
                     if (!(mw.y > 0.0 && mw.y < 1.0e300 && mw.x >= 0.0 && mw.x < 1.0e300)) continue;
@@ -439,12 +486,26 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     // too: measured with cycle counters it spent 520 cycles per K-block in the two bulk
     // copies on top of 420 issuing the MMAs and was the critical path of the whole kernel.)
     const char *volt = reinterpret_cast<const char *>(tv.volt);
-    auto load = [&](int kb) {
-        const int rs = kb % TC_RS;
-        mbar_wait(&S.raw_empty[rs], ((kb / TC_RS) & 1) ^ 1);
-        const int rows = min(TC_KB, nseg - kb * TC_KB);
-        const long long row = rbase + (long long)kb * TC_KB;
-        unsigned char *dst = raw_ring + rs * TC_RAW_BYTES;
+    // (`sg` = raw stage number = K-block number for tables, pairs of K-blocks for arrays)
+    auto load = [&](int sg) {
+        const int rs = sg % RS;
+        mbar_wait(&S.raw_empty[rs], ((sg / RS) & 1) ^ 1);
+        const int rows = min(SPS * TC_KB, nseg - sg * SPS * TC_KB);
+        const long long row = rbase + (long long)sg * SPS * TC_KB;
+        unsigned char *dst = raw_ring + rs * RAW_BYTES;
+        if (ARR) {
+            // ONE 2-D tensor request for the 64 rows of all 40 channels (the box is always whole:
+            // rows past the end of the arrays arrive as zeros) + the basis.  40 separate bulk copies
+            // per K-block kept the SM's TMA unit busy for 1 500 cycles: slower than the arithmetic.
+            if (lane == 0) {
+                mbar_expect_tx(&S.raw_full[rs], (unsigned)TC_RAW_ARR_DATA + (unsigned)rows * 16u);
+                tensor_g2s_2d(dst, tb.tmap, (int)(2 * row), 0, &S.raw_full[rs]);
+            } else if (lane == 1) {
+                bulk_g2s(dst + TC_RAW_ARR_DATA, tb.basis + row, (unsigned)rows * 16u, &S.raw_full[rs]);
+            }
+            __syncwarp();
+            return;
+        }
         // two lanes, one bulk copy each (issuing one takes a few hundred cycles); the barrier's
         // pending arrival (lane 0's expect_tx) keeps the phase open whichever copy lands first
         if (lane == 0) {
@@ -455,8 +516,9 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         }
         __syncwarp();
     };
-    constexpr int TC_LEAD = TC_RS - TC_EW;
-    static_assert(TC_LEAD >= 2, "the loads must run ahead of the producers");
+    constexpr int TC_LEAD = RS - TC_EW;
+    static_assert(ARR || TC_LEAD >= 2, "the loads must run ahead of the producers");
+    const int nstage = (nkb + SPS - 1) / SPS;
 
     if (warp == TC_MMA_WARP) {
         // ---- control warp: MMA issuer (and loader of the first TC_RS K-blocks) ------------------
@@ -468,7 +530,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         TCP_T(tc0);
         TCP_ADD(0, 1);
         TCP_ADD(1, tc0 - tk0);
-        for (int kb = 0; kb < min(TC_RS, nkb); ++kb) load(kb);
+        for (int sg = 0; sg < min(RS, nstage); ++sg) load(sg);
         for (int kb = 0; kb < nkb; ++kb) {
             const int os = kb % TC_OS;
             TCP_T(tw0);
@@ -504,15 +566,23 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 #pragma unroll 1
         TCP_T(tel0);
         for (int kb = e; kb < nkb; kb += TC_EW) {
-            const int rs = kb % TC_RS, os = kb % TC_OS;
+            const int rs = (kb / SPS) % RS, os = kb % TC_OS;
             TCP_T(tl0);
-            if (kb + TC_LEAD >= TC_RS && kb + TC_LEAD < nkb) load(kb + TC_LEAD);
+            if (ARR) {
+                // the warp that starts the SECOND K-block of stage sg loads stage sg + 2 into the
+                // ring slot of stage sg - 1, whose K-blocks (kb - 3, kb - 2) are long done
+                const int sg = kb / SPS;
+                if ((kb % SPS) == SPS - 1 && sg + 2 >= RS && sg + 2 < nstage) load(sg + 2);
+            } else {
+                if (kb + TC_LEAD >= RS && kb + TC_LEAD < nkb) load(kb + TC_LEAD);
+            }
             TCP_T(te0);
             if (e == 0) TCP_ADD(6, te0 - tl0);
-            tc_wait(b_raw_full + 8 * rs, (kb / TC_RS) & 1);
+            tc_wait(b_raw_full + 8 * rs, ((kb / SPS) / RS) & 1);
             TCP_T(te1);
             if (e == 0) TCP_ADD(10, te1 - te0);
-            const uint4 bw = *reinterpret_cast<const uint4 *>(raw_ring + rs * TC_RAW_BYTES + TC_RAW_VOLT + lane * 16);
+            const uint4 bw = *reinterpret_cast<const uint4 *>(raw_ring + rs * RAW_BYTES + RAW_BASIS +
+                                                             ((kb % SPS) * TC_KB + lane) * 16);
             // basis = (sin theta, cos theta)
             double2 e1 = make_double2(__hiloint2double(bw.w, bw.z), __hiloint2double(bw.y, bw.x));
             if (kb * TC_KB + lane >= nseg) e1 = make_double2(1.0, 0.0);
@@ -572,10 +642,11 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
         if (e == 0) TCP_ADD(12, tel1 - tel0);
     } else {
         TCP_T(tvl0);
-        if (faint) tc_v_producer<KIND, OFFS, true>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
-        else tc_v_producer<KIND, OFFS, false>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
+        if (faint) tc_v_producer<KIND, OFFS, true, ARR>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
+        else tc_v_producer<KIND, OFFS, false, ARR>(S, raw_ring, op_ring, tb, flags, rbase, nseg, nkb, warp, lane, mu, cst, cnt);
         // bright tables: all nseg rows are valid and NORMAL; one lane per group carries the count
-        if (!faint) cnt = (warp == 0 && r4 == 0) ? (unsigned long long)nseg << (16 * (ST_NORMAL & 3)) : 0ull;
+        // (arrays: warps 0 and 1 hold groups 0..3 and 4..7)
+        if (!faint) cnt = (warp < (ARR ? 2 : 1) && vlead) ? (unsigned long long)nseg << (16 * (ST_NORMAL & 3)) : 0ull;
         TCP_T(tvl1);
         if (warp == 0) TCP_ADD(9, tvl1 - tvl0);
     }
@@ -585,17 +656,33 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
     double *s_red = reinterpret_cast<double *>(raw_ring);                          // [TC_VW][NGROUP][20]
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(s_red + TC_VW * NGROUP * 20);
     if (warp < TC_VW) {
-        // constant sums: the 4 row lanes of a group, then (below) the V warps in order
+        // constant sums: the row lanes of a group (tables: 4 lanes 8 apart; arrays: 8 adjacent
+        // lanes), then (below) the V warps in order.  An array warp holds 4 of the 8 groups: its
+        // second lane of every group writes zeros for the group of the other half.
 #pragma unroll
         for (int q = 0; q < NACC * 4; ++q) {
             double sv = cst[q];
-            sv += __shfl_xor_sync(0xffffffffu, sv, 8);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 16);
-            if (r4 == 0) s_red[(warp * NGROUP + g) * 20 + q] = sv;
+            if (ARR) {
+                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+                if ((lane & 7) == 1) s_red[(warp * NGROUP + (gv ^ 4)) * 20 + q] = 0.0;
+            } else {
+                sv += __shfl_xor_sync(0xffffffffu, sv, 8);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 16);
+            }
+            if (vlead) s_red[(warp * NGROUP + gv) * 20 + q] = sv;
         }
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
-        if (r4 == 0) s_cnt[warp * NGROUP + g] = cnt;
+        if (ARR) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+            if ((lane & 7) == 1) s_cnt[warp * NGROUP + (gv ^ 4)] = 0ull;
+        } else {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+        }
+        if (vlead) s_cnt[warp * NGROUP + gv] = cnt;
     }
     __syncthreads();
 
@@ -685,20 +772,27 @@ int harm_tc_min_rows() {
 }
 
 void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
-                         unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY) {
+                         unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY,
+                         bool arrays) {
     // (per device: set at every launch, it costs nothing next to the launch itself)
-    cudaFuncSetAttribute(k_harm_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    cudaFuncSetAttribute(k_harm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    cudaFuncSetAttribute(k_harm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     dim3 grid(njobs, P);
-    if (flags & 2u) {
-        k_harm_tc<0, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
-        k_harm_tc<1, true><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY);
-        *L.counter += 2;
-    } else {
-        k_harm_tc<0, false><<<grid, TC_THREADS, TC_SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ);
-        *L.counter += 1;
-    }
+#define GPPD_LAUNCH_TC(ARR, SMEM)                                                                              \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(k_harm_tc<0, false, ARR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);     \
+        cudaFuncSetAttribute(k_harm_tc<0, true, ARR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);      \
+        cudaFuncSetAttribute(k_harm_tc<1, true, ARR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);      \
+        if (flags & 2u) {                                                                                      \
+            k_harm_tc<0, true, ARR><<<grid, TC_THREADS, SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ); \
+            k_harm_tc<1, true, ARR><<<grid, TC_THREADS, SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partY); \
+            *L.counter += 2;                                                                                   \
+        } else {                                                                                               \
+            k_harm_tc<0, false, ARR><<<grid, TC_THREADS, SMEM, L.stream>>>(d_tabs, d_jobs, flags, P, d_spart2, d_partZ); \
+            *L.counter += 1;                                                                                   \
+        }                                                                                                      \
+    } while (0)
+    if (arrays) GPPD_LAUNCH_TC(true, TC_SMEM_ARR);
+    else GPPD_LAUNCH_TC(false, TC_SMEM);
+#undef GPPD_LAUNCH_TC
 }
 
 }  // namespace gppd

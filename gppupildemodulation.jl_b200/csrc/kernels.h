@@ -50,13 +50,14 @@ int stats_max_segments(long long max_rows_per_job);  // fixed 1024-row segments
 void launch_harmonics(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                       unsigned flags, int P, int SP, const double *d_spart1,
                       const double *d_spart2, double *d_partZ, double *d_partY, double *d_htab,
-                      bool tensor);
+                      int tensor);   // 0: FP64 DMMA kernel, 1: int8 tensor cores on tables, 2: on complex128 arrays
 void tc_profile_read(unsigned long long *out16, int reset);   // TC_PROFILE experiment builds
 int harm_tc_min_rows();   // shortest job the tensor kernel is used for (1; GPPD_HARMONICS=dmma: never)
 void launch_harmonics_tc32(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
                            unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY);
 void launch_harmonics_tc(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs, int njobs,
-                         unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY);
+                         unsigned flags, int P, const double *d_spart2, double *d_partZ, double *d_partY,
+                         bool arrays);
 
 // the fit, harmonic evaluator (one thread per fit)
 void launch_fit_harmonic(const Launcher &L, const TableDesc *d_tabs, const JobInfo *d_jobs,

@@ -37,6 +37,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// global -> shared through a 2-D tensor map (CUtensorMap in device memory): box at element
+// coordinates (c0, c1); the mbarrier receives the box's bytes (out-of-range elements are zero-filled)
+__device__ __forceinline__ void tensor_g2s_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
 // shared -> global (bulk async-group); call after the writers' __syncthreads
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),

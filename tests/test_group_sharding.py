@@ -2,7 +2,8 @@
 (iii)): the 8 (telescope, side) groups are independent (reference src/Modulation.jl:387-390),
 so rank r runs the call with gppd_options.group_mask = its groups and the host gathers the
 columns.  Here the ranks are played one after the other on one GPU: the gathered result
-must be bit-identical to the unsharded call (and the unsharded call is held to the oracle)."""
+must be bit-identical to the unsharded call made with the same harmonic kernel (and the
+unsharded call is held to the oracle)."""
 import ctypes as C
 
 import numpy as np
@@ -14,12 +15,22 @@ from conftest import make_case
 pytestmark = pytest.mark.gpu
 
 
+# The harmonic sums of complex128 arrays have two kernels: int8 tensor cores (one block serves all
+# 8 groups) and FP64 DMMA (one block per group).  A call whose mask holds fewer than 4 groups takes
+# the per-group kernel (less work); the sums of the two differ in the last bits (2e-14), so the
+# bit-for-bit statement is made with the kernel fixed (GPPD_TENSOR_MIN_GROUPS = 1: always tensor,
+# 9: never), and across kernels the fits are held to the fork envelope.
+KERNELS = {"tensor": "1", "dmma": "9"}
+
+
+@pytest.mark.parametrize("kernel", ["tensor", "dmma"])
 @pytest.mark.parametrize("faint", [False, True])
-def test_group_mask_equals_unsharded(gp, ora, faint):
+def test_group_mask_equals_unsharded(gp, ora, monkeypatch, faint, kernel):
     n = 20_000
     tab = make_case(gp.synthetic, n, k=51, faint=faint, ora=ora)
     t, z = gp.synthetic.to_complex(tab, gp.synthetic.stefan_centres())
     state = tab["state"]
+    monkeypatch.setenv("GPPD_TENSOR_MIN_GROUPS", KERNELS[kernel])
     full = gp.demodulateall(t, z, faintparam=state, raw=True, return_info=True)
     oo, op, ol, onf = ora.demodulateall(t, z, faintparam=state, nthreads=8, return_nfev=True)
     coincide, stats = fitref.compare_fits(full[1], full[2], op, ol, full[3][:, 0], onf)
@@ -38,8 +49,35 @@ def test_group_mask_equals_unsharded(gp, ora, faint):
         assert mp_.tobytes() == full[1].tobytes() and ml.tobytes() == full[2].tobytes()
 
 
-def test_group_mask_windows_and_untouched_entries(gp, ora):
+def test_group_mask_default_kernel_choice(gp, ora, monkeypatch):
+    """The default: 8 and 4 groups on the tensor cores, 2 and 1 on the per-group kernel.  Sharded
+    over 2 ranks the bits are those of the unsharded call; over 4 and 8 ranks the fits follow the
+    same trajectories or fork inside the envelope (fitref)."""
+    monkeypatch.delenv("GPPD_TENSOR_MIN_GROUPS", raising=False)
+    n = 20_000
+    tab = make_case(gp.synthetic, n, k=54, faint=True, ora=ora)
+    t, z = gp.synthetic.to_complex(tab, gp.synthetic.stefan_centres())
+    state = tab["state"]
+    full = gp.demodulateall(t, z, faintparam=state, raw=True, return_info=True)
+    sh = gp.sharding
+    for world in (2, 4, 8):
+        parts, masks = [], []
+        for r in range(world):
+            m = sh.partition_groups(r, world)
+            parts.append(gp.demodulateall(t, z, faintparam=state, raw=True, return_info=True, groups=m))
+            masks.append(m)
+        mo, mp_, ml = sh.gather_groups([p[:3] for p in parts], masks)
+        if world == 2:
+            assert mp_.tobytes() == full[1].tobytes() and np.array_equal(mo, full[0])
+        else:
+            coincide, stats = fitref.compare_fits(mp_, ml, full[1], full[2])
+            assert coincide.sum() >= fitref.MIN_COINCIDE, stats
+
+
+@pytest.mark.parametrize("kernel", ["tensor", "dmma"])
+def test_group_mask_windows_and_untouched_entries(gp, ora, monkeypatch, kernel):
     """Window mode with a mask; entries of the other groups are left untouched."""
+    monkeypatch.setenv("GPPD_TENSOR_MIN_GROUPS", KERNELS[kernel])
     n, w = 6000, 1500
     tab = make_case(gp.synthetic, n, k=52)
     t, z = gp.synthetic.to_complex(tab, gp.synthetic.stefan_centres())

@@ -157,3 +157,62 @@ def test_tensor_unusual_inputs(gp, ora, monkeypatch):
         a, b = _fit_both(gp, monkeypatch, tab, v, off)
         assert np.array_equal(np.isnan(a[1]), np.isnan(b[1]))
         assert np.array_equal(np.isfinite(a[0]), np.isfinite(b[0]))
+
+
+# ---- complex128 arrays (the demodulateall boundary): the same kernel with a loader and a V-producer
+# lane mapping of its own (csrc/harm_tc_kernels.cu, template parameter ARR)
+def _htab_arrays(gp, monkeypatch, mode, t, z, state, nvals, min_groups=None, **kw):
+    from gppd_b200 import _lib
+    monkeypatch.setenv("GPPD_HARMONICS", mode)
+    if min_groups is not None:
+        monkeypatch.setenv("GPPD_TENSOR_MIN_GROUPS", str(min_groups))
+    res = gp.demodulateall(t, z, faintparam=state, raw=True, return_info=True, **kw)
+    out = np.empty(nvals)
+    _lib.check(_lib.lib().gppd_debug_harmonics(_lib.default_handle().raw, 0, _lib.ptr(out), nvals))
+    return out.reshape(-1, 32), res
+
+
+@pytest.mark.parametrize("n,faint,fit,onlyhigh,nwindow", [
+    (700, False, False, False, 0), (6144, False, False, False, 0), (20011, True, False, False, 0),
+    (20011, True, False, True, 0), (30000, False, True, False, 0), (30000, True, True, False, 0),
+    (30011, True, False, False, 5003), (100000, False, False, False, 0)])
+def test_tensor_sums_on_arrays_equal_dmma_sums(gp, ora, monkeypatch, n, faint, fit, onlyhigh, nwindow):
+    tab = make_case(gp.synthetic, n, k=7, faint=faint, ora=ora)
+    off = None if fit else gp.synthetic.stefan_centres()
+    t, z = gp.synthetic.to_complex(tab, off)
+    nwin = -(-n // nwindow) if nwindow else 1
+    nv = (201 if fit else 103) * 32 * nwin
+    kw = dict(fitoffsets=fit, onlyhigh=onlyhigh, nwindow=nwindow)
+    a, ra = _htab_arrays(gp, monkeypatch, "dmma", t, z, tab["state"], nv, **kw)
+    b, rb = _htab_arrays(gp, monkeypatch, "tensor", t, z, tab["state"], nv, **kw)
+    assert a.tobytes() != b.tobytes()                        # the other kernel did run
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    per = 201 if fit else 103
+    a2, b2 = a.reshape(per, -1), b.reshape(per, -1)
+    err = np.nanmax(np.abs(a2 - b2) / np.nanmax(np.abs(a2), axis=0))
+    assert err <= 10 * SUM_TOL, err
+    assert (rb[3][:, 2] == ra[3][:, 2]).all()                # same evaluator per fit
+    assert np.abs(ra[1][:, 4:6] - rb[1][:, 4:6]).max() <= 2e-3
+    assert np.array_equal(ra[0][:, 32:], rb[0][:, 32:])      # FC columns: copies
+
+
+@pytest.mark.parametrize("mask", [0x0f, 0xf0, 0x35, 0x80])
+def test_tensor_on_arrays_with_a_group_mask(gp, ora, monkeypatch, mask):
+    """gppd_options.group_mask on the tensor kernel: the groups of the mask get the bits of the
+    unmasked call, the other columns are neither read (they hold NaN here) nor written."""
+    n = 20011
+    tab = make_case(gp.synthetic, n, k=9, faint=True, ora=ora)
+    off = gp.synthetic.stefan_centres()
+    t, z = gp.synthetic.to_complex(tab, off)
+    full, rf = _htab_arrays(gp, monkeypatch, "tensor", t, z, tab["state"], 103 * 32, min_groups=1)
+    zz = z.copy()
+    on = [g for g in range(8) if (mask >> g) & 1]
+    offg = [g for g in range(8) if not (mask >> g) & 1]
+    for g in offg:
+        zz[:, 4 * g:4 * g + 4] = np.nan
+        zz[:, 32 + g] = np.nan
+    part, rp = _htab_arrays(gp, monkeypatch, "tensor", t, zz, tab["state"], 103 * 32, min_groups=1, groups=mask)
+    cols = np.concatenate([np.arange(4 * g, 4 * g + 4) for g in on])
+    assert np.array_equal(full[:, cols], part[:, cols])
+    assert rf[1][cols].tobytes() == rp[1][cols].tobytes() and rf[2][cols].tobytes() == rp[2][cols].tobytes()
+    assert np.array_equal(rf[0][:, cols], rp[0][:, cols])
