@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 
 # The harmonic sums of complex128 arrays have two kernels: int8 tensor cores (one block serves all
-# 8 groups) and FP64 DMMA (one block per group).  A call whose mask holds fewer than 4 groups takes
+# 8 groups) and FP64 DMMA (one block per group).  A call whose mask holds fewer than 5 groups takes
 # the per-group kernel (less work); the sums of the two differ in the last bits (2e-14), so the
 # bit-for-bit statement is made with the kernel fixed (GPPD_TENSOR_MIN_GROUPS = 1: always tensor,
 # 9: never), and across kernels the fits are held to the fork envelope.
@@ -50,9 +50,9 @@ def test_group_mask_equals_unsharded(gp, ora, monkeypatch, faint, kernel):
 
 
 def test_group_mask_default_kernel_choice(gp, ora, monkeypatch):
-    """The default: 8 and 4 groups on the tensor cores, 2 and 1 on the per-group kernel.  Sharded
-    over 2 ranks the bits are those of the unsharded call; over 4 and 8 ranks the fits follow the
-    same trajectories or fork inside the envelope (fitref)."""
+    """The default: the unsharded call on the tensor cores, the sharded ones (4, 2, 1 groups per
+    rank) on the per-group kernel: the same bits whatever the number of ranks, and against the
+    unsharded call the same trajectories or forks inside the envelope (fitref)."""
     monkeypatch.delenv("GPPD_TENSOR_MIN_GROUPS", raising=False)
     n = 20_000
     tab = make_case(gp.synthetic, n, k=54, faint=True, ora=ora)
@@ -68,10 +68,11 @@ def test_group_mask_default_kernel_choice(gp, ora, monkeypatch):
             masks.append(m)
         mo, mp_, ml = sh.gather_groups([p[:3] for p in parts], masks)
         if world == 2:
-            assert mp_.tobytes() == full[1].tobytes() and np.array_equal(mo, full[0])
+            first = (mo, mp_, ml)
         else:
-            coincide, stats = fitref.compare_fits(mp_, ml, full[1], full[2])
-            assert coincide.sum() >= fitref.MIN_COINCIDE, stats
+            assert mp_.tobytes() == first[1].tobytes() and np.array_equal(mo, first[0])
+        coincide, stats = fitref.compare_fits(mp_, ml, full[1], full[2])
+        assert coincide.sum() >= fitref.MIN_COINCIDE, stats
 
 
 @pytest.mark.parametrize("kernel", ["tensor", "dmma"])
