@@ -399,7 +399,8 @@ int run_batch(gppd_handle h, Slot &s, cudaStream_t stream, std::vector<TableArgs
         }
     }
     // the int8 tensor-core form of the harmonic sums takes dense METROLOGY tables (rows of
-    // 80 floats, 16-byte aligned); the other layouts use the FP64 DMMA kernel.
+    // 80 floats, 16-byte aligned) and 16-byte aligned complex128 arrays; the other layouts
+    // (strided FITS records before the unpack pass never get here) use the FP64 DMMA kernel.
     // GPPD_HARMONICS=dmma forces the DMMA kernel everywhere.
     bool dense = true;      // every table: rows of 80 floats back to back, 16-byte aligned
     for (int t = 0; t < T; ++t) {

@@ -41,6 +41,11 @@
 // k_harm_ws, so k_harm_reduce and the fit are unchanged.  Integer accumulation makes the
 // result independent of any summation order.
 //
+// Two input layouts (template parameter ARR): METROLOGY tables (rows of 80 floats; a raw stage =
+// 32 rows + basis, two 1-D bulk copies) and the complex128 arrays of the demodulateall boundary
+// (channel-major [40][n]; a raw stage = 64 rows of all channels, ONE 2-D tensor-map request, and
+// V-producer lanes = (8 consecutive rows, group) instead of (row, 8 groups)).
+//
 // A value outside the sampled range (16x headroom) would wrap: it is detected from the
 // mantissa bits, the group's sums of that segment are poisoned with NaN and its fits go
 // to the direct evaluator through the fallback queue.
