@@ -29,6 +29,11 @@
 
 namespace gppd {
 
+#ifndef TC_SAMPLE_UNROLL_N
+#define TC_SAMPLE_UNROLL_N 1
+#endif
+constexpr int TC_SAMPLE_UNROLL = TC_SAMPLE_UNROLL_N;   // iterations of the scale sampling in flight
+
 constexpr int T3_SEG_ROWS = 6144;             // = TC_SEG_ROWS: the partial buffers are shared
 constexpr int T3_KB = 32;                     // rows per K-block = K of one int8 MMA
 #ifndef T3_RS_N
@@ -326,7 +331,7 @@ k_harm_tc32(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, c
         // 128 rows spread over the segment: the largest |V| component of each diode
         float mx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const int r = threadIdx.x >> 3;
-#pragma unroll 1
+#pragma unroll TC_SAMPLE_UNROLL
         for (int it = 0; it < 4; ++it) {
             const int i = (int)(((long long)(it * 32 + r) * nseg) >> 7);
             const long long row = rbase + i;

@@ -59,6 +59,11 @@
 
 namespace gppd {
 
+#ifndef TC_SAMPLE_UNROLL_N
+#define TC_SAMPLE_UNROLL_N 1
+#endif
+constexpr int TC_SAMPLE_UNROLL = TC_SAMPLE_UNROLL_N;   // iterations of the scale sampling in flight
+
 constexpr int TC_SEG_ROWS = 6144;             // = HARM_SEG_ROWS (harm_kernels.cu).  Shorter than the
 // night alone would want (12 288 rows: 1 % faster there): a single table then is 17 blocks
 // instead of 9, which is what the table-by-table end-to-end path needs (+6 % there)
@@ -425,7 +430,7 @@ k_harm_tc(const TableDesc *tabs, const JobInfo *jobs, unsigned flags, int P, con
 #pragma unroll
         for (int d = 0; d < 4; ++d)
             mus[d] = (ARR && OFFS) ? (group_on(flags, g) ? row_sample(tv, ji.row0, g * 4 + d) : make_double2(0.0, 0.0)) : mu[d];
-#pragma unroll 1
+#pragma unroll TC_SAMPLE_UNROLL
         for (int it = 0; it < (ARR && !group_on(flags, g) ? 0 : 4); ++it) {
             const int i = (int)(((long long)(it * 32 + r) * nseg) >> 7);
             const long long row = rbase + i;
