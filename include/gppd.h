@@ -88,7 +88,13 @@ typedef struct gppd_options {
                             and writes only the columns of its groups (the others' output
                             columns, params, chi2 and info entries are left untouched).
                             gppd_demodulate_f64 / gppd_demodulate_f64_dev only; the table
-                            entry points return GPPD_ERR_UNSUPPORTED for a partial mask. */
+                            entry points return GPPD_ERR_UNSUPPORTED for a partial mask.
+                            A call with 5 or more groups forms the harmonic sums on the int8
+                            tensor cores, one with fewer on the per-group FP64 kernel (less
+                            work); the two agree to 2e-14, so sharded and unsharded calls give
+                            the same bits when made with the same kernel (environment
+                            GPPD_TENSOR_MIN_GROUPS = 1 or 9) and the same fits up to NEWUOA's
+                            rounding-level ties otherwise (DESIGN.md sections 2 and 6). */
     uint32_t reserved;  /* 0 */
 } gppd_options;
 

@@ -3,6 +3,7 @@ host-only helpers work without a GPU, and GPU entry points fail loudly (no CPU
 fallback) when no B200 is visible."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -75,3 +76,24 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(base, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
                 assert "#include \"../oracle" not in txt and "oracle/" not in txt.replace("(oracle/newuoa.c)", ""), f
+
+
+def test_option_flags_agree_everywhere():
+    """The option bits of include/gppd.h, of the Python mirror and of the Julia binding."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "gppd.h")).read()
+    jl = open(os.path.join(root, "julia", "GPPDB200.jl")).read()
+    sys.path.insert(0, root)
+    from gppd_b200 import _lib
+    flags = dict(re.findall(r"#define (GPPD_[A-Z0-9_]+) (\d+)u", hdr))
+    assert {"GPPD_ONLYHIGH", "GPPD_FITOFFSETS", "GPPD_NO_RECENTER", "GPPD_KEEPRAW", "GPPD_BIG_ENDIAN",
+            "GPPD_CENTER_EMPIRICAL", "GPPD_FP32"} <= set(flags)
+    vals = sorted(int(v) for v in flags.values())
+    assert vals == [1, 2, 4, 8, 16, 32, 64]
+    for name, v in flags.items():
+        assert getattr(_lib, name[5:]) == int(v), name
+        m = re.search(r"const %s\s*=\s*UInt32\((\d+)\)" % name, jl)
+        if m:                                   # (the binding declares the flags it uses)
+            assert int(m.group(1)) == int(v), name
+    assert re.search(r"const GPPD_FP32\s*=\s*UInt32\(64\)", jl)
