@@ -179,6 +179,104 @@ function processrows!(rows_out::Vector{UInt8}, rows::Vector{UInt8}, row_bytes::I
     return (params, chi2, isnothing(faintparam) ? nothing : state)
 end
 
+# ---- native file path (include/gppd.h: gppd_file_*) -------------------------------------
+# The night loop of src/GPPupilDemodulation.jl:358-392 with the library reading and writing the
+# METROLOGY records itself (src/FitsUtils.jl:31-37 and :95-156 on its I/O threads, pinned
+# staging, asynchronous copies): Julia keeps the header parsing, the gating and the text of
+# the new header.  Ring of `numslots()` files in flight:
+#
+#     for (i, f) in enumerate(files)
+#         s = (i - 1) % nslots
+#         i > nslots && finishfile!(s, ...)          # results of the file submitted nslots ago
+#         submitfile!(s, f.path, f.data_offset, f.n, f.row_bytes, f.time_off, f.volt_off, f.mjd; ...)
+#     end
+#     ...finish the remaining slots...;  drainfiles()
+const GPPD_SEG_COPY    = Int32(0)   # `length` bytes of the input file from `offset`
+const GPPD_SEG_BYTES   = Int32(1)   # `length` bytes from memory (copied at call time)
+const GPPD_SEG_RECORDS = Int32(2)   # the output records (+ per-row extra columns), padded to 2880
+
+# struct gppd_file_segment
+struct FileSegment
+    kind::Int32
+    reserved::Int32
+    offset::Int64
+    length::Int64
+    bytes::Ptr{Cvoid}
+end
+copysegment(offset::Integer, length::Integer) = FileSegment(GPPD_SEG_COPY, 0, offset, length, C_NULL)
+recordsegment() = FileSegment(GPPD_SEG_RECORDS, 0, 0, 0, C_NULL)
+
+numslots() = Int(ccall((:gppd_num_slots, libgppd), Cint, (Ptr{Cvoid},), gethandle()))
+
+"""
+    submitfile!(slot, path, data_offset, n, row_bytes, time_off, volt_off, mjd; offsets, faintparam,
+                window, keepraw, onlyhigh)
+
+Queue one FITS file: `n` METROLOGY records of `row_bytes` bytes start at byte `data_offset` of
+`path` (TIME at `time_off`, VOLT at `volt_off` inside a record).  Returns at once.
+"""
+function submitfile!(slot::Integer, path::AbstractString, data_offset::Integer, n::Integer,
+                     row_bytes::Integer, time_off::Integer, volt_off::Integer, mjd::Real;
+                     offsets::Union{Nothing,Bool,Vector{ComplexF64}} = nothing,
+                     faintparam::Union{Nothing,FaintStates} = nothing, window::Real = 0.0,
+                     keepraw::Bool = false, onlyhigh::Bool = false)
+    flags = (onlyhigh ? GPPD_ONLYHIGH : UInt32(0)) | (keepraw ? GPPD_KEEPRAW : UInt32(0)) |
+            (offsets === true ? GPPD_CENTER_EMPIRICAL : UInt32(0))
+    offsets isa Bool && (offsets = nothing)
+    opt = Options(flags, 0, 0, 0, (0.0, 0.0), 0.0, 0.0)
+    t1 = isnothing(faintparam) ? Float64[] : Vector{Float64}(faintparam.timer1)
+    t2 = isnothing(faintparam) ? Float64[] : Vector{Float64}(faintparam.timer2)
+    GC.@preserve offsets t1 t2 begin       # (the library copies all of them before it returns)
+        gppd_assert_ok(ccall((:gppd_file_submit, libgppd), Cint,
+            (Ptr{Cvoid}, Cint, Cstring, Int64, Int64, Int64, Int64, Int64, Float64, Ptr{ComplexF64},
+             Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ref{Options}),
+            gethandle(), slot, path, data_offset, n, row_bytes, time_off, volt_off, mjd,
+            isnothing(offsets) ? C_NULL : pointer(offsets), t1, length(t1), t2, length(t2), window, opt))
+    end
+    return nothing
+end
+
+"""
+    waitfile(slot, nwin; faint) -> (params 6 x 32 nwin, chi2, state | nothing)
+
+Block until the fits of the slot's file are done (`state` needs the caller to pass the number
+of rows through `nrows` when `faint`).
+"""
+function waitfile(slot::Integer, nwin::Integer = 1; nrows::Integer = 0)
+    params = Matrix{Float64}(undef, 6, 32 * nwin)
+    chi2 = Vector{Float64}(undef, 32 * nwin)
+    state = nrows > 0 ? Vector{Int8}(undef, nrows) : Int8[]
+    gppd_assert_ok(ccall((:gppd_file_wait, libgppd), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int8}),
+        gethandle(), slot, params, chi2, C_NULL, nrows > 0 ? pointer(state) : C_NULL))
+    return (params, chi2, nrows > 0 ? state : nothing)
+end
+
+"""
+    writefile!(slot, out_path, segments; extra = nothing, extra_row_bytes = 0)
+
+Queue the output file of the slot's job: the segments in order (`copysegment`, header bytes
+as `Vector{UInt8}`, `recordsegment()`).  `extra` (the per-row columns of window mode, one block
+of `extra_row_bytes` bytes per row) must stay alive until the slot's next `submitfile!` or
+`drainfiles()` returns: the caller keeps the reference.
+"""
+function writefile!(slot::Integer, out_path::AbstractString, segments::Vector;
+                    extra::Union{Nothing,Vector{UInt8}} = nothing, extra_row_bytes::Integer = 0)
+    blobs = [s for s in segments if s isa Vector{UInt8}]
+    GC.@preserve blobs extra begin
+        segs = FileSegment[s isa Vector{UInt8} ?
+                           FileSegment(GPPD_SEG_BYTES, 0, 0, length(s), pointer(s)) : s for s in segments]
+        gppd_assert_ok(ccall((:gppd_file_write, libgppd), Cint,
+            (Ptr{Cvoid}, Cint, Cstring, Ptr{FileSegment}, Int32, Ptr{UInt8}, Int64),
+            gethandle(), slot, out_path, segs, length(segs),
+            isnothing(extra) ? C_NULL : pointer(extra), extra_row_bytes))
+    end
+    return nothing
+end
+
+"wait for every pending file of the handle; raises the first error"
+drainfiles() = gppd_assert_ok(ccall((:gppd_file_drain, libgppd), Cint, (Ptr{Cvoid},), gethandle()))
+
 "centres fitted by the last `offsets = true` call on `slot` (40 complex values)"
 function centres(slot::Integer = 0)
     c = Vector{ComplexF64}(undef, 40)
